@@ -1,0 +1,204 @@
+/* include/sllm_b200.h — the drop-in boundary: C ABI of libsllm_b200.so.
+ *
+ * B200-native (sm_100a) replacement for the transformer forward hot path of Boundwhd/SimpleLLMInference.
+ * Plain pointers and sizes only: no C++ types, no torch types, no CUDA headers needed to include this file.
+ * The reference has no FFI of its own (it is one C++ program); its hot-path boundary is the set of free
+ * functions kernel::*_cuda (include/kernel/cuda/*.cuh) that the op layers call (source/op/*.cpp) plus
+ * model::LlamaModel::forward (source/model/model.cpp:40-140). Each entry point below names the reference
+ * interface it replaces. The C++ host mirror in simplellminference_b200/host/ (mem::Tensor, op::*Layer,
+ * kernel::*_cuda, model::LlamaModel) is a thin layer over exactly these functions; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer named *_dev / every tensor argument is DEVICE memory of the current CUDA device unless the
+ *    name ends in _host; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - launchers never allocate, never synchronise, never throw; they enqueue on `stream` and return;
+ *  - return value: 0 = SLLM_OK; >0 = a cudaError_t; <0 = an SLLM_E* code; sllm_last_error() gives the text
+ *    (thread-local). The C++ shims turn non-zero into the reference's convention: LOG(...) prints
+ *    "file: .. line: .. - msg" and std::exit(EXIT_FAILURE) (include/base/base.h:6-10);
+ *  - `token` and `pos` may be read from device memory (token_dev / pos_dev non-NULL) so that the launch
+ *    sequence is CUDA-graph capturable — a deliberate deviation from the reference, which reads them on the
+ *    host (emb_kernel.cu:15, rope_kernel.cu:49). With the *_dev pointer NULL the by-value argument is used;
+ *  - activations, RoPE tables and accumulators are fp32. Matrix weights are stored as fp32, bf16 or
+ *    int8-with-group-scales (SLLM_F32 / SLLM_BF16 / SLLM_INT8); the KV cache as fp32 or bf16.
+ *  - there is NO CPU fallback anywhere behind this header.
+ */
+#ifndef SLLM_B200_H
+#define SLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLLM_OK 0
+#define SLLM_EINVAL (-1)   /* bad argument (null pointer, size, alignment, divisibility) */
+#define SLLM_ENOTSUP (-2)  /* shape or type combination not supported by the kernels */
+#define SLLM_ENOMEM (-3)   /* device allocation failed */
+#define SLLM_ESTATE (-4)   /* call sequence error (e.g. decode before weights are loaded) */
+#define SLLM_ECOMM (-5)    /* NCCL / peer-memory error */
+
+enum { SLLM_F32 = 0, SLLM_BF16 = 1, SLLM_INT8 = 2 };
+
+typedef void* sllm_stream_t;
+
+const char* sllm_last_error(void);
+int sllm_abi_version(void);
+/* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
+int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Op launchers — one per reference CUDA kernel entry point.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* replaces kernel::add_kernel_cuda (include/kernel/cuda/add_kernel.cuh:6): out[i] = a[i] + b[i] */
+int sllm_add_f32(const float* a, const float* b, float* out, int32_t n, sllm_stream_t stream);
+
+/* replaces kernel::emb_kernel_cuda (emb_kernel.cuh:6-7): out[0..d) = table[token][:], dequantised to fp32.
+ * scales: [vocab][d/group] fp32, only for SLLM_INT8. Fails with SLLM_EINVAL if the by-value token is outside
+ * [0, vocab) (the reference's guard is `token > vocab`, off by one: emb_kernel.cu:16); a device-side token
+ * outside the range is clamped into it. */
+int sllm_embedding(const int32_t* token_dev, int32_t token, const void* table, int32_t w_dtype,
+                   const float* scales, int32_t group, float* out, int32_t vocab, int32_t d,
+                   sllm_stream_t stream);
+
+/* replaces kernel::rmsnorm_kernel_cuda (rms_kernel.cuh:6-7): y = (x * 1/sqrt(mean(x^2)+eps)) * w */
+int sllm_rmsnorm_f32(const float* x, const float* w, float* y, int32_t d, float eps, sllm_stream_t stream);
+
+/* replaces kernel::matmul_kernel_cuda (matmul_kernel.cuh:6-7): y[r] = (sum_j x[j] * W[r][j]) * scale,
+ * W row-major [rows][cols]. Unlike the reference's CUDA kernel, `scale` is honoured (matmul_kernel.cu:41-55
+ * drops it; the CPU kernel applies it, matmul_kernel.cpp:26). cols must be a multiple of 16 bytes' worth of
+ * elements (4 / 8 / 16 for f32 / bf16 / int8), W 16-byte aligned, and for SLLM_INT8 cols % group == 0,
+ * group % 16 == 0, scales = [rows][cols/group] fp32. */
+int sllm_gemv(const float* x, const void* W, int32_t w_dtype, const float* scales, int32_t group, float* y,
+              int32_t rows, int32_t cols, float scale, sllm_stream_t stream);
+
+/* replaces kernel::rope_cache_cal_cuda (rope_kernel.cuh:5): sin/cos tables [max_len][head_dim/2]. Computed
+ * on the HOST with the same libm calls the reference CPU path makes (rope_kernel.cpp:8-17) and uploaded, so
+ * the tables are bit-identical to the oracle's (GPU powf/sinf/cosf differ by ulps). Synchronous. */
+int sllm_rope_tables(int32_t head_dim, int32_t max_len, float theta, float* sin_dev, float* cos_dev,
+                     sllm_stream_t stream);
+
+/* replaces kernel::rope_kernel_cuda (rope_kernel.cuh:7-8): rotate-half RoPE in place on q[0..q_dim) and
+ * k[0..k_dim). The reference rotates k over q_dim too (GQA over-run); here k_dim is
+ * explicit. k may be fp32 only (it is a row of an fp32 cache or a scratch vector). */
+int sllm_rope_f32(float* q, float* k, const int32_t* pos_dev, int32_t pos, const float* sin_tab,
+                  const float* cos_tab, int32_t q_dim, int32_t k_dim, int32_t head_dim, sllm_stream_t stream);
+
+/* replaces kernel::mha_kernel_cuda (mha_kernel.cuh:6-21): single-query attention over cache rows 0..pos of
+ * `layer`, caches laid out [layers][max_len][kv_heads*head_dim] (fp32 or bf16). Split-KV flash decoding with
+ * an in-kernel combine; the reference's `score` scratch is not needed. workspace: device scratch of at least
+ * sllm_mha_workspace_bytes(heads, head_dim, max_len) bytes, 16-byte aligned, zero-initialised once (the
+ * kernel leaves it zeroed). head_dim must be a multiple of 8 and <= 256. */
+size_t sllm_mha_workspace_bytes(int32_t heads, int32_t head_dim, int32_t max_len);
+int sllm_mha_decode(const float* q, const void* key_cache, const void* value_cache, int32_t kv_dtype,
+                    float* out, void* workspace, int32_t layer, const int32_t* pos_dev, int32_t pos,
+                    int32_t max_len, int32_t head_dim, int32_t heads, int32_t kv_heads, sllm_stream_t stream);
+
+/* replaces kernel::swiglu_kernel_cuda (swiglu_kernel.cuh:5): out = sigmoid(gate) * up  (sic: not SiLU,
+ * swiglu_kernel.cpp:12-13) */
+int sllm_swiglu_f32(const float* up, const float* gate, float* out, int32_t n, sllm_stream_t stream);
+
+/* device version of op::argmaxLayer::forward (source/op/argmax.cpp:7-17; CPU-only in the reference): index of
+ * the FIRST maximum of logits[0..n). idx_dev receives the int32 index. */
+int sllm_argmax_f32(const float* logits, int32_t n, int32_t* idx_dev, sllm_stream_t stream);
+
+/* KV-row store used by the op-by-op path when the cache is bf16: cache_row[i] = bf16(src[i]) */
+int sllm_store_kv_row(const float* src, void* cache_row, int32_t kv_dtype, int32_t n, sllm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Synthetic weights (device side of oracle/synth_weights.h: same integer hash, bit-identical values).
+ * Fills `count` elements [first, first+count) of blob segment `segment` (0 E, 1 norms, 2 wq, 3 wk, 4 wv,
+ * 5 wo, 6 up, 7 gate, 8 down) of the given shape into dst in w_dtype; int8 also writes count/group scales.
+ * row_len/row_stride_* let a tensor-parallel shard be cut out of the full matrix: the destination is
+ * [n_rows][row_len] taken from source rows of length src_row_len starting at column src_col0.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t vocab, head_dim, hidden, kv_hidden, inter, max_len, layers, heads, kv_heads;
+    float eps, theta;
+} sllm_shape;
+
+int sllm_synth_fill(const sllm_shape* shape, uint64_t seed, int32_t segment, int64_t src_first_row,
+                    int64_t n_rows, int64_t src_row_len, int64_t src_col0, int64_t row_len, void* dst,
+                    int32_t w_dtype, float* scales, int32_t group, sllm_stream_t stream);
+
+/* fp32 -> storage type conversion of an uploaded fp32 matrix [rows][cols] (the path real checkpoints take) */
+int sllm_convert_weights(const float* src_f32_dev, void* dst, int32_t w_dtype, float* scales, int32_t group,
+                         int64_t rows, int64_t cols, sllm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Engine — replaces model::LlamaModel::{init_mem, create_param_layers, forward} and the greedy loop of
+ * predict (source/model/model.cpp:40-187, 247-469) with a static device arena, a KV cache and a
+ * CUDA-graph-captured, fused decode step. One engine per GPU; tensor parallelism = one process per GPU.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    sllm_shape shape;
+    int32_t w_dtype;   /* SLLM_F32 / SLLM_BF16 / SLLM_INT8 */
+    int32_t kv_dtype;  /* SLLM_F32 / SLLM_BF16 */
+    int32_t group;     /* int8 group size along the input dimension */
+    int32_t tp_rank, tp_size;
+    int32_t flags;     /* SLLM_ENGINE_* */
+} sllm_engine_config;
+
+#define SLLM_ENGINE_UNFUSED 1u   /* run the 13-ops-per-layer sequence of the reference instead of fused kernels */
+#define SLLM_ENGINE_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
+#define SLLM_ENGINE_NO_PDL 4u    /* no programmatic dependent launch between the kernels of a step */
+#define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
+
+typedef struct sllm_engine sllm_engine;
+
+int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm_engine** out);
+void sllm_engine_destroy(sllm_engine* e);
+
+/* weights: generated on the device (synthetic), or taken from a HOST fp32 blob in the reference's order
+ * (source/model/model.cpp:340-468), converted to w_dtype and cut to this rank's tensor-parallel shard. */
+int sllm_engine_load_synthetic(sllm_engine* e, uint64_t seed);
+int sllm_engine_load_blob_f32(sllm_engine* e, const float* blob_host, int64_t n_floats);
+
+/* tensor-parallel communicator: id_bytes = 128-byte ncclUniqueId produced by sllm_comm_unique_id on rank 0
+ * and distributed by the caller (torch.distributed / MPI / a file — plumbing is the host's business). */
+int sllm_comm_unique_id(void* id_bytes_128);
+int sllm_engine_init_comm(sllm_engine* e, const void* id_bytes_128);
+/* peer-memory exchange for SLLM_ENGINE_P2P_ALLREDUCE: each rank exports a 64-byte IPC handle, the caller
+ * all-gathers them, every rank imports all of them. */
+int sllm_engine_p2p_export(sllm_engine* e, void* handle_bytes_64);
+int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles /* tp_size * 64 bytes */);
+
+/* One token, one position: the semantics of LlamaModel::forward(). token/pos by value (host), synchronous.
+ * logits_host (vocab floats, may be NULL) receives model_pred; next_token_host (may be NULL) the greedy
+ * argmax (first maximum). */
+int sllm_engine_forward(sllm_engine* e, int32_t token, int32_t pos, float* logits_host,
+                        int32_t* next_token_host);
+
+/* Greedy loop of LlamaModel::predict without tokenizer/printing: feeds prompt[0..n_prompt) one token at a
+ * time, then feeds back the argmax; writes the n_total-1 tokens that follow prompt[0] to tokens_out_host.
+ * Runs entirely on the device (token and position live in device memory, one graph replay per token);
+ * asynchronous until the final copy of the token list. */
+int sllm_engine_greedy(sllm_engine* e, const int32_t* prompt_host, int32_t n_prompt, int32_t n_total,
+                       int32_t* tokens_out_host);
+
+/* Device-resident stepping for benchmarks: set state, enqueue n steps (no host sync), read results. */
+int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos);
+int sllm_engine_enqueue_steps(sllm_engine* e, int32_t n_steps);
+int sllm_engine_read_tokens(sllm_engine* e, int32_t* tokens_out_host, int32_t n);
+
+/* Batched prefill of prompt[0..n) at positions start_pos.. : fills the KV cache, leaves the last token's
+ * logits in model_pred and its argmax as the current token (tcgen05/TMEM GEMMs; bf16 operands). */
+int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt_host, int32_t n, int32_t start_pos);
+
+/* Introspection for parity tests and the roofline: named buffers follow the reference's ModelBufferType
+ * numbering (include/model/model.h:14-34); returns a device pointer and its element count/dtype. */
+int sllm_engine_buffer(sllm_engine* e, int32_t buffer_id, void** dev_ptr, int64_t* n_elems, int32_t* dtype);
+/* algorithmic HBM bytes one decode step at position pos must move on this rank */
+int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos);
+/* number of kernel launches (graph kernel nodes) one decode step issues on this rank */
+int32_t sllm_engine_step_launches(const sllm_engine* e);
+/* total launches issued by this engine since creation */
+int64_t sllm_engine_total_launches(const sllm_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLLM_B200_H */

@@ -1,0 +1,686 @@
+// csrc/engine.cu — sllm_engine_*: device arena, KV cache, weight loading/sharding and the decode step
+// (replaces model::LlamaModel::{init_mem, create_param_layers, forward} and the loop of predict, reference
+// source/model/model.cpp:40-187, 247-469).
+//
+// Memory: ONE cudaMalloc per engine (a static arena, bump-allocated at 256-byte granularity): weights, KV
+// cache [L][S][kv_local], RoPE tables, activations, workspaces, device-resident step state. Nothing is
+// allocated or freed in the hot loop (the reference allocates per call, rms_kernel.cu:48-51).
+// Decode step: 5 fused kernels per layer + embedding + classifier/argmax, chained with programmatic dependent
+// launch and captured once into a CUDA graph; token and position live in device memory and are advanced by
+// the last kernel of the step, so n tokens = n graph replays with no host round trip.
+// Tensor parallelism: one engine per GPU/process; Q/K/V/gate/up split by output rows, O/down by input
+// columns (repacked contiguous at load), classifier by vocab rows; NCCL all-reduce after O and down.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "decode_fused.cuh"
+
+namespace sllm {
+int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_dtype, float* out, void* ws, int layer,
+                        const int32_t* pos_dev, int pos, int max_len, int hd, int heads, int kv_heads, cudaStream_t st, bool pdl);
+size_t mha_workspace_bytes(int heads, int head_dim, int max_len);
+int check_gemv_args(const void* W, int w_dtype, const float* scales, int group, int rows, int cols);
+}  // namespace sllm
+
+using namespace sllm;
+
+#define SLLM_NCCL(call)                                                                           \
+    do {                                                                                          \
+        ncclResult_t _r = (call);                                                                 \
+        if (_r != ncclSuccess) {                                                                  \
+            set_error("NCCL error %d (%s) at %s:%d in %s", (int)_r, ncclGetErrorString(_r), __FILE__, __LINE__, #call); \
+            return SLLM_ECOMM;                                                                    \
+        }                                                                                         \
+    } while (0)
+
+struct Matrix {          // a weight matrix (or stack of per-layer matrices) in storage dtype
+    void* w = nullptr;
+    float* sc = nullptr; // int8 group scales
+    int64_t rows = 0, cols = 0;   // per layer
+};
+
+struct sllm_engine {
+    sllm_engine_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool fused = true, use_graph = true, pdl = true;
+    // local (this rank's) dimensions
+    int d = 0, hd = 0, L = 0, S = 0, V = 0, H = 0, KVH = 0, I = 0;
+    int tp = 1, rank = 0;
+    int q_loc = 0, kv_loc = 0, I_loc = 0, V_loc = 0, v0 = 0, H_loc = 0, KVH_loc = 0;
+    int esz_w = 2, esz_kv = 2;
+    // arena
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    // weights
+    Matrix emb, wqkv, wo, wug, wdown;
+    float* norms = nullptr;
+    bool weights_loaded = false;
+    // caches, tables, activations (names follow ModelBufferType, model.h:14-34)
+    void *key_cache = nullptr, *value_cache = nullptr;
+    float *sin_t = nullptr, *cos_t = nullptr;
+    float *x = nullptr /*emb_output*/, *xb = nullptr /*rms_output*/, *q = nullptr /*query*/, *att = nullptr /*mha_output*/,
+          *att_out = nullptr /*att_output*/, *h = nullptr /*ffn_input*/, *up = nullptr, *gate = nullptr, *swi = nullptr,
+          *ffn_out = nullptr, *logits = nullptr /*model_pred*/, *kv_tmp = nullptr;
+    float *part_a = nullptr, *part_b = nullptr;   // TP partial sums (wo / down)
+    void* mha_ws = nullptr;
+    float* blk_val = nullptr;
+    int32_t* blk_idx = nullptr;
+    float* tp_pairs = nullptr;   // [tp][2] gathered (value, index-as-float-bits)
+    StepState* state = nullptr;
+    int32_t *prompt_dev = nullptr, *history_dev = nullptr;
+    int cls_grid = 0;
+    // pinned host staging
+    int32_t* h_state = nullptr;   // 8 ints
+    // graph
+    cudaGraphExec_t graph_exec = nullptr;
+    int step_launches = 0;
+    int64_t total_launches = 0;
+    // comm
+    ncclComm_t comm = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------- helpers ---
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t wbytes(int dtype, int64_t n) { return dtype == SLLM_F32 ? 4 * (size_t)n : dtype == SLLM_BF16 ? 2 * (size_t)n : (size_t)n; }
+
+template <class T>
+static T* carve(sllm_engine* e, size_t bytes) {
+    const size_t off = align_up(e->arena_used, 256);
+    e->arena_used = off + bytes;
+    return e->arena ? reinterpret_cast<T*>(e->arena + off) : nullptr;
+}
+
+static void carve_matrix(sllm_engine* e, Matrix& m, int64_t layers, int64_t rows, int64_t cols) {
+    m.rows = rows;
+    m.cols = cols;
+    m.w = carve<void>(e, wbytes(e->cfg.w_dtype, layers * rows * cols));
+    m.sc = (e->cfg.w_dtype == SLLM_INT8) ? carve<float>(e, sizeof(float) * (size_t)(layers * rows * cols / e->cfg.group)) : nullptr;
+}
+
+// Lays out every buffer; first pass (arena == nullptr) only measures.
+static void layout(sllm_engine* e) {
+    e->arena_used = 0;
+    const int64_t d = e->d, L = e->L, S = e->S;
+    carve_matrix(e, e->emb, 1, e->V, d);
+    e->norms = carve<float>(e, sizeof(float) * (size_t)((2 * L + 1) * d));
+    carve_matrix(e, e->wqkv, L, e->q_loc + 2 * e->kv_loc, d);
+    carve_matrix(e, e->wo, L, d, e->q_loc);
+    carve_matrix(e, e->wug, L, 2 * e->I_loc, d);
+    carve_matrix(e, e->wdown, L, d, e->I_loc);
+    e->key_cache = carve<void>(e, (size_t)e->esz_kv * L * S * e->kv_loc);
+    e->value_cache = carve<void>(e, (size_t)e->esz_kv * L * S * e->kv_loc);
+    e->sin_t = carve<float>(e, sizeof(float) * (size_t)S * (e->hd / 2));
+    e->cos_t = carve<float>(e, sizeof(float) * (size_t)S * (e->hd / 2));
+    e->x = carve<float>(e, 4 * (size_t)d);
+    e->xb = carve<float>(e, 4 * (size_t)d);
+    e->q = carve<float>(e, 4 * (size_t)std::max(e->q_loc, (int)d));
+    e->att = carve<float>(e, 4 * (size_t)std::max(e->q_loc, (int)d));
+    e->att_out = carve<float>(e, 4 * (size_t)d);
+    e->h = carve<float>(e, 4 * (size_t)d);
+    e->up = carve<float>(e, 4 * (size_t)e->I_loc);
+    e->gate = carve<float>(e, 4 * (size_t)e->I_loc);
+    e->swi = carve<float>(e, 4 * (size_t)e->I_loc);
+    e->ffn_out = carve<float>(e, 4 * (size_t)d);
+    e->logits = carve<float>(e, 4 * (size_t)e->V_loc);
+    e->kv_tmp = carve<float>(e, 4 * (size_t)2 * e->kv_loc);
+    e->part_a = carve<float>(e, 4 * (size_t)d);
+    e->part_b = carve<float>(e, 4 * (size_t)d);
+    e->mha_ws = carve<void>(e, mha_workspace_bytes(e->H_loc, e->hd, e->S));
+    e->cls_grid = gemv_grid((e->V_loc + 1) / 2, 4);
+    e->blk_val = carve<float>(e, 4 * (size_t)(e->cls_grid + 1));
+    e->blk_idx = carve<int32_t>(e, 4 * (size_t)(e->cls_grid + 1));
+    e->tp_pairs = carve<float>(e, 8 * (size_t)std::max(1, e->tp));
+    e->state = carve<StepState>(e, sizeof(StepState));
+    e->prompt_dev = carve<int32_t>(e, 4 * (size_t)S);
+    e->history_dev = carve<int32_t>(e, 4 * (size_t)S);
+}
+
+static int count_launch(sllm_engine* e) {
+    e->total_launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- fused launches --
+template <int WD, class Policy>
+static int launch_policy(sllm_engine* e, Policy& p, int units, int grid_override = 0) {
+    const size_t smem = gemv_smem_bytes(p.cols_);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SLLM_REQUIRE(smem <= (size_t)smem_optin_bytes(), SLLM_ENOTSUP, "input length %d does not fit shared memory", p.cols_);
+        SLLM_CUDA(cudaFuncSetAttribute(fused_gemv_kernel<WD, Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = grid_override ? grid_override : gemv_grid(units, 4);
+    LaunchCfg lc(dim3(grid), dim3(kGemvThreads), smem, e->stream, e->pdl);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, fused_gemv_kernel<WD, Policy>, p));
+    g_launches++;
+    count_launch(e);
+    return SLLM_OK;
+}
+
+static const void* mat_layer(const sllm_engine* e, const Matrix& m, int l) {
+    return reinterpret_cast<const uint8_t*>(m.w) + wbytes(e->cfg.w_dtype, (int64_t)l * m.rows * m.cols);
+}
+static const float* sc_layer(const sllm_engine* e, const Matrix& m, int l) {
+    return m.sc ? m.sc + (int64_t)l * m.rows * m.cols / e->cfg.group : nullptr;
+}
+static void* kv_layer(const sllm_engine* e, void* cache, int l) {
+    return reinterpret_cast<uint8_t*>(cache) + (size_t)e->esz_kv * l * e->S * e->kv_loc;
+}
+
+__global__ void embed_state_kernel(const StepState* st, const void* table, int w_dtype, const float* scales, int group,
+                                   float* out, int vocab, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    int tok = st->token;
+    tok = min(max(tok, 0), vocab - 1);
+    const int64_t base = (int64_t)tok * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+        float v;
+        if (w_dtype == SLLM_F32) v = reinterpret_cast<const float*>(table)[base + i];
+        else if (w_dtype == SLLM_BF16) v = __uint_as_float((uint32_t) reinterpret_cast<const uint16_t*>(table)[base + i] << 16);
+        else v = (float)reinterpret_cast<const int8_t*>(table)[base + i] * scales[(base + i) / group];
+        out[i] = v;
+    }
+}
+
+// TP: merge the ranks' (best value, best index) pairs and advance the step state (every rank identically)
+__global__ void tp_merge_kernel(const float* pairs, int tp, StepState* st, const int32_t* prompt, int32_t* history) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float v = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int r = 0; r < tp; ++r) {
+        const float ov = pairs[2 * r];
+        const int oi = __float_as_int(pairs[2 * r + 1]);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    ClsPolicy<SLLM_F32>::step_feedback(st, prompt, history, idx == 0x7fffffff ? 0 : idx);
+}
+__global__ void tp_pack_kernel(const float* blk_val, const int32_t* blk_idx, int slot, float* pair) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        pair[0] = blk_val[slot];
+        pair[1] = __int_as_float(blk_idx[slot]);
+    }
+}
+
+template <int WD>
+static int enqueue_fused_step(sllm_engine* e) {
+    const sllm_shape& s = e->cfg.shape;
+    const int d = e->d, L = e->L;
+    const bool tp = e->tp > 1;
+    const int32_t* pos_dev = &e->state->pos;
+    {
+        LaunchCfg lc(dim3(std::max(1, std::min((d + 255) / 256, 64))), dim3(256), 0, e->stream, e->pdl);
+        SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, embed_state_kernel, (const StepState*)e->state, (const void*)e->emb.w, e->cfg.w_dtype,
+                                     (const float*)e->emb.sc, e->cfg.group, e->x, e->V, d));
+        g_launches++;
+        count_launch(e);
+    }
+    // residual-stream bookkeeping under TP: after the all-reduce of a row-parallel GEMV the partial sum sits
+    // in part_*; the NEXT kernel's prologue adds it to the residual (and CTA 0 stores the sum).
+    for (int l = 0; l < L; ++l) {
+        QkvPolicy<WD> A{};
+        A.W_ = mat_layer(e, e->wqkv, l); A.sc_ = sc_layer(e, e->wqkv, l); A.grp_ = e->cfg.group; A.cols_ = d;
+        if (tp && l > 0) { A.x = e->h; A.add = e->part_b; A.sum_out = e->x; } else { A.x = e->x; A.add = nullptr; A.sum_out = nullptr; }
+        A.norm_w = e->norms + (int64_t)(2 * l) * d; A.eps = s.eps; A.pos_dev = pos_dev; A.sin_t = e->sin_t; A.cos_t = e->cos_t;
+        A.q_out = e->q; A.k_cache = kv_layer(e, e->key_cache, l); A.v_cache = kv_layer(e, e->value_cache, l);
+        A.kv_dtype = e->cfg.kv_dtype; A.q_dim = e->q_loc; A.kv_dim = e->kv_loc; A.hd = e->hd;
+        if (int rc = launch_policy<WD>(e, A, (e->q_loc + 2 * e->kv_loc) / 2)) return rc;
+
+        if (int rc = mha_decode_dispatch(e->q, e->key_cache, e->value_cache, e->cfg.kv_dtype, e->att, e->mha_ws, l, pos_dev, 0, e->S,
+                                         e->hd, e->H_loc, e->KVH_loc, e->stream, e->pdl)) return rc;
+        count_launch(e);
+
+        ResidualPolicy<WD> C{};
+        C.W_ = mat_layer(e, e->wo, l); C.sc_ = sc_layer(e, e->wo, l); C.grp_ = e->cfg.group; C.cols_ = e->q_loc;
+        C.x = e->att; C.nrows = d;
+        if (tp) { C.resid = nullptr; C.y = e->part_a; } else { C.resid = e->x; C.y = e->h; }
+        if (int rc = launch_policy<WD>(e, C, (d + 1) / 2)) return rc;
+        if (tp) { SLLM_NCCL(ncclAllReduce(e->part_a, e->part_a, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
+
+        GateUpPolicy<WD> D{};
+        D.W_ = mat_layer(e, e->wug, l); D.sc_ = sc_layer(e, e->wug, l); D.grp_ = e->cfg.group; D.cols_ = d;
+        // TP: the residual stream entering this layer is x (layer 0) or h+part_b, which kernel A stored in x
+        if (tp) { D.h = e->x; D.add = e->part_a; D.sum_out = e->h; } else { D.h = e->h; D.add = nullptr; D.sum_out = nullptr; }
+        D.norm_w = e->norms + (int64_t)(2 * l + 1) * d; D.eps = s.eps; D.s_out = e->swi; D.inter = e->I_loc;
+        if (int rc = launch_policy<WD>(e, D, e->I_loc)) return rc;
+
+        ResidualPolicy<WD> E{};
+        E.W_ = mat_layer(e, e->wdown, l); E.sc_ = sc_layer(e, e->wdown, l); E.grp_ = e->cfg.group; E.cols_ = e->I_loc;
+        E.x = e->swi; E.nrows = d;
+        if (tp) { E.resid = nullptr; E.y = e->part_b; } else { E.resid = e->h; E.y = e->x; }
+        if (int rc = launch_policy<WD>(e, E, (d + 1) / 2)) return rc;
+        if (tp) { SLLM_NCCL(ncclAllReduce(e->part_b, e->part_b, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
+    }
+    ClsPolicy<WD> F{};
+    F.W_ = reinterpret_cast<const uint8_t*>(e->emb.w) + wbytes(e->cfg.w_dtype, (int64_t)e->v0 * d);
+    F.sc_ = e->emb.sc ? e->emb.sc + (int64_t)e->v0 * d / e->cfg.group : nullptr;
+    F.grp_ = e->cfg.group; F.cols_ = d;
+    if (tp) { F.x = e->h; F.add = e->part_b; F.sum_out = e->x; } else { F.x = e->x; F.add = nullptr; F.sum_out = nullptr; }
+    F.norm_w = e->norms + (int64_t)(2 * L) * d; F.eps = s.eps; F.logits = e->logits; F.nrows = e->V_loc; F.row0 = e->v0;
+    F.blk_val = e->blk_val; F.blk_idx = e->blk_idx; F.st = e->state; F.prompt = e->prompt_dev; F.history = e->history_dev;
+    F.single_rank = tp ? 0 : 1;
+    if (int rc = launch_policy<WD>(e, F, (e->V_loc + 1) / 2, e->cls_grid)) return rc;
+    if (tp) {
+        tp_pack_kernel<<<1, 32, 0, e->stream>>>(e->blk_val, e->blk_idx, e->cls_grid, e->tp_pairs + 2 * e->rank);
+        count_launch(e);
+        SLLM_NCCL(ncclAllGather(e->tp_pairs + 2 * e->rank, e->tp_pairs, 2, ncclFloat, e->comm, e->stream));
+        count_launch(e);
+        tp_merge_kernel<<<1, 32, 0, e->stream>>>(e->tp_pairs, e->tp, e->state, e->prompt_dev, e->history_dev);
+        count_launch(e);
+        SLLM_LAUNCH_CHECK();
+    }
+    return SLLM_OK;
+}
+
+// ------------------------------------------------------------------------------ unfused (op-by-op) step --
+// The reference's own 13-ops-per-layer sequence (model.cpp:48-139) through the public op launchers; position
+// known on the host. Single rank only. Used for A/B against the fused path and as a second parity target.
+__global__ void set_state_kernel(StepState* st, int token, int pos, int n_prompt) {
+    st->token = token;
+    st->pos = pos;
+    st->n_prompt = n_prompt;
+}
+__global__ void feedback_kernel(StepState* st, const int32_t* idx, const int32_t* prompt, int32_t* history) {
+    ClsPolicy<SLLM_F32>::step_feedback(st, prompt, history, *idx);
+}
+
+static int enqueue_unfused_step(sllm_engine* e, int pos) {
+    SLLM_REQUIRE(e->tp == 1, SLLM_ENOTSUP, "the op-by-op path is single-GPU");
+    const sllm_shape& s = e->cfg.shape;
+    const int d = e->d, L = e->L, wd = e->cfg.w_dtype, grp = e->cfg.group;
+    sllm_stream_t st = e->stream;
+    const int64_t before = g_launches;
+#define OP(call) do { if (int rc = (call)) return rc; } while (0)
+    OP(sllm_embedding(&e->state->token, 0, e->emb.w, wd, e->emb.sc, grp, e->x, e->V, d, st));
+    for (int l = 0; l < L; ++l) {
+        const uint8_t* wqkv = reinterpret_cast<const uint8_t*>(mat_layer(e, e->wqkv, l));
+        const float* sqkv = sc_layer(e, e->wqkv, l);
+        auto row_ptr = [&](int64_t row) { return wqkv + wbytes(wd, row * d); };
+        auto row_sc = [&](int64_t row) { return sqkv ? sqkv + row * d / grp : nullptr; };
+        OP(sllm_rmsnorm_f32(e->x, e->norms + (int64_t)(2 * l) * d, e->xb, d, s.eps, st));
+        float *krow, *vrow;
+        uint8_t* kdst = reinterpret_cast<uint8_t*>(kv_layer(e, e->key_cache, l)) + (size_t)e->esz_kv * pos * e->kv_loc;
+        uint8_t* vdst = reinterpret_cast<uint8_t*>(kv_layer(e, e->value_cache, l)) + (size_t)e->esz_kv * pos * e->kv_loc;
+        if (e->cfg.kv_dtype == SLLM_F32) { krow = reinterpret_cast<float*>(kdst); vrow = reinterpret_cast<float*>(vdst); }
+        else { krow = e->kv_tmp; vrow = e->kv_tmp + e->kv_loc; }
+        OP(sllm_gemv(e->xb, row_ptr(0), wd, row_sc(0), grp, e->q, e->q_loc, d, 1.0f, st));
+        OP(sllm_gemv(e->xb, row_ptr(e->q_loc), wd, row_sc(e->q_loc), grp, krow, e->kv_loc, d, 1.0f, st));
+        OP(sllm_gemv(e->xb, row_ptr(e->q_loc + e->kv_loc), wd, row_sc(e->q_loc + e->kv_loc), grp, vrow, e->kv_loc, d, 1.0f, st));
+        OP(sllm_rope_f32(e->q, krow, nullptr, pos, e->sin_t, e->cos_t, e->q_loc, e->kv_loc, e->hd, st));
+        if (e->cfg.kv_dtype != SLLM_F32) {
+            OP(sllm_store_kv_row(krow, kdst, e->cfg.kv_dtype, e->kv_loc, st));
+            OP(sllm_store_kv_row(vrow, vdst, e->cfg.kv_dtype, e->kv_loc, st));
+        }
+        OP(sllm_mha_decode(e->q, e->key_cache, e->value_cache, e->cfg.kv_dtype, e->att, e->mha_ws, l, nullptr, pos, e->S, e->hd,
+                           e->H_loc, e->KVH_loc, st));
+        OP(sllm_gemv(e->att, mat_layer(e, e->wo, l), wd, sc_layer(e, e->wo, l), grp, e->att_out, d, e->q_loc, 1.0f, st));
+        OP(sllm_add_f32(e->x, e->att_out, e->h, d, st));
+        OP(sllm_rmsnorm_f32(e->h, e->norms + (int64_t)(2 * l + 1) * d, e->xb, d, s.eps, st));
+        const uint8_t* wug = reinterpret_cast<const uint8_t*>(mat_layer(e, e->wug, l));
+        const float* sug = sc_layer(e, e->wug, l);
+        OP(sllm_gemv(e->xb, wug, wd, sug, grp, e->up, e->I_loc, d, 1.0f, st));
+        OP(sllm_gemv(e->xb, wug + wbytes(wd, (int64_t)e->I_loc * d), wd, sug ? sug + (int64_t)e->I_loc * d / grp : nullptr, grp, e->gate,
+                     e->I_loc, d, 1.0f, st));
+        OP(sllm_swiglu_f32(e->up, e->gate, e->swi, e->I_loc, st));
+        OP(sllm_gemv(e->swi, mat_layer(e, e->wdown, l), wd, sc_layer(e, e->wdown, l), grp, e->ffn_out, d, e->I_loc, 1.0f, st));
+        OP(sllm_add_f32(e->ffn_out, e->h, e->x, d, st));
+    }
+    OP(sllm_rmsnorm_f32(e->x, e->norms + (int64_t)(2 * L) * d, e->xb, d, s.eps, st));
+    OP(sllm_gemv(e->xb, e->emb.w, wd, e->emb.sc, grp, e->logits, e->V, d, 1.0f, st));
+    OP(sllm_argmax_f32(e->logits, e->V, e->blk_idx, st));
+#undef OP
+    feedback_kernel<<<1, 1, 0, e->stream>>>(e->state, e->blk_idx, e->prompt_dev, e->history_dev);
+    g_launches++;
+    SLLM_LAUNCH_CHECK();
+    e->total_launches += g_launches - before;
+    return SLLM_OK;
+}
+
+static int enqueue_fused_dispatch(sllm_engine* e) {
+    switch (e->cfg.w_dtype) {
+        case SLLM_F32: return enqueue_fused_step<SLLM_F32>(e);
+        case SLLM_BF16: return enqueue_fused_step<SLLM_BF16>(e);
+        default: return enqueue_fused_step<SLLM_INT8>(e);
+    }
+}
+
+// capture one fused step into a graph (once)
+static int build_graph(sllm_engine* e) {
+    if (e->graph_exec) return SLLM_OK;
+    // warm-up launch outside capture: sets the per-kernel shared-memory attributes and loads the modules
+    const int64_t t0 = e->total_launches;
+    if (int rc = enqueue_fused_dispatch(e)) return rc;
+    e->step_launches = (int)(e->total_launches - t0);
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    cudaGraph_t g = nullptr;
+    SLLM_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_fused_dispatch(e);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->total_launches -= e->step_launches;  // the captured pass launched nothing
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    SLLM_CUDA(ce);
+    SLLM_CUDA(cudaGraphInstantiate(&e->graph_exec, g, 0));
+    SLLM_CUDA(cudaGraphDestroy(g));
+    return SLLM_OK;
+}
+
+static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
+    SLLM_REQUIRE(e->weights_loaded, SLLM_ESTATE, "weights not loaded");
+    if (!e->fused) {
+        for (int i = 0; i < n; ++i)
+            if (int rc = enqueue_unfused_step(e, host_pos + i)) return rc;
+        return SLLM_OK;
+    }
+    if (e->use_graph) {
+        SLLM_REQUIRE(e->graph_exec, SLLM_ESTATE, "decode graph not built (weights or communicator missing)");
+        for (int i = 0; i < n; ++i) SLLM_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+        e->total_launches += (int64_t)n * e->step_launches;
+        g_launches += (int64_t)n * e->step_launches;
+        return SLLM_OK;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int64_t t0 = e->total_launches;
+        if (int rc = enqueue_fused_dispatch(e)) return rc;
+        e->step_launches = (int)(e->total_launches - t0);
+    }
+    return SLLM_OK;
+}
+
+static int set_state(sllm_engine* e, int token, int pos, int n_prompt) {
+    SLLM_REQUIRE(pos >= 0 && pos < e->S, SLLM_EINVAL, "position %d outside [0, %d)", pos, e->S);
+    SLLM_REQUIRE(token >= 0 && token < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", token, e->V);
+    set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, token, pos, n_prompt);
+    g_launches++;
+    e->total_launches++;
+    SLLM_LAUNCH_CHECK();
+    return SLLM_OK;
+}
+
+static int set_state(sllm_engine* e, int token, int pos, int n_prompt);
+// ------------------------------------------------------------------------------------------ weights ----
+struct ShardSpec { int seg; int64_t first_row, n_rows, src_row_len, col0, row_len; void* dst; float* sc; };
+
+static std::vector<ShardSpec> shard_plan(sllm_engine* e) {
+    std::vector<ShardSpec> plan;
+    const int64_t d = e->d, kv = e->cfg.shape.kv_hidden, I = e->I, L = e->L, r = e->rank;
+    const int wd = e->cfg.w_dtype, grp = e->cfg.group;
+    auto off_w = [&](const Matrix& m, int64_t elems) { return (void*)(reinterpret_cast<uint8_t*>(m.w) + wbytes(wd, elems)); };
+    auto off_s = [&](const Matrix& m, int64_t elems) { return m.sc ? m.sc + elems / grp : nullptr; };
+    plan.push_back({0, 0, e->V, d, 0, d, e->emb.w, e->emb.sc});
+    plan.push_back({1, 0, 2 * L + 1, d, 0, d, e->norms, nullptr});
+    for (int64_t l = 0; l < L; ++l) {
+        const int64_t qkv_rows = e->q_loc + 2 * e->kv_loc;
+        const int64_t base = l * qkv_rows * d;
+        plan.push_back({2, l * d + r * e->q_loc, e->q_loc, d, 0, d, off_w(e->wqkv, base), off_s(e->wqkv, base)});
+        plan.push_back({3, l * kv + r * e->kv_loc, e->kv_loc, d, 0, d, off_w(e->wqkv, base + (int64_t)e->q_loc * d), off_s(e->wqkv, base + (int64_t)e->q_loc * d)});
+        plan.push_back({4, l * kv + r * e->kv_loc, e->kv_loc, d, 0, d, off_w(e->wqkv, base + (int64_t)(e->q_loc + e->kv_loc) * d), off_s(e->wqkv, base + (int64_t)(e->q_loc + e->kv_loc) * d)});
+        plan.push_back({5, l * d, d, d, r * e->q_loc, e->q_loc, off_w(e->wo, l * d * e->q_loc), off_s(e->wo, l * d * e->q_loc)});
+        const int64_t ug = l * 2 * e->I_loc * d;
+        plan.push_back({6, l * I + r * e->I_loc, e->I_loc, d, 0, d, off_w(e->wug, ug), off_s(e->wug, ug)});
+        plan.push_back({7, l * I + r * e->I_loc, e->I_loc, d, 0, d, off_w(e->wug, ug + (int64_t)e->I_loc * d), off_s(e->wug, ug + (int64_t)e->I_loc * d)});
+        plan.push_back({8, l * d, d, I, r * e->I_loc, e->I_loc, off_w(e->wdown, l * d * e->I_loc), off_s(e->wdown, l * d * e->I_loc)});
+    }
+    return plan;
+}
+
+static int64_t segment_offset(const sllm_shape& s, int seg) {
+    const int64_t V = s.vocab, d = s.hidden, kv = s.kv_hidden, I = s.inter, L = s.layers;
+    const int64_t counts[9] = {V * d, (2 * L + 1) * d, L * d * d, L * kv * d, L * kv * d, L * d * d, L * I * d, L * I * d, L * d * I};
+    int64_t off = 0;
+    for (int k = 0; k < seg; ++k) off += counts[k];
+    return off;
+}
+
+// The graph is built eagerly (when weights and, under TP, the communicator are both present), never lazily in
+// the middle of a run: its warm-up pass executes one real step at (token 0, position 0).
+static int maybe_build_graph(sllm_engine* e) {
+    if (!e->fused || !e->use_graph || e->graph_exec || !e->weights_loaded) return SLLM_OK;
+    if (e->tp > 1 && !e->comm) return SLLM_OK;
+    if (int rc = set_state(e, 0, 0, 0)) return rc;
+    if (int rc = build_graph(e)) return rc;
+    if (int rc = set_state(e, 0, 0, 0)) return rc;
+    SLLM_CUDA(cudaMemsetAsync(e->history_dev, 0, sizeof(int32_t) * (size_t)e->S, e->stream));
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    return SLLM_OK;
+}
+
+static int finish_weights(sllm_engine* e) {
+    if (int rc = sllm_rope_tables(e->hd, e->S, e->cfg.shape.theta, e->sin_t, e->cos_t, e->stream)) return rc;
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    e->weights_loaded = true;
+    return maybe_build_graph(e);
+}
+
+// -------------------------------------------------------------------------------------------- C ABI ----
+extern "C" {
+
+int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm_engine** out) {
+    SLLM_REQUIRE(cfg && out, SLLM_EINVAL, "engine_create: null argument");
+    const sllm_shape& s = cfg->shape;
+    SLLM_REQUIRE(s.vocab > 0 && s.head_dim > 0 && s.hidden > 0 && s.kv_hidden > 0 && s.inter > 0 && s.max_len > 0 && s.layers > 0 &&
+                 s.heads > 0 && s.kv_heads > 0, SLLM_EINVAL, "engine_create: non-positive dimension");
+    SLLM_REQUIRE(s.heads * s.head_dim == s.hidden, SLLM_ENOTSUP, "heads*head_dim (%d) != hidden (%d): the reference's wq/wo are d x d (model.cpp:372-378)", s.heads * s.head_dim, s.hidden);
+    SLLM_REQUIRE(s.kv_heads * s.head_dim == s.kv_hidden && s.heads % s.kv_heads == 0, SLLM_EINVAL, "inconsistent kv dims");
+    const int tp = cfg->tp_size < 1 ? 1 : cfg->tp_size;
+    SLLM_REQUIRE(cfg->tp_rank >= 0 && cfg->tp_rank < tp, SLLM_EINVAL, "tp_rank %d outside [0,%d)", cfg->tp_rank, tp);
+    SLLM_REQUIRE(s.heads % tp == 0 && s.kv_heads % tp == 0 && s.inter % tp == 0 && s.vocab % tp == 0, SLLM_ENOTSUP,
+                 "tensor parallel size %d must divide heads, kv_heads, intermediate and vocab", tp);
+    SLLM_REQUIRE(cfg->w_dtype >= SLLM_F32 && cfg->w_dtype <= SLLM_INT8, SLLM_EINVAL, "bad weight dtype");
+    SLLM_REQUIRE(cfg->kv_dtype == SLLM_F32 || cfg->kv_dtype == SLLM_BF16, SLLM_EINVAL, "bad kv dtype");
+    int ndev = 0;
+    SLLM_CUDA(cudaGetDeviceCount(&ndev));
+    SLLM_REQUIRE(ndev > 0, SLLM_ESTATE, "no CUDA device: libsllm_b200 has no CPU fallback");
+
+    auto* e = new sllm_engine();
+    e->cfg = *cfg;
+    e->cfg.tp_size = tp;
+    if (e->cfg.w_dtype != SLLM_INT8) e->cfg.group = e->cfg.group > 0 ? e->cfg.group : 64;
+    e->stream = as_stream(stream);
+    e->fused = !(cfg->flags & SLLM_ENGINE_UNFUSED);
+    e->use_graph = e->fused && !(cfg->flags & SLLM_ENGINE_NO_GRAPH);
+    e->pdl = e->fused && !(cfg->flags & SLLM_ENGINE_NO_PDL);
+    e->d = s.hidden; e->hd = s.head_dim; e->L = s.layers; e->S = s.max_len; e->V = s.vocab; e->H = s.heads; e->KVH = s.kv_heads; e->I = s.inter;
+    e->tp = tp; e->rank = cfg->tp_rank;
+    e->H_loc = s.heads / tp; e->KVH_loc = s.kv_heads / tp; e->q_loc = e->H_loc * s.head_dim; e->kv_loc = e->KVH_loc * s.head_dim;
+    e->I_loc = s.inter / tp; e->V_loc = s.vocab / tp; e->v0 = e->rank * e->V_loc;
+    e->esz_w = (int)wbytes(cfg->w_dtype, 1); e->esz_kv = cfg->kv_dtype == SLLM_F32 ? 4 : 2;
+    auto fail = [&](int rc) { delete e; return rc; };
+    const int E = cfg->w_dtype == SLLM_F32 ? 4 : cfg->w_dtype == SLLM_BF16 ? 8 : 16;
+    if (e->d % E || e->q_loc % E || e->I_loc % E) { set_error("hidden/local dims must be multiples of %d for this weight type", E); return fail(SLLM_ENOTSUP); }
+    if (cfg->w_dtype == SLLM_INT8 && (cfg->group < 16 || cfg->group % 16 || e->d % cfg->group || e->q_loc % cfg->group || e->I_loc % cfg->group)) {
+        set_error("int8: group=%d must be a multiple of 16 dividing hidden=%d, local q dim=%d and local intermediate=%d", cfg->group, e->d, e->q_loc, e->I_loc);
+        return fail(SLLM_ENOTSUP);
+    }
+    if (e->hd % 16 || e->hd > 256) { set_error("head_dim=%d must be a multiple of 16, <= 256", e->hd); return fail(SLLM_ENOTSUP); }
+    if (gemv_smem_bytes(std::max(e->d, e->I_loc)) > (size_t)smem_optin_bytes()) { set_error("activation vector does not fit shared memory"); return fail(SLLM_ENOTSUP); }
+
+    layout(e);  // measure
+    e->arena_bytes = align_up(e->arena_used, 1 << 20);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (e->arena_bytes > free_b) { set_error("engine needs %zu MiB of HBM, %zu MiB free", e->arena_bytes >> 20, free_b >> 20); return fail(SLLM_ENOMEM); }
+    if (cudaMalloc(&e->arena, e->arena_bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu MiB) failed", e->arena_bytes >> 20); return fail(SLLM_ENOMEM); }
+    layout(e);  // assign
+    // zero everything that is read before it is written: KV cache, workspaces, state
+    cudaError_t ce = cudaMemsetAsync(e->key_cache, 0, e->arena + e->arena_used - reinterpret_cast<uint8_t*>(e->key_cache), e->stream);
+    if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void**>(&e->h_state), 64);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) { cuda_fail(ce, "engine init", __FILE__, __LINE__); sllm_engine_destroy(e); return (int)ce; }
+    *out = e;
+    return SLLM_OK;
+}
+
+void sllm_engine_destroy(sllm_engine* e) {
+    if (!e) return;
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->comm) ncclCommDestroy(e->comm);
+    if (e->h_state) cudaFreeHost(e->h_state);
+    if (e->arena) cudaFree(e->arena);
+    delete e;
+}
+
+int sllm_engine_load_synthetic(sllm_engine* e, uint64_t seed) {
+    SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
+    for (const ShardSpec& p : shard_plan(e))
+        if (int rc = sllm_synth_fill(&e->cfg.shape, seed, p.seg, p.first_row, p.n_rows, p.src_row_len, p.col0, p.row_len, p.dst,
+                                     e->cfg.w_dtype, p.sc, e->cfg.group, e->stream)) return rc;
+    return finish_weights(e);
+}
+
+int sllm_engine_load_blob_f32(sllm_engine* e, const float* blob, int64_t n_floats) {
+    SLLM_REQUIRE(e && blob, SLLM_EINVAL, "null argument");
+    const sllm_shape& s = e->cfg.shape;
+    const int64_t need = segment_offset(s, 8) + (int64_t)s.layers * s.hidden * s.inter;
+    SLLM_REQUIRE(n_floats >= need, SLLM_EINVAL, "weight blob has %lld floats, the shape needs %lld (model.cpp:340-468 layout)", (long long)n_floats, (long long)need);
+    const size_t stage_bytes = (size_t)64 << 20;
+    float* stage = nullptr;
+    SLLM_CUDA(cudaMalloc(&stage, stage_bytes));
+    int rc = SLLM_OK;
+    for (const ShardSpec& p : shard_plan(e)) {
+        const float* src = blob + segment_offset(s, p.seg);
+        const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(stage_bytes / 4) / p.row_len);
+        const int wd = (p.seg == 1) ? SLLM_F32 : e->cfg.w_dtype;
+        for (int64_t r0 = 0; r0 < p.n_rows && rc == SLLM_OK; r0 += rows_per_chunk) {
+            const int64_t nr = std::min(rows_per_chunk, p.n_rows - r0);
+            cudaError_t ce = cudaMemcpy2DAsync(stage, (size_t)p.row_len * 4, src + (p.first_row + r0) * p.src_row_len + p.col0,
+                                               (size_t)p.src_row_len * 4, (size_t)p.row_len * 4, (size_t)nr, cudaMemcpyHostToDevice, e->stream);
+            if (ce != cudaSuccess) { rc = cuda_fail(ce, "cudaMemcpy2DAsync(weights)", __FILE__, __LINE__); break; }
+            void* dst = reinterpret_cast<uint8_t*>(p.dst) + wbytes(wd, r0 * p.row_len);
+            float* sc = p.sc ? p.sc + r0 * p.row_len / e->cfg.group : nullptr;
+            rc = sllm_convert_weights(stage, dst, wd, sc, e->cfg.group, nr, p.row_len, e->stream);
+            if (rc == SLLM_OK) { ce = cudaStreamSynchronize(e->stream); if (ce != cudaSuccess) rc = cuda_fail(ce, "sync", __FILE__, __LINE__); }
+        }
+        if (rc) break;
+    }
+    cudaFree(stage);
+    if (rc) return rc;
+    return finish_weights(e);
+}
+
+int sllm_comm_unique_id(void* id_bytes_128) {
+    SLLM_REQUIRE(id_bytes_128, SLLM_EINVAL, "null id buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    SLLM_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(id_bytes_128, &id, 128);
+    return SLLM_OK;
+}
+
+int sllm_engine_init_comm(sllm_engine* e, const void* id_bytes_128) {
+    SLLM_REQUIRE(e && id_bytes_128, SLLM_EINVAL, "null argument");
+    SLLM_REQUIRE(e->tp > 1, SLLM_ESTATE, "init_comm on a single-rank engine");
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes_128, 128);
+    SLLM_NCCL(ncclCommInitRank(&e->comm, e->tp, id, e->rank));
+    return maybe_build_graph(e);
+}
+
+int sllm_engine_p2p_export(sllm_engine*, void*) { set_error("peer-memory all-reduce: not built yet"); return SLLM_ENOTSUP; }
+int sllm_engine_p2p_import(sllm_engine*, const void*) { set_error("peer-memory all-reduce: not built yet"); return SLLM_ENOTSUP; }
+
+int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos) {
+    SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
+    e->h_state[7] = pos;  // host shadow of the position for the op-by-op path
+    return set_state(e, token, pos, 0);
+}
+
+int sllm_engine_enqueue_steps(sllm_engine* e, int32_t n_steps) {
+    SLLM_REQUIRE(e && n_steps >= 0, SLLM_EINVAL, "bad argument");
+    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel engine without a communicator");
+    SLLM_REQUIRE(e->h_state[7] + n_steps <= e->S, SLLM_EINVAL, "%d steps from position %d overrun max_len %d", n_steps, e->h_state[7], e->S);
+    int rc = enqueue_steps(e, n_steps, e->h_state[7]);
+    e->h_state[7] += n_steps;
+    return rc;
+}
+
+int sllm_engine_read_tokens(sllm_engine* e, int32_t* out, int32_t n) {
+    SLLM_REQUIRE(e && out && n >= 0 && n <= e->S, SLLM_EINVAL, "bad argument");
+    const int first = e->h_state[7] - n;
+    SLLM_REQUIRE(first >= 0, SLLM_EINVAL, "asked for %d tokens, only %d steps taken", n, e->h_state[7]);
+    SLLM_CUDA(cudaMemcpyAsync(out, e->history_dev + first, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    return SLLM_OK;
+}
+
+int sllm_engine_forward(sllm_engine* e, int32_t token, int32_t pos, float* logits_host, int32_t* next_token_host) {
+    SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
+    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel engine without a communicator");
+    // host -> device: token and position travel through pinned memory like any other input
+    e->h_state[0] = token; e->h_state[1] = pos; e->h_state[2] = 0; e->h_state[3] = 0;
+    SLLM_REQUIRE(pos >= 0 && pos < e->S, SLLM_EINVAL, "position %d outside [0, %d)", pos, e->S);
+    SLLM_REQUIRE(token >= 0 && token < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", token, e->V);
+    SLLM_CUDA(cudaMemcpyAsync(e->state, e->h_state, 16, cudaMemcpyHostToDevice, e->stream));
+    e->h_state[7] = pos;
+    if (int rc = enqueue_steps(e, 1, pos)) return rc;
+    e->h_state[7] = pos + 1;
+    if (logits_host) SLLM_CUDA(cudaMemcpyAsync(logits_host, e->logits, sizeof(float) * (size_t)e->V_loc, cudaMemcpyDeviceToHost, e->stream));
+    if (next_token_host) SLLM_CUDA(cudaMemcpyAsync(e->h_state + 4, &e->state->next, 4, cudaMemcpyDeviceToHost, e->stream));
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    if (next_token_host) *next_token_host = e->h_state[4];
+    return SLLM_OK;
+}
+
+int sllm_engine_greedy(sllm_engine* e, const int32_t* prompt, int32_t n_prompt, int32_t n_total, int32_t* tokens_out) {
+    SLLM_REQUIRE(e && prompt && tokens_out, SLLM_EINVAL, "null argument");
+    SLLM_REQUIRE(n_prompt >= 1 && n_total >= n_prompt && n_total <= e->S, SLLM_EINVAL, "need 1 <= n_prompt <= n_total <= max_len (%d, %d, %d)", n_prompt, n_total, e->S);
+    for (int i = 0; i < n_prompt; ++i) SLLM_REQUIRE(prompt[i] >= 0 && prompt[i] < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", prompt[i], e->V);
+    SLLM_CUDA(cudaMemcpyAsync(e->prompt_dev, prompt, sizeof(int32_t) * (size_t)n_prompt, cudaMemcpyHostToDevice, e->stream));
+    if (int rc = set_state(e, prompt[0], 0, n_prompt)) return rc;
+    e->h_state[7] = 0;
+    if (int rc = sllm_engine_enqueue_steps(e, n_total - 1)) return rc;
+    return sllm_engine_read_tokens(e, tokens_out, n_total - 1);
+}
+
+int sllm_engine_prefill(sllm_engine*, const int32_t*, int32_t, int32_t) { set_error("batched prefill: not built yet"); return SLLM_ENOTSUP; }
+
+int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32_t* dtype) {
+    SLLM_REQUIRE(e && ptr && n && dtype, SLLM_EINVAL, "null argument");
+    const int64_t kvn = (int64_t)e->L * e->S * e->kv_loc;
+    *dtype = SLLM_F32;
+    switch (id) {
+        case 2: *ptr = e->key_cache; *n = kvn; *dtype = e->cfg.kv_dtype; break;
+        case 3: *ptr = e->value_cache; *n = kvn; *dtype = e->cfg.kv_dtype; break;
+        case 4: *ptr = e->x; *n = e->d; break;
+        case 5: *ptr = e->xb; *n = e->d; break;
+        case 6: *ptr = e->q; *n = e->q_loc; break;
+        case 8: *ptr = e->att; *n = e->q_loc; break;
+        case 9: *ptr = e->att_out; *n = e->d; break;
+        case 10: *ptr = e->h; *n = e->d; break;
+        case 11: *ptr = e->up; *n = e->I_loc; break;
+        case 12: *ptr = e->gate; *n = e->I_loc; break;
+        case 14: *ptr = e->swi; *n = e->I_loc; break;
+        case 15: *ptr = e->ffn_out; *n = e->d; break;
+        case 16: *ptr = e->logits; *n = e->V_loc; break;
+        case 17: *ptr = e->sin_t; *n = (int64_t)e->S * (e->hd / 2); break;
+        case 18: *ptr = e->cos_t; *n = (int64_t)e->S * (e->hd / 2); break;
+        case 100: *ptr = e->emb.w; *n = (int64_t)e->V * e->d; *dtype = e->cfg.w_dtype; break;
+        case 101: *ptr = e->norms; *n = (int64_t)(2 * e->L + 1) * e->d; break;
+        case 102: *ptr = e->wqkv.w; *n = (int64_t)e->L * e->wqkv.rows * e->wqkv.cols; *dtype = e->cfg.w_dtype; break;
+        case 103: *ptr = e->wo.w; *n = (int64_t)e->L * e->wo.rows * e->wo.cols; *dtype = e->cfg.w_dtype; break;
+        case 104: *ptr = e->wug.w; *n = (int64_t)e->L * e->wug.rows * e->wug.cols; *dtype = e->cfg.w_dtype; break;
+        case 105: *ptr = e->wdown.w; *n = (int64_t)e->L * e->wdown.rows * e->wdown.cols; *dtype = e->cfg.w_dtype; break;
+        case 110: *ptr = e->emb.sc; *n = e->emb.sc ? (int64_t)e->V * e->d / e->cfg.group : 0; break;
+        case 112: *ptr = e->wqkv.sc; *n = e->wqkv.sc ? (int64_t)e->L * e->wqkv.rows * e->wqkv.cols / e->cfg.group : 0; break;
+        default: SLLM_REQUIRE(false, SLLM_EINVAL, "unknown buffer id %d", id);
+    }
+    return SLLM_OK;
+}
+
+int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos) {
+    if (!e) return 0;
+    const double bw = e->cfg.w_dtype == SLLM_F32 ? 4.0 : e->cfg.w_dtype == SLLM_BF16 ? 2.0 : 1.0 + 4.0 / e->cfg.group;
+    const double d = e->d, L = e->L;
+    const double mats = (double)e->V_loc * d + L * ((double)(e->q_loc + 2 * e->kv_loc) * d + d * e->q_loc + 3.0 * e->I_loc * d);
+    const double bytes = bw * mats + 4.0 * (2 * L + 1) * d + bw * d + (double)e->esz_kv * 2 * L * e->kv_loc * (pos + 1) +
+                         (double)e->esz_kv * 2 * L * e->kv_loc;
+    return (int64_t)bytes;
+}
+
+int32_t sllm_engine_step_launches(const sllm_engine* e) { return e ? e->step_launches : 0; }
+int64_t sllm_engine_total_launches(const sllm_engine* e) { return e ? e->total_launches : 0; }
+
+}  // extern "C"

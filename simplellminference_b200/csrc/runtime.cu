@@ -1,0 +1,66 @@
+// csrc/runtime.cu — error reporting and device facts behind include/sllm_b200.h.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace sllm {
+
+static thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return (int)e;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int smem_optin_bytes() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (n <= 0) n = 48 * 1024;
+    }
+    return n;
+}
+
+}  // namespace sllm
+
+extern "C" {
+
+const char* sllm_last_error(void) { return sllm::g_err; }
+int sllm_abi_version(void) { return 1; }
+
+int sllm_device_info(int32_t* sms, int32_t* smem, size_t* total, size_t* free_) {
+    int n = 0;
+    SLLM_CUDA(cudaGetDeviceCount(&n));
+    SLLM_REQUIRE(n > 0, SLLM_ESTATE, "no CUDA device visible: libsllm_b200 has no CPU fallback");
+    if (sms) *sms = sllm::sm_count();
+    if (smem) *smem = sllm::smem_optin_bytes();
+    size_t f = 0, t = 0;
+    SLLM_CUDA(cudaMemGetInfo(&f, &t));
+    if (total) *total = t;
+    if (free_) *free_ = f;
+    return SLLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""CPU tests of the oracle itself: the C restatement (oracle/llama_oracle.c) must agree BIT FOR BIT with
+ (a) the golden fixtures generated from the unmodified reference (tests/golden/make_golden.py), always;
+ (b) the reference compiled here (oracle/_ref), live, whenever it is available."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import loader
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+
+def test_ops_match_golden(port, golden_ops):
+    i, g = mg.op_inputs(), golden_ops
+    assert np.array_equal(port.rmsnorm(i["x"], i["w"], i["eps"]), g["rmsnorm"])
+    assert np.array_equal(port.matmul(i["x"], i["W"]), g["matmul"])
+    assert np.array_equal(port.add(i["a"], i["b"]), g["add"])
+    assert np.array_equal(port.swiglu(i["up"], i["gate"]), g["swiglu"])
+    assert np.array_equal(port.embedding(i["token"], i["table"]), g["embedding"])
+    s, c = port.rope_cache(i["hd"], i["S"], i["theta"])
+    assert np.array_equal(s, g["sin"]) and np.array_equal(c, g["cos"])
+    # the reference rotates k over q's length; the port over k's own length: same thing here (k.size == q.size)
+    q, k = port.rope(i["q"], i["k"], i["pos"], s, c, i["hd"])
+    assert np.array_equal(q, g["rope_q"]) and np.array_equal(k, g["rope_k"])
+    assert np.array_equal(port.mha(i["q"], i["kc"], i["vc"], i["layer"], i["pos"], i["hd"], i["H"], i["KVH"]), g["mha"])
+    assert port.argmax(i["logits"]) == int(g["argmax"])
+    # ties resolve to the first maximum (argmax.cpp:11)
+    lg = i["logits"]
+    assert (lg == lg.max()).sum() > 1 and port.argmax(lg) == int(np.flatnonzero(lg == lg.max())[0])
+
+
+@pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
+def test_models_match_golden(port, golden_models, name):
+    prompt, n_total, wd = mg.MODEL_RUNS[name]
+    shape = mg.SHAPES[name.replace("_bf16w", "").replace("_int8w", "")]
+    blob = port.fill_blob(shape, mg.SEED, wd, 64)
+    m = port.model(shape, blob, threads=os.cpu_count() or 1)
+    toks, last = m.greedy(prompt, n_total)
+    assert np.array_equal(toks, golden_models[name + "/tokens"])
+    assert np.array_equal(last, golden_models[name + "/last_logits"])
+    kv = shape.kv_hidden
+    assert np.array_equal(m.read(2, (n_total - 2) * kv, kv), golden_models[name + "/k_l0_last"])
+    assert np.array_equal(m.read(4, 0, shape.hidden), golden_models[name + "/x_last"])
+
+
+def test_port_vs_reference_live(port, ref):
+    """Fresh seeds (not the golden ones), including a GQA model, against the compiled reference."""
+    rng = np.random.default_rng(99)
+    for d, rows in ((64, 5), (288, 33), (1000, 7)):
+        x = rng.standard_normal(d).astype(np.float32)
+        w = rng.standard_normal(d).astype(np.float32)
+        W = rng.standard_normal((rows, d)).astype(np.float32)
+        assert np.array_equal(port.rmsnorm(x, w, 1e-6), ref.rmsnorm(x, w, 1e-6))
+        assert np.array_equal(port.matmul(x, W), ref.matmul(x, W))
+        assert np.array_equal(port.swiglu(x, 8 * w), ref.swiglu(x, 8 * w))
+        assert np.array_equal(port.add(x, w), ref.add(x, w))
+    shape = loader.Shape(640, 16, 64, 32, 96, 24, 2, 4, 2, 1e-6, 500000.0)
+    blob = port.fill_blob(shape, 77)
+    a, b = port.model(shape, blob), ref.model(shape, blob)
+    ta, la = a.greedy([3, 9, 27], 23)   # pos <= S - H/KVH = 22
+    tb, lb = b.greedy([3, 9, 27], 23)
+    assert np.array_equal(ta, tb) and np.array_equal(la, lb)
+    for buf in (2, 3):
+        n = shape.layers * shape.max_len * shape.kv_hidden
+        ka, kb = a.read(buf, 0, n).reshape(shape.layers, shape.max_len, -1), b.read(buf, 0, n).reshape(shape.layers, shape.max_len, -1)
+        assert np.array_equal(ka[:, :22], kb[:, :22])   # rows actually written inside the parity domain
+
+
+def test_threads_do_not_change_bits(port):
+    shape = mg.SHAPES["tiny_gqa"]
+    blob = port.fill_blob(shape, 5)
+    t1, l1 = port.model(shape, blob, threads=1).greedy([1], 30)
+    t8, l8 = port.model(shape, blob, threads=8).greedy([1], 30)
+    assert np.array_equal(t1, t8) and np.array_equal(l1, l8)
+
+
+def test_kv_bf16_extension_rounds_cache(port):
+    shape = mg.SHAPES["tiny_gqa"]
+    blob = port.fill_blob(shape, 5, loader.BF16)
+    m = port.model(shape, blob, kv_bf16=True)
+    m.greedy([1], 10)
+    k = m.read(2, 0, 8 * shape.kv_hidden)
+    as_bits = k.view(np.uint32)
+    assert np.all((as_bits & 0xFFFF) == 0) and np.any(k != 0)
+
+
+def test_synthetic_weights_contract(port):
+    """bf16 rounding = RNE, int8 dequant = q*scale with scale = amax/127, norms stay fp32."""
+    shape = mg.SHAPES["tiny_gqa"]
+    raw = port.fill_segment(shape, 2, 0, 4096, wdtype=loader.F32)
+    bf = port.fill_segment(shape, 2, 0, 4096, wdtype=loader.BF16)
+    import torch
+    assert np.array_equal(torch.from_numpy(raw).to(torch.bfloat16).float().numpy(), bf)
+    q, sc = port.fill_segment_int8(shape, 2, 0, 4096, group=64)
+    dq = port.fill_segment(shape, 2, 0, 4096, wdtype=loader.INT8, group=64)
+    assert np.array_equal(q.astype(np.float32).reshape(-1, 64) * sc[:, None], dq.reshape(-1, 64))
+    amax = np.abs(raw.reshape(-1, 64)).max(1)
+    assert np.array_equal(sc, (amax / np.float32(127.0)).astype(np.float32))
+    assert np.abs(dq - raw).max() <= sc.max() * 0.5 + 1e-7
+    norms_bf = port.fill_segment(shape, 1, 0, 256, wdtype=loader.BF16)
+    assert np.array_equal(norms_bf, port.fill_segment(shape, 1, 0, 256, wdtype=loader.F32))
+    # moments: Irwin-Hall(4) scaled to unit variance
+    big = port.fill_segment(mg.SHAPES["cfg1_stories15M"], 0, 0, 1 << 20)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1.0) < 5e-3
