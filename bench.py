@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s (batch 1, greedy) and fraction of the HBM roofline (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our arm (CUDA, sm_100a)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's CPU path, host cores
+  torchrun ... bench.py --gpus N ...                                   tensor parallel over N GPUs (one rank each)
+
+Workload (config.workload): Llama-2-7B-shaped model (BASELINE.json configs[3], the configuration the metric
+and the >=70 % target are quoted on; it fits one GPU), random-init synthetic weights (counter-based hash, bf16
+storage), batch-1 greedy decode continuing a 512-token synthetic prompt. A "step" is ONE decoded token = one
+pass of the whole forward hot path (all weights + the KV cache read once). Per-step working set (13.5 GB) is
+far larger than the 126 MB L2, so no L2 flush is needed between steps (stated in config.l2).
+
+One JSON line on stdout (rank 0). `value` = tokens/s with everything resident in HBM (CUDA-graph replays,
+token feedback on the device); `e2e` = the same metric through the reference-facing call — forward(token,
+pos) per token with host buffers: H2D of token+position, D2H of the next token, a host sync per token.
+`roofline` = the dominant kernel (gate_up GEMV) timed alone with CUDA events, cycling over the layers so its
+weights always come from HBM; `step_roofline` = whole-step algorithmic bytes B(p) / step time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode_tokens_per_sec_batch1_greedy"
+UNIT = "tokens/s"
+PROMPT_LEN = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="llama2-7b", help="shape preset (simplellminference_b200/config.py)")
+    ap.add_argument("--wdtype", default="bf16", choices=["f32", "bf16", "int8"])
+    ap.add_argument("--kvdtype", default="bf16", choices=["f32", "bf16"])
+    ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
+    return ap.parse_args()
+
+
+def peaks():
+    """(HBM GB/s, source) — MEASURED_PEAKS.json when the driver wrote it, else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def prompt_ids(n, vocab):
+    import numpy as np
+    rng = np.random.default_rng(20260101)
+    ids = rng.integers(1, vocab, size=n, dtype=np.int32)
+    ids[0] = 1
+    return ids
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/sllm_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm --
+def cpu_reference_sample(ms, pos, steps, warmup, want_fast=True):
+    """Times the reference's own CPU forward (oracle/_ref = the unmodified sources compiled by oracle/Makefile;
+    falls back to the C port only if that library was never built) on a BOUNDED sample of the workload:
+    the full-shape model cut to L1 and L2 layers (+ the full classifier), one forward at position `pos` per
+    step; the 32-layer token time is extrapolated linearly in the layer count (layers are identical in cost).
+    The reference is single-threaded by construction (no threads/OpenMP anywhere in it): cores = 1."""
+    import numpy as np
+    from oracle import loader
+    port = loader.Port()
+    kind, flags, ref = "port", "gcc -O2 -ffp-contract=off (C restatement)", None
+    if loader.have_ref():
+        fast = want_fast and loader.cpu_supports_v3() and os.path.exists(loader.REF_FAST_SO)
+        ref = loader.Ref(fast=fast)
+        kind, flags = "reference", ref.flags
+    L1, L2 = 1, 2
+    times = {}
+    cwd = os.getcwd()
+    os.chdir("/tmp")  # LlamaModel::forward() opens layer_outputs_cpu.txt in the cwd on every call (model.cpp:42)
+    try:
+        for L in (L1, L2):
+            shape = loader.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, L, ms.heads, ms.kv_heads,
+                                 ms.eps, ms.theta)
+            blob = port.fill_blob(shape, 1234, loader.BF16)
+            m = ref.model(shape, blob) if ref else port.model(shape, blob)
+            for _ in range(warmup):
+                m.step(1, pos)
+            ts = []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                m.step(1, pos)
+                ts.append(time.perf_counter() - t0)
+            times[L] = statistics.median(ts)
+            m.close()
+            del blob
+    finally:
+        os.chdir(cwd)
+    per_layer = (times[L2] - times[L1]) / (L2 - L1)
+    t_token = times[L1] + (ms.layers - L1) * per_layer
+    return {
+        "value": 1.0 / t_token, "unit": UNIT, "cores": 1, "kind": kind,
+        "sample": f"{steps} forwards each of the {L1}- and {L2}-layer cuts of the full-shape model (+ full classifier) at pos={pos}; "
+                  f"{ms.layers}-layer token time extrapolated linearly ({times[L1]*1e3:.0f} ms + {ms.layers - L1} x {per_layer*1e3:.0f} ms); "
+                  f"build: {flags}; host has {os.cpu_count()} cores, the reference uses 1",
+        "sec_per_token": t_token,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from simplellminference_b200.config import PRESETS
+    ms = PRESETS[args.config]
+    steps, warmup = min(args.steps, 6), min(args.warmup, 1)
+    base = cpu_reference_sample(ms, args.prompt_len, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * base["sec_per_token"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, ms),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, ms):
+    return {"workload": f"{args.config}-shaped (d={ms.hidden} L={ms.layers} H={ms.heads} KVH={ms.kv_heads} I={ms.inter} V={ms.vocab}), "
+                        f"{args.wdtype} weights, {args.kvdtype} KV cache, batch-1 greedy decode continuing a {args.prompt_len}-token prompt",
+            "prompt_len": args.prompt_len, "weights": args.wdtype, "kv_cache": args.kvdtype, "parallelism": f"tp{args.gpus}",
+            "l2": "no flush: every step streams its whole working set (weights+KV >> 126 MB L2) from HBM"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm --
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from simplellminference_b200.config import PRESETS, F32, BF16, INT8
+    from simplellminference_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ms = PRESETS[args.config]
+    wd = {"f32": F32, "bf16": BF16, "int8": INT8}[args.wdtype]
+    kvd = {"f32": F32, "bf16": BF16}[args.kvdtype]
+    K, W, P = args.steps, max(args.warmup, 3), args.prompt_len
+    assert P + W + 2 * K + 8 <= ms.max_len, "prompt + steps exceed the model's max_len"
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
+                 graph=not (args.no_graph or args.unfused), pdl=not args.no_pdl)
+    eng.load_synthetic(1234)
+    if world > 1:
+        eng.init_comm(dist)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms_val):
+        if world == 1:
+            return ms_val
+        t = torch.tensor([ms_val], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.kernel_only:   # profiling aid (ncu): a short loop of one fused kernel over the layers
+        eng.set_state(1, P)
+        for it in range(3):
+            for l in range(ms.layers):
+                eng.enqueue_kernel(args.kernel_only, l)
+        torch.cuda.synchronize()
+        print(json.dumps({"kernel_only": args.kernel_only, "launches": 3 * ms.layers}))
+        return
+
+    # ---- prompt: fed token by token through the same decode step (the reference has no batched prefill,
+    # model.cpp:157-166), untimed; it leaves the KV cache filled for positions 0..P-1
+    ids = prompt_ids(P, ms.vocab)
+    barrier()
+    t_prompt0 = time.perf_counter()
+    toks = eng.greedy(ids, P + 1)            # P forwards: positions 0..P-1; state is now (argmax, pos=P)
+    t_prompt = time.perf_counter() - t_prompt0
+    assert toks.size == P and np.array_equal(toks[:P - 1], ids[1:]), "prompt echo mismatch"
+
+    # ---- resident decode: W warm-up + K timed graph replays, token feedback on the device
+    sampler = ClockSampler(local)
+    eng.enqueue_steps(W)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.total_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    eng.enqueue_steps(K)
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.total_launches - launches0
+    pos_first = P + W
+    tokens = eng.read_tokens(K)
+    value = K / (ms_total * 1e-3)
+    step_bytes = float(np.mean([eng.step_bytes(p) for p in range(pos_first, pos_first + K)]))
+    full_bytes = float(np.mean([ms.step_bytes(p, wd, kvd) for p in range(pos_first, pos_first + K)]))
+
+    # ---- e2e: the reference-facing call, host buffers, one sync per token
+    pos = pos_first + K
+    tok = int(tokens[-1])
+    for _ in range(3):
+        _, tok = eng.forward(tok, pos, want_logits=False); pos += 1
+    barrier()
+    Ke = min(K, ms.max_len - pos - 1)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(Ke):
+        _, tok = eng.forward(tok, pos, want_logits=False); pos += 1
+    ev3.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(ev2.elapsed_time(ev3))
+    e2e = {"value": Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4,
+           "steps": Ke, "api": "Engine.forward(token,pos) == sllm_engine_forward: LlamaModel::forward semantics + device argmax"}
+
+    # ---- the dominant kernel alone (gate_up: RMSNorm + [Wup;Wgate] GEMV + sigmoid*up), cycling over layers
+    roof = None
+    peak, peak_src = peaks()
+    if not args.unfused:
+        eng.set_state(tok, min(pos, ms.max_len - 1))
+        reps = max(2, 64 // ms.layers)
+        for l in range(ms.layers):
+            eng.enqueue_kernel("gate_up", l)
+        barrier()
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev4.record(stream)
+        for _ in range(reps):
+            for l in range(ms.layers):
+                eng.enqueue_kernel("gate_up", l)
+        ev5.record(stream)
+        barrier()
+        k_ms = max_over_ranks(ev4.elapsed_time(ev5)) / (reps * ms.layers)
+        kb = eng.kernel_bytes("gate_up", 0)
+        ach = kb / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "fused_gemv_kernel<GateUpPolicy> (RMSNorm + up/gate GEMV + sigmoid(gate)*up)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "bytes_per_launch": kb, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src,
+                "how": f"{reps * ms.layers} back-to-back launches cycling over {ms.layers} layers (weights {kb * ms.layers / 1e9:.1f} GB >> L2), CUDA events"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    ach_step = step_bytes * world / (ms_total * 1e-3 / K) / 1e9   # aggregate over ranks
+    step_roof = {"bound": "hbm", "achieved": ach_step, "peak": peak * world, "unit": "GB/s", "frac": ach_step / (peak * world),
+                 "frac_of_8TBs_nominal": ach_step / (8000.0 * world), "bytes_per_step": full_bytes, "peak_source": peak_src,
+                 "positions": [pos_first, pos_first + K - 1]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_sample(ms, P, 3, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the baseline is informational; never lose the GPU numbers over it
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.wdtype, "data": "synthetic",
+        "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
+        "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
+        "mode": {"fused": not args.unfused, "graph": not (args.no_graph or args.unfused), "pdl": not args.no_pdl},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

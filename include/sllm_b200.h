@@ -46,6 +46,8 @@ typedef void* sllm_stream_t;
 
 const char* sllm_last_error(void);
 int sllm_abi_version(void);
+/* development knobs (not part of the drop-in surface): key 0 = GEMV CTAs per SM (0 = built-in choice) */
+int sllm_tune(int32_t key, int32_t value);
 /* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
 int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);
 
@@ -149,6 +151,8 @@ typedef struct {
 
 typedef struct sllm_engine sllm_engine;
 
+/* stream: the stream every engine operation is enqueued on; NULL = the engine creates and owns a
+ * non-blocking stream (the legacy default stream cannot be captured into a CUDA graph). */
 int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm_engine** out);
 void sllm_engine_destroy(sllm_engine* e);
 
@@ -193,6 +197,13 @@ int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt_host, int32_t n, i
 int sllm_engine_buffer(sllm_engine* e, int32_t buffer_id, void** dev_ptr, int64_t* n_elems, int32_t* dtype);
 /* algorithmic HBM bytes one decode step at position pos must move on this rank */
 int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos);
+/* Enqueue ONE fused kernel of the decode step for `layer` at the current device-side position, for per-kernel
+ * timing and profiling. kind: 0 embedding, 1 qkv (RMSNorm+QKV GEMV+RoPE+cache write), 2 mha (flash decoding),
+ * 3 wo (+residual), 4 gate_up (RMSNorm+GEMV+sigmoid*up), 5 down (+residual), 6 classifier (+argmax; the step
+ * state is left untouched). sllm_engine_kernel_bytes = the algorithmic HBM bytes of that launch (its share of
+ * B(p): weights it streams, norm vector, KV rows read/written). */
+int sllm_engine_enqueue_kernel(sllm_engine* e, int32_t kind, int32_t layer);
+int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos);
 /* number of kernel launches (graph kernel nodes) one decode step issues on this rank */
 int32_t sllm_engine_step_launches(const sllm_engine* e);
 /* total launches issued by this engine since creation */

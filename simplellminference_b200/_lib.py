@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsllm_b200.so")
+LIB_PATH = os.environ.get("SLLM_LIB") or os.path.join(HERE, "lib", "libsllm_b200.so")
 
 
 class SllmError(RuntimeError):
@@ -40,6 +40,7 @@ _F = C.c_float
 SIGNATURES = {
     "sllm_last_error": (C.c_char_p, []),
     "sllm_abi_version": (C.c_int, []),
+    "sllm_tune": (C.c_int, [_I, _I]),
     "sllm_device_info": (C.c_int, [C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sllm_add_f32": (C.c_int, [_P, _P, _P, _I, _P]),
     "sllm_embedding": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
@@ -70,6 +71,8 @@ SIGNATURES = {
     "sllm_engine_prefill": (C.c_int, [_P, _P, _I, _I]),
     "sllm_engine_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_engine_step_bytes": (_L, [_P, _I]),
+    "sllm_engine_enqueue_kernel": (C.c_int, [_P, _I, _I]),
+    "sllm_engine_kernel_bytes": (_L, [_P, _I, _I]),
     "sllm_engine_step_launches": (_I, [_P]),
     "sllm_engine_total_launches": (_L, [_P]),
 }

@@ -45,6 +45,7 @@ struct Matrix {          // a weight matrix (or stack of per-layer matrices) in 
 struct sllm_engine {
     sllm_engine_config cfg{};
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
     bool fused = true, use_graph = true, pdl = true;
     // local (this rank's) dimensions
     int d = 0, hd = 0, L = 0, S = 0, V = 0, H = 0, KVH = 0, I = 0;
@@ -206,64 +207,95 @@ __global__ void tp_pack_kernel(const float* blk_val, const int32_t* blk_idx, int
     }
 }
 
+// One fused kernel of the step. kind: 0 embed, 1 qkv(A), 2 mha(B), 3 wo(C), 4 gate_up(D), 5 down(E), 6 cls(F).
+// Residual-stream bookkeeping under TP: after the all-reduce of a row-parallel GEMV the partial sum sits in
+// part_*; the NEXT kernel's prologue adds it to the residual (and CTA 0 stores the sum).
+enum { K_EMBED = 0, K_QKV = 1, K_MHA = 2, K_WO = 3, K_GATEUP = 4, K_DOWN = 5, K_CLS = 6 };
+
 template <int WD>
-static int enqueue_fused_step(sllm_engine* e) {
+static int enqueue_kernel(sllm_engine* e, int kind, int l) {
     const sllm_shape& s = e->cfg.shape;
     const int d = e->d, L = e->L;
     const bool tp = e->tp > 1;
     const int32_t* pos_dev = &e->state->pos;
-    {
-        LaunchCfg lc(dim3(std::max(1, std::min((d + 255) / 256, 64))), dim3(256), 0, e->stream, e->pdl);
-        SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, embed_state_kernel, (const StepState*)e->state, (const void*)e->emb.w, e->cfg.w_dtype,
-                                     (const float*)e->emb.sc, e->cfg.group, e->x, e->V, d));
-        g_launches++;
-        count_launch(e);
+    switch (kind) {
+        case K_EMBED: {
+            LaunchCfg lc(dim3(std::max(1, std::min((d + 255) / 256, 64))), dim3(256), 0, e->stream, e->pdl);
+            SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, embed_state_kernel, (const StepState*)e->state, (const void*)e->emb.w, e->cfg.w_dtype,
+                                         (const float*)e->emb.sc, e->cfg.group, e->x, e->V, d));
+            g_launches++;
+            count_launch(e);
+            return SLLM_OK;
+        }
+        case K_QKV: {
+            QkvPolicy<WD> A{};
+            A.W_ = mat_layer(e, e->wqkv, l); A.sc_ = sc_layer(e, e->wqkv, l); A.grp_ = e->cfg.group; A.cols_ = d;
+            if (tp && l > 0) { A.x = e->h; A.add = e->part_b; A.sum_out = e->x; } else { A.x = e->x; A.add = nullptr; A.sum_out = nullptr; }
+            A.norm_w = e->norms + (int64_t)(2 * l) * d; A.eps = s.eps; A.pos_dev = pos_dev; A.sin_t = e->sin_t; A.cos_t = e->cos_t;
+            A.q_out = e->q; A.k_cache = kv_layer(e, e->key_cache, l); A.v_cache = kv_layer(e, e->value_cache, l);
+            A.kv_dtype = e->cfg.kv_dtype; A.q_dim = e->q_loc; A.kv_dim = e->kv_loc; A.hd = e->hd;
+            return launch_policy<WD>(e, A, (e->q_loc + 2 * e->kv_loc) / 2);
+        }
+        case K_MHA: {
+            if (int rc = mha_decode_dispatch(e->q, e->key_cache, e->value_cache, e->cfg.kv_dtype, e->att, e->mha_ws, l, pos_dev, 0, e->S,
+                                             e->hd, e->H_loc, e->KVH_loc, e->stream, e->pdl)) return rc;
+            count_launch(e);
+            return SLLM_OK;
+        }
+        case K_WO: {
+            ResidualPolicy<WD> C{};
+            C.W_ = mat_layer(e, e->wo, l); C.sc_ = sc_layer(e, e->wo, l); C.grp_ = e->cfg.group; C.cols_ = e->q_loc;
+            C.x = e->att; C.nrows = d;
+            if (tp) { C.resid = nullptr; C.y = e->part_a; } else { C.resid = e->x; C.y = e->h; }
+            return launch_policy<WD>(e, C, (d + 1) / 2);
+        }
+        case K_GATEUP: {
+            GateUpPolicy<WD> D{};
+            D.W_ = mat_layer(e, e->wug, l); D.sc_ = sc_layer(e, e->wug, l); D.grp_ = e->cfg.group; D.cols_ = d;
+            // TP: the residual stream entering this layer is x (layer 0) or h+part_b, which kernel A stored in x
+            if (tp) { D.h = e->x; D.add = e->part_a; D.sum_out = e->h; } else { D.h = e->h; D.add = nullptr; D.sum_out = nullptr; }
+            D.norm_w = e->norms + (int64_t)(2 * l + 1) * d; D.eps = s.eps; D.s_out = e->swi; D.inter = e->I_loc;
+            return launch_policy<WD>(e, D, e->I_loc);
+        }
+        case K_DOWN: {
+            ResidualPolicy<WD> E{};
+            E.W_ = mat_layer(e, e->wdown, l); E.sc_ = sc_layer(e, e->wdown, l); E.grp_ = e->cfg.group; E.cols_ = e->I_loc;
+            E.x = e->swi; E.nrows = d;
+            if (tp) { E.resid = nullptr; E.y = e->part_b; } else { E.resid = e->h; E.y = e->x; }
+            return launch_policy<WD>(e, E, (d + 1) / 2);
+        }
+        case K_CLS: {
+            ClsPolicy<WD> F{};
+            F.W_ = reinterpret_cast<const uint8_t*>(e->emb.w) + wbytes(e->cfg.w_dtype, (int64_t)e->v0 * d);
+            F.sc_ = e->emb.sc ? e->emb.sc + (int64_t)e->v0 * d / e->cfg.group : nullptr;
+            F.grp_ = e->cfg.group; F.cols_ = d;
+            if (tp) { F.x = e->h; F.add = e->part_b; F.sum_out = e->x; } else { F.x = e->x; F.add = nullptr; F.sum_out = nullptr; }
+            F.norm_w = e->norms + (int64_t)(2 * L) * d; F.eps = s.eps; F.logits = e->logits; F.nrows = e->V_loc; F.row0 = e->v0;
+            F.blk_val = e->blk_val; F.blk_idx = e->blk_idx; F.st = e->state; F.prompt = e->prompt_dev; F.history = e->history_dev;
+            F.single_rank = (tp || l < 0) ? 0 : 1;   // l < 0: timing-only launch, leave the step state alone
+            return launch_policy<WD>(e, F, (e->V_loc + 1) / 2, e->cls_grid);
+        }
+        default: SLLM_REQUIRE(false, SLLM_EINVAL, "unknown kernel kind %d", kind);
     }
-    // residual-stream bookkeeping under TP: after the all-reduce of a row-parallel GEMV the partial sum sits
-    // in part_*; the NEXT kernel's prologue adds it to the residual (and CTA 0 stores the sum).
+}
+
+template <int WD>
+static int enqueue_fused_step(sllm_engine* e) {
+    const int d = e->d, L = e->L;
+    const bool tp = e->tp > 1;
+#define STEP(kind, layer) do { if (int rc = enqueue_kernel<WD>(e, kind, layer)) return rc; } while (0)
+    STEP(K_EMBED, 0);
     for (int l = 0; l < L; ++l) {
-        QkvPolicy<WD> A{};
-        A.W_ = mat_layer(e, e->wqkv, l); A.sc_ = sc_layer(e, e->wqkv, l); A.grp_ = e->cfg.group; A.cols_ = d;
-        if (tp && l > 0) { A.x = e->h; A.add = e->part_b; A.sum_out = e->x; } else { A.x = e->x; A.add = nullptr; A.sum_out = nullptr; }
-        A.norm_w = e->norms + (int64_t)(2 * l) * d; A.eps = s.eps; A.pos_dev = pos_dev; A.sin_t = e->sin_t; A.cos_t = e->cos_t;
-        A.q_out = e->q; A.k_cache = kv_layer(e, e->key_cache, l); A.v_cache = kv_layer(e, e->value_cache, l);
-        A.kv_dtype = e->cfg.kv_dtype; A.q_dim = e->q_loc; A.kv_dim = e->kv_loc; A.hd = e->hd;
-        if (int rc = launch_policy<WD>(e, A, (e->q_loc + 2 * e->kv_loc) / 2)) return rc;
-
-        if (int rc = mha_decode_dispatch(e->q, e->key_cache, e->value_cache, e->cfg.kv_dtype, e->att, e->mha_ws, l, pos_dev, 0, e->S,
-                                         e->hd, e->H_loc, e->KVH_loc, e->stream, e->pdl)) return rc;
-        count_launch(e);
-
-        ResidualPolicy<WD> C{};
-        C.W_ = mat_layer(e, e->wo, l); C.sc_ = sc_layer(e, e->wo, l); C.grp_ = e->cfg.group; C.cols_ = e->q_loc;
-        C.x = e->att; C.nrows = d;
-        if (tp) { C.resid = nullptr; C.y = e->part_a; } else { C.resid = e->x; C.y = e->h; }
-        if (int rc = launch_policy<WD>(e, C, (d + 1) / 2)) return rc;
+        STEP(K_QKV, l);
+        STEP(K_MHA, l);
+        STEP(K_WO, l);
         if (tp) { SLLM_NCCL(ncclAllReduce(e->part_a, e->part_a, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
-
-        GateUpPolicy<WD> D{};
-        D.W_ = mat_layer(e, e->wug, l); D.sc_ = sc_layer(e, e->wug, l); D.grp_ = e->cfg.group; D.cols_ = d;
-        // TP: the residual stream entering this layer is x (layer 0) or h+part_b, which kernel A stored in x
-        if (tp) { D.h = e->x; D.add = e->part_a; D.sum_out = e->h; } else { D.h = e->h; D.add = nullptr; D.sum_out = nullptr; }
-        D.norm_w = e->norms + (int64_t)(2 * l + 1) * d; D.eps = s.eps; D.s_out = e->swi; D.inter = e->I_loc;
-        if (int rc = launch_policy<WD>(e, D, e->I_loc)) return rc;
-
-        ResidualPolicy<WD> E{};
-        E.W_ = mat_layer(e, e->wdown, l); E.sc_ = sc_layer(e, e->wdown, l); E.grp_ = e->cfg.group; E.cols_ = e->I_loc;
-        E.x = e->swi; E.nrows = d;
-        if (tp) { E.resid = nullptr; E.y = e->part_b; } else { E.resid = e->h; E.y = e->x; }
-        if (int rc = launch_policy<WD>(e, E, (d + 1) / 2)) return rc;
+        STEP(K_GATEUP, l);
+        STEP(K_DOWN, l);
         if (tp) { SLLM_NCCL(ncclAllReduce(e->part_b, e->part_b, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
     }
-    ClsPolicy<WD> F{};
-    F.W_ = reinterpret_cast<const uint8_t*>(e->emb.w) + wbytes(e->cfg.w_dtype, (int64_t)e->v0 * d);
-    F.sc_ = e->emb.sc ? e->emb.sc + (int64_t)e->v0 * d / e->cfg.group : nullptr;
-    F.grp_ = e->cfg.group; F.cols_ = d;
-    if (tp) { F.x = e->h; F.add = e->part_b; F.sum_out = e->x; } else { F.x = e->x; F.add = nullptr; F.sum_out = nullptr; }
-    F.norm_w = e->norms + (int64_t)(2 * L) * d; F.eps = s.eps; F.logits = e->logits; F.nrows = e->V_loc; F.row0 = e->v0;
-    F.blk_val = e->blk_val; F.blk_idx = e->blk_idx; F.st = e->state; F.prompt = e->prompt_dev; F.history = e->history_dev;
-    F.single_rank = tp ? 0 : 1;
-    if (int rc = launch_policy<WD>(e, F, (e->V_loc + 1) / 2, e->cls_grid)) return rc;
+    STEP(K_CLS, 0);
+#undef STEP
     if (tp) {
         tp_pack_kernel<<<1, 32, 0, e->stream>>>(e->blk_val, e->blk_idx, e->cls_grid, e->tp_pairs + 2 * e->rank);
         count_launch(e);
@@ -480,6 +512,10 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     e->cfg.tp_size = tp;
     if (e->cfg.w_dtype != SLLM_INT8) e->cfg.group = e->cfg.group > 0 ? e->cfg.group : 64;
     e->stream = as_stream(stream);
+    if (!e->stream) {  // the legacy default stream cannot be captured into a graph: own a stream instead
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete e; set_error("cudaStreamCreate failed"); return SLLM_ENOMEM; }
+        e->own_stream = true;
+    }
     e->fused = !(cfg->flags & SLLM_ENGINE_UNFUSED);
     e->use_graph = e->fused && !(cfg->flags & SLLM_ENGINE_NO_GRAPH);
     e->pdl = e->fused && !(cfg->flags & SLLM_ENGINE_NO_PDL);
@@ -520,6 +556,7 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->comm) ncclCommDestroy(e->comm);
     if (e->h_state) cudaFreeHost(e->h_state);
     if (e->arena) cudaFree(e->arena);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -678,6 +715,33 @@ int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos) {
     const double bytes = bw * mats + 4.0 * (2 * L + 1) * d + bw * d + (double)e->esz_kv * 2 * L * e->kv_loc * (pos + 1) +
                          (double)e->esz_kv * 2 * L * e->kv_loc;
     return (int64_t)bytes;
+}
+
+int sllm_engine_enqueue_kernel(sllm_engine* e, int32_t kind, int32_t layer) {
+    SLLM_REQUIRE(e && e->weights_loaded && e->fused, SLLM_ESTATE, "enqueue_kernel needs a fused engine with weights");
+    SLLM_REQUIRE(layer >= 0 && layer < e->L, SLLM_EINVAL, "layer %d outside [0,%d)", layer, e->L);
+    const int l = (kind == K_CLS) ? -1 : layer;
+    switch (e->cfg.w_dtype) {
+        case SLLM_F32: return enqueue_kernel<SLLM_F32>(e, kind, l);
+        case SLLM_BF16: return enqueue_kernel<SLLM_BF16>(e, kind, l);
+        default: return enqueue_kernel<SLLM_INT8>(e, kind, l);
+    }
+}
+
+int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos) {
+    if (!e) return 0;
+    const double bw = e->cfg.w_dtype == SLLM_F32 ? 4.0 : e->cfg.w_dtype == SLLM_BF16 ? 2.0 : 1.0 + 4.0 / e->cfg.group;
+    const double d = e->d;
+    switch (kind) {
+        case K_EMBED: return (int64_t)(bw * d);
+        case K_QKV: return (int64_t)(bw * (e->q_loc + 2.0 * e->kv_loc) * d + 4.0 * d + e->esz_kv * 2.0 * e->kv_loc);
+        case K_MHA: return (int64_t)(e->esz_kv * 2.0 * e->kv_loc * (pos + 1));
+        case K_WO: return (int64_t)(bw * d * e->q_loc);
+        case K_GATEUP: return (int64_t)(bw * 2.0 * e->I_loc * d + 4.0 * d);
+        case K_DOWN: return (int64_t)(bw * d * e->I_loc);
+        case K_CLS: return (int64_t)(bw * e->V_loc * d + 4.0 * d);
+        default: return 0;
+    }
 }
 
 int32_t sllm_engine_step_launches(const sllm_engine* e) { return e ? e->step_launches : 0; }

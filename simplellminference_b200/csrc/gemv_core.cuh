@@ -28,7 +28,10 @@ template <> struct WInfo<SLLM_INT8> { static constexpr int E = 16; static conste
 
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = kGemvThreads / 32;
-constexpr int kGemvU = 4;  // 16-byte loads in flight per row per lane
+#ifndef SLLM_GEMV_U
+#define SLLM_GEMV_U 4
+#endif
+constexpr int kGemvU = SLLM_GEMV_U;  // 16-byte loads in flight per row per lane
 
 __host__ __device__ inline size_t gemv_smem_bytes(int cols) { return (size_t)cols * sizeof(float) + 64 * sizeof(float); }
 
@@ -248,8 +251,10 @@ __device__ __forceinline__ void gemv_body(Policy& pol) {
 
 // grid size for a GEMV-shaped kernel: a multiple of the SM count, no more CTAs than there are warps' worth
 // of units.
+extern int g_tune_ctas_per_sm;   // 0 = use the caller's value (sllm_tune)
 inline int gemv_grid(int units, int ctas_per_sm) {
     const int sms = sm_count();
+    if (g_tune_ctas_per_sm > 0) ctas_per_sm = g_tune_ctas_per_sm;
     const int need = (units + kGemvWarps - 1) / kGemvWarps;
     int g = sms * ctas_per_sm;
     if (need < g) g = need;

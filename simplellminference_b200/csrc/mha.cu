@@ -58,9 +58,11 @@ __host__ __device__ inline MhaSmem mha_smem_layout(int hd, int g, int esz) {
     off = (off + 15) & ~(size_t)15;
     L.k_off = off; off += (size_t)kMhaStages * kMhaTile * L.stride;
     L.v_off = off; off += (size_t)kMhaStages * kMhaTile * L.stride;
-    // cross-stripe reduction scratch for O reuses the K stages (needs stripes*g*hd*4 <= stages*T*stride: checked on host)
+    // the cross-stripe reduction scratch for O ([stripes][g][hd] fp32) reuses the K/V stages once they are drained
     L.o_off = L.k_off;
-    L.total = off;
+    const size_t stripes = kMhaThreads / (size_t)(hd * esz / 16);
+    const size_t o_end = L.o_off + stripes * g * hd * 4;
+    L.total = off > o_end ? off : o_end;
     return L;
 }
 
@@ -310,9 +312,6 @@ static int launch_mha(const float* q, const void* kc, const void* vc, float* out
                       int pos, int max_len, int hd, int kv_heads, cudaStream_t st, bool pdl) {
     const int nsplit = mha_nsplit(kv_heads, max_len);
     const MhaSmem L = mha_smem_layout(hd, G, KvInfo<KVD>::ESZ);
-    const int nstripes = kMhaThreads / (hd * KvInfo<KVD>::ESZ / 16);
-    SLLM_REQUIRE((size_t)nstripes * G * hd * 4 <= (size_t)kMhaStages * kMhaTile * L.stride, SLLM_ENOTSUP,
-                 "mha: reduction scratch does not fit (hd=%d g=%d)", hd, G);
     SLLM_REQUIRE(L.total <= (size_t)smem_optin_bytes(), SLLM_ENOTSUP, "mha: tile does not fit shared memory (hd=%d)", hd);
     static size_t configured = 0;
     if (L.total > 48 * 1024 && L.total > configured) {
@@ -345,9 +344,13 @@ int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_d
     switch (g) {
         SLLM_MHA_CASE(1)
         SLLM_MHA_CASE(2)
+        SLLM_MHA_CASE(3)
         SLLM_MHA_CASE(4)
+        SLLM_MHA_CASE(5)
+        SLLM_MHA_CASE(6)
+        SLLM_MHA_CASE(7)
         SLLM_MHA_CASE(8)
-        default: SLLM_REQUIRE(false, SLLM_ENOTSUP, "mha: heads/kv_heads=%d not in {1,2,4,8}", g);
+        default: SLLM_REQUIRE(false, SLLM_ENOTSUP, "mha: heads/kv_heads=%d > 8 query heads per KV head", g);
     }
 #undef SLLM_MHA_CASE
 }

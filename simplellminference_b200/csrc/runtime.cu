@@ -8,6 +8,7 @@ namespace sllm {
 
 static thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+int g_tune_ctas_per_sm = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -49,6 +50,13 @@ extern "C" {
 
 const char* sllm_last_error(void) { return sllm::g_err; }
 int sllm_abi_version(void) { return 1; }
+
+int sllm_tune(int32_t key, int32_t value) {
+    switch (key) {
+        case 0: sllm::g_tune_ctas_per_sm = value; return SLLM_OK;
+        default: sllm::set_error("unknown tunable %d", key); return SLLM_EINVAL;
+    }
+}
 
 int sllm_device_info(int32_t* sms, int32_t* smem, size_t* total, size_t* free_) {
     int n = 0;

@@ -28,9 +28,11 @@ class Engine:
         cfg = _lib.EngineConfig(_lib.Shape(shape.vocab, shape.head_dim, shape.hidden, shape.kv_hidden, shape.inter, shape.max_len,
                                            shape.layers, shape.heads, shape.kv_heads, shape.eps, shape.theta),
                                 w_dtype, kv_dtype, group, tp_rank, tp_size, flags)
-        self.stream = stream if stream is not None else torch.cuda.current_stream()
+        # no stream given -> the engine owns one (the legacy default stream cannot be graph-captured); every
+        # host-visible call below ends with a synchronise of that stream, so torch reads that follow are safe
+        self.stream = stream
         h = C.c_void_p()
-        _lib.check(self.lib.sllm_engine_create(C.byref(cfg), self.stream.cuda_stream, C.byref(h)))
+        _lib.check(self.lib.sllm_engine_create(C.byref(cfg), stream.cuda_stream if stream is not None else None, C.byref(h)))
         self.h = h
         self._pin_tokens = None
 
@@ -102,6 +104,14 @@ class Engine:
         # wrap device memory without copying: go through __cuda_array_interface__
         t = torch.as_tensor(_CudaView(ptr.value, n.value, tdt), device="cuda")
         return t.view(torch.bfloat16) if tdt == torch.bfloat16 else t
+
+    KERNELS = dict(embed=0, qkv=1, mha=2, wo=3, gate_up=4, down=5, cls=6)
+
+    def enqueue_kernel(self, kind: str, layer: int) -> None:
+        _lib.check(self.lib.sllm_engine_enqueue_kernel(self.h, self.KERNELS[kind], layer))
+
+    def kernel_bytes(self, kind: str, pos: int) -> int:
+        return int(self.lib.sllm_engine_kernel_bytes(self.h, self.KERNELS[kind], pos))
 
     def step_bytes(self, pos: int) -> int:
         return int(self.lib.sllm_engine_step_bytes(self.h, pos))

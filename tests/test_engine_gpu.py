@@ -1,0 +1,137 @@
+"""GPU parity tests, model level: the engine (fused CUDA-graph path, and the op-by-op path) against the golden
+token streams/logits produced by the unmodified reference, and against the CPU oracle on fresh seeds.
+
+Decode tolerance: token sequence IDENTICAL; max|dlogit| <= 3e-4 * max(1, max|logit|) at the end of a greedy run
+of up to 256 tokens, 1e-4 for a single forward from oracle-identical history; and the oracle's top1-top2 margin
+must dwarf the observed logit error so identity is meaningful. Why 3e-4 and not SURVEY.md's 1e-4: everything is
+fp32 on both sides and only the summation order differs, but the synthetic projections have gain 4
+(std 4/sqrt(fan_in)), which amplifies rounding noise layer by layer. The yardstick is the reference against
+ITSELF: its -O2 -ffp-contract=off and -O3 -march=x86-64-v3 (FMA-contracted) builds differ by 8.1e-5 * max|logit|
+in the final logits of the cfg2 run below (measured in the dev container, see DESIGN.md "Tolerances").
+Residual stream / KV rows are held to the same relative bound against their own max magnitude."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import oracle_shape
+from simplellminference_b200.config import F32, BF16, INT8, PRESETS, ModelShape
+from simplellminference_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+PRESET_OF = {"cfg1_stories15M": "stories15M", "cfg2_stories110M": "stories110M", "tiny_gqa": "tiny_gqa",
+             "tiny_gqa_bf16w": "tiny_gqa", "tiny_gqa_int8w": "tiny_gqa", "tiny_mha_hd48": "tiny_mha_hd48"}
+
+
+def logit_tol(want):
+    return 3e-4 * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
+@pytest.mark.parametrize("mode", ["fused_graph", "fused_nograph_nopdl", "unfused"])
+def test_golden_models(golden_models, name, mode):
+    """Token streams and final logits recorded from the reference itself (tests/golden/models_ref.npz)."""
+    prompt, n_total, wd = mg.MODEL_RUNS[name]
+    ms = PRESETS[PRESET_OF[name]]
+    kw = dict(fused_graph={}, fused_nograph_nopdl=dict(graph=False, pdl=False), unfused=dict(fused=False))[mode]
+    eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
+    toks = eng.greedy(prompt, n_total)
+    want = golden_models[name + "/tokens"]
+    assert np.array_equal(toks, want), (np.flatnonzero(toks != want)[:5], toks[:8], want[:8])
+    logits = eng.buffer("model_pred").cpu().numpy()
+    want_l = golden_models[name + "/last_logits"]
+    err = float(np.abs(logits - want_l).max())
+    assert err <= logit_tol(want_l), err
+    srt = np.sort(want_l)
+    assert srt[-1] - srt[-2] >= 20 * err or err < 1e-5
+    kv = ms.kv_hidden
+    k_last = eng.buffer("key_cache")[(n_total - 2) * kv:(n_total - 1) * kv].float().cpu().numpy()
+    want_k = golden_models[name + "/k_l0_last"]
+    assert float(np.abs(k_last - want_k).max()) <= logit_tol(want_k)
+    x_last, want_x = eng.buffer("emb_output").cpu().numpy(), golden_models[name + "/x_last"]
+    assert float(np.abs(x_last - want_x).max()) <= logit_tol(want_x)
+    eng.close()
+
+
+def test_blob_loader_equals_synthetic(port):
+    """Loading the reference-format fp32 blob from the host == generating on the device (all three dtypes)."""
+    ms = PRESETS["tiny_gqa"]
+    for wd in (F32, BF16, INT8):
+        blob = port.fill_blob(oracle_shape(ms), 1234, F32)       # raw fp32: the engine converts
+        a = Engine(ms, w_dtype=wd, kv_dtype=F32).load_blob(blob)
+        b = Engine(ms, w_dtype=wd, kv_dtype=F32).load_synthetic(1234)
+        for bid in (100, 101, 102, 103, 104, 105):
+            ta, tb = a.buffer(bid), b.buffer(bid)
+            assert torch.equal(ta.view(torch.uint8) if ta.dtype == torch.bfloat16 else ta, tb.view(torch.uint8) if tb.dtype == torch.bfloat16 else tb), (wd, bid)
+        assert np.array_equal(a.greedy([1, 2, 3], 20), b.greedy([1, 2, 3], 20))
+        a.close(); b.close()
+
+
+def test_forward_api_matches_oracle_per_position(port):
+    """LlamaModel::forward semantics: explicit (token, pos), logits back on the host, every position checked."""
+    ms = PRESETS["tiny_mha_hd48"]
+    blob = port.fill_blob(oracle_shape(ms), 42)
+    om = port.model(oracle_shape(ms), blob)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_blob(blob)
+    tok = 5
+    for pos in range(ms.max_len):
+        want = om.forward(tok, pos)
+        got, nxt = eng.forward(tok, pos)
+        assert float(np.abs(got - want).max()) <= 1e-4 * max(1.0, float(np.abs(want).max()))
+        assert nxt == int(np.argmax(want))
+        tok = nxt
+    eng.close()
+
+
+@pytest.mark.parametrize("wd,kvd", [(BF16, BF16), (INT8, BF16), (F32, BF16)])
+def test_bf16_kv_cache_variant(port, wd, kvd):
+    """bf16 KV cache has no reference implementation: its definition is the oracle with cache rows rounded to
+    bf16 (orc_set_kv_bf16). Tokens identical, logits within the decode tolerance."""
+    ms = PRESETS["tiny_gqa"]
+    blob = port.fill_blob(oracle_shape(ms), 7, wd, 64)
+    om = port.model(oracle_shape(ms), blob, kv_bf16=True)
+    want, want_l = om.greedy([1, 9], 46)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd).load_synthetic(7)
+    got = eng.greedy([1, 9], 46)
+    logits = eng.buffer("model_pred").cpu().numpy()
+    err = float(np.abs(logits - want_l).max())
+    srt = np.sort(want_l)
+    assert np.array_equal(got, want), (err, srt[-1] - srt[-2])
+    assert err <= 5e-3 * max(1.0, float(np.abs(want_l).max())), err   # a cache value on a bf16 rounding boundary may flip
+    eng.close()
+
+
+def test_full_context_and_state_api(port):
+    """Run to the last position of the parity domain (pos <= S - H/KVH); device-resident stepping API."""
+    ms = PRESETS["tiny_gqa"]
+    blob = port.fill_blob(oracle_shape(ms), 11)
+    want, _ = port.model(oracle_shape(ms), blob).greedy([3], 47)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_synthetic(11)
+    eng.set_state(3, 0)
+    eng.enqueue_steps(20)
+    eng.enqueue_steps(26)
+    assert np.array_equal(eng.read_tokens(46), want)
+    with pytest.raises(Exception):
+        eng.enqueue_steps(10)     # would overrun max_len
+    assert eng.step_launches == 2 + 5 * ms.layers
+    eng.close()
+
+
+def test_medium_shape_tokens(port):
+    """A GQA shape with the production head_dim (128) and a long-ish context, bf16 weights, fp32 KV."""
+    ms = ModelShape(4096, 128, 1024, 256, 2816, 160, 4, 8, 2)
+    blob = port.fill_blob(oracle_shape(ms), 3, BF16)
+    want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1).greedy(list(range(1, 33)), 150)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32).load_synthetic(3)
+    got = eng.greedy(list(range(1, 33)), 150)
+    assert np.array_equal(got, want)
+    err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
+    assert err <= logit_tol(want_l), err
+    eng.close()
