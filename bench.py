@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
     return ap.parse_args()
@@ -218,7 +218,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
-                 graph=not (args.no_graph or args.unfused), pdl=not args.no_pdl)
+                 graph=not (args.no_graph or args.unfused), pdl=args.pdl)
     eng.load_synthetic(1234)
     if world > 1:
         eng.init_comm(dist)
@@ -338,7 +338,7 @@ def run_ours(args):
         "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
         "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
-        "mode": {"fused": not args.unfused, "graph": not (args.no_graph or args.unfused), "pdl": not args.no_pdl},
+        "mode": {"fused": not args.unfused, "graph": not (args.no_graph or args.unfused), "pdl": args.pdl},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -146,7 +146,8 @@ typedef struct {
 
 #define SLLM_ENGINE_UNFUSED 1u   /* run the 13-ops-per-layer sequence of the reference instead of fused kernels */
 #define SLLM_ENGINE_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
-#define SLLM_ENGINE_NO_PDL 4u    /* no programmatic dependent launch between the kernels of a step */
+#define SLLM_ENGINE_PDL 4u       /* programmatic dependent launch between the kernels of a step (measured slower
+                                    inside a CUDA graph on B200 than plain graph edges: off by default) */
 #define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
 
 typedef struct sllm_engine sllm_engine;

@@ -130,7 +130,7 @@ static void layout(sllm_engine* e) {
     e->part_a = carve<float>(e, 4 * (size_t)d);
     e->part_b = carve<float>(e, 4 * (size_t)d);
     e->mha_ws = carve<void>(e, mha_workspace_bytes(e->H_loc, e->hd, e->S));
-    e->cls_grid = gemv_grid((e->V_loc + 1) / 2, 4);
+    e->cls_grid = gemv_grid((e->V_loc + 1) / 2, 2);
     e->blk_val = carve<float>(e, 4 * (size_t)(e->cls_grid + 1));
     e->blk_idx = carve<int32_t>(e, 4 * (size_t)(e->cls_grid + 1));
     e->tp_pairs = carve<float>(e, 8 * (size_t)std::max(1, e->tp));
@@ -154,7 +154,7 @@ static int launch_policy(sllm_engine* e, Policy& p, int units, int grid_override
         SLLM_CUDA(cudaFuncSetAttribute(fused_gemv_kernel<WD, Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = grid_override ? grid_override : gemv_grid(units, 4);
+    const int grid = grid_override ? grid_override : gemv_grid(units, 2);
     LaunchCfg lc(dim3(grid), dim3(kGemvThreads), smem, e->stream, e->pdl);
     SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, fused_gemv_kernel<WD, Policy>, p));
     g_launches++;
@@ -518,7 +518,7 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     }
     e->fused = !(cfg->flags & SLLM_ENGINE_UNFUSED);
     e->use_graph = e->fused && !(cfg->flags & SLLM_ENGINE_NO_GRAPH);
-    e->pdl = e->fused && !(cfg->flags & SLLM_ENGINE_NO_PDL);
+    e->pdl = e->fused && (cfg->flags & SLLM_ENGINE_PDL);
     e->d = s.hidden; e->hd = s.head_dim; e->L = s.layers; e->S = s.max_len; e->V = s.vocab; e->H = s.heads; e->KVH = s.kv_heads; e->I = s.inter;
     e->tp = tp; e->rank = cfg->tp_rank;
     e->H_loc = s.heads / tp; e->KVH_loc = s.kv_heads / tp; e->q_loc = e->H_loc * s.head_dim; e->kv_loc = e->KVH_loc * s.head_dim;

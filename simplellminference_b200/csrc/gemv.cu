@@ -42,7 +42,7 @@ static int launch_plain(const PlainPolicy& p, cudaStream_t st) {
     }
     PlainPolicyT<WD> pt;
     static_cast<PlainPolicy&>(pt) = p;
-    const int grid = gemv_grid((p.nrows + 1) / 2, 4);
+    const int grid = gemv_grid((p.nrows + 1) / 2, 2);
     gemv_plain_kernel<WD><<<grid, kGemvThreads, smem, st>>>(pt);
     g_launches++;
     SLLM_LAUNCH_CHECK();

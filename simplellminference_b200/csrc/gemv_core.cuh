@@ -29,7 +29,7 @@ template <> struct WInfo<SLLM_INT8> { static constexpr int E = 16; static conste
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = kGemvThreads / 32;
 #ifndef SLLM_GEMV_U
-#define SLLM_GEMV_U 4
+#define SLLM_GEMV_U 8
 #endif
 constexpr int kGemvU = SLLM_GEMV_U;  // 16-byte loads in flight per row per lane
 
@@ -219,7 +219,9 @@ __device__ __forceinline__ void gemv_body(Policy& pol) {
         pol.rows(unit, r0, r1);
         load_batch<WD>(cur, Wv + r0 * nchunks, Wv + r1 * nchunks, Sc + r0 * groups_per_row, Sc + r1 * groups_per_row, cpg, 0, lane, nchunks);
     }
+#ifdef SLLM_PDL_EARLY
     pdl_launch_dependents();
+#endif
     pdl_wait();
     pol.stage(xs, red);
     __syncthreads();
@@ -247,6 +249,11 @@ __device__ __forceinline__ void gemv_body(Policy& pol) {
         a1 = warp_sum(a1);
         if (lane == 0) pol.emit(this_unit, a0, a1);
     }
+#ifndef SLLM_PDL_EARLY
+    // late trigger: this warp has issued all of its loads; once every CTA got here (or exited) the next
+    // kernel's CTAs may take over the freed SM slots and start prefetching ITS weights
+    pdl_launch_dependents();
+#endif
 }
 
 // grid size for a GEMV-shaped kernel: a multiple of the SM count, no more CTAs than there are warps' worth

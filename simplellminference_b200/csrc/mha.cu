@@ -132,7 +132,6 @@ mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, c
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pdl_launch_dependents();
     pdl_wait();  // q and the newest cache row come from the previous kernel; pos from the previous step
     const int pos = pos_dev ? *pos_dev : pos_val;
     const int n = pos + 1;
@@ -250,6 +249,7 @@ mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, c
         }
     }
 
+    pdl_launch_dependents();  // late trigger: all of this CTA's HBM reads are done
     // ---- reduce the stripes' accumulators through shared memory (reuses the K stages)
     float* o_s = reinterpret_cast<float*>(smem + L.o_off);  // [nstripes][G][hd]
     if (pv_active) {

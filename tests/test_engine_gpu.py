@@ -35,12 +35,12 @@ def logit_tol(want):
 
 
 @pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
-@pytest.mark.parametrize("mode", ["fused_graph", "fused_nograph_nopdl", "unfused"])
+@pytest.mark.parametrize("mode", ["fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
 def test_golden_models(golden_models, name, mode):
     """Token streams and final logits recorded from the reference itself (tests/golden/models_ref.npz)."""
     prompt, n_total, wd = mg.MODEL_RUNS[name]
     ms = PRESETS[PRESET_OF[name]]
-    kw = dict(fused_graph={}, fused_nograph_nopdl=dict(graph=False, pdl=False), unfused=dict(fused=False))[mode]
+    kw = dict(fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
     toks = eng.greedy(prompt, n_total)
     want = golden_models[name + "/tokens"]

@@ -12,7 +12,7 @@ ap.add_argument("--config", default="llama2-7b")
 ap.add_argument("--ctas", default="0")
 ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--wdtype", default="bf16")
-ap.add_argument("--no-pdl", action="store_true")
+ap.add_argument("--pdl", action="store_true")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 wd = dict(f32=F32, bf16=BF16, int8=INT8)[a.wdtype]
@@ -20,7 +20,7 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 lib = _lib.load()
 for ctas in [int(c) for c in a.ctas.split(",")]:
     lib.sllm_tune(0, ctas)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=not a.no_pdl).load_synthetic(1)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=a.pdl).load_synthetic(1)
     eng.set_state(1, a.pos)
     res = {"ctas_per_sm": ctas, "lib": os.path.basename(_lib.LIB_PATH)}
     for kind in ("qkv", "mha", "wo", "gate_up", "down"):
