@@ -3,7 +3,7 @@
  * B200-native (sm_100a) replacement for the transformer forward hot path of Boundwhd/SimpleLLMInference.
  * Plain pointers and sizes only: no C++ types, no torch types, no CUDA headers needed to include this file.
  * The reference has no FFI of its own (it is one C++ program); its hot-path boundary is the set of free
- * functions kernel::*_cuda (include/kernel/cuda/*.cuh) that the op layers call (source/op/*.cpp) plus
+ * functions kernel::<op>_kernel_cuda (include/kernel/cuda/<op>_kernel.cuh) that the op layers call (source/op/<op>.cpp) plus
  * model::LlamaModel::forward (source/model/model.cpp:40-140). Each entry point below names the reference
  * interface it replaces. The C++ host mirror in simplellminference_b200/host/ (mem::Tensor, op::*Layer,
  * kernel::*_cuda, model::LlamaModel) is a thin layer over exactly these functions; INTEGRATION.md shows the
@@ -148,6 +148,9 @@ typedef struct {
 #define SLLM_ENGINE_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
 #define SLLM_ENGINE_PDL 4u       /* programmatic dependent launch between the kernels of a step (measured slower
                                     inside a CUDA graph on B200 than plain graph edges: off by default) */
+#define SLLM_ENGINE_MEGAKERNEL 16u /* whole decode step as ONE persistent cooperative kernel whose TMA weight rings
+                                    keep streaming across phases (single GPU; shapes it cannot take fall back to the
+                                    per-kernel fused path — sllm_engine_mode() tells which one runs) */
 #define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
 
 typedef struct sllm_engine sllm_engine;
@@ -205,6 +208,13 @@ int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos);
  * B(p): weights it streams, norm vector, KV rows read/written). */
 int sllm_engine_enqueue_kernel(sllm_engine* e, int32_t kind, int32_t layer);
 int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos);
+/* layout of the key_cache / value_cache buffers: 0 = [layers][max_len][kv_heads*head_dim] (the reference's,
+ * model.cpp:264-265), 1 = head-major [layers][kv_heads][max_len][head_dim] (megakernel mode: a tile of positions
+ * of one head is one contiguous TMA copy). Weight matrices of a megakernel engine are stored tiled (buffer ids
+ * 100-105 are then opaque). */
+int32_t sllm_engine_kv_layout(const sllm_engine* e);
+/* which decode path this engine runs: "megakernel", "fused+graph", "fused", "unfused", ... (static string) */
+const char* sllm_engine_mode(const sllm_engine* e);
 /* number of kernel launches (graph kernel nodes) one decode step issues on this rank */
 int32_t sllm_engine_step_launches(const sllm_engine* e);
 /* total launches issued by this engine since creation */

@@ -29,7 +29,7 @@ class EngineConfig(C.Structure):
                 ("tp_rank", C.c_int32), ("tp_size", C.c_int32), ("flags", C.c_int32)]
 
 
-ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE = 1, 2, 4, 8
+ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE, ENGINE_MEGAKERNEL = 1, 2, 4, 8, 16
 
 _P = C.c_void_p
 _I = C.c_int32
@@ -73,6 +73,8 @@ SIGNATURES = {
     "sllm_engine_step_bytes": (_L, [_P, _I]),
     "sllm_engine_enqueue_kernel": (C.c_int, [_P, _I, _I]),
     "sllm_engine_kernel_bytes": (_L, [_P, _I, _I]),
+    "sllm_engine_kv_layout": (_I, [_P]),
+    "sllm_engine_mode": (C.c_char_p, [_P]),
     "sllm_engine_step_launches": (_I, [_P]),
     "sllm_engine_total_launches": (_L, [_P]),
 }

@@ -16,7 +16,7 @@
 #include <cstring>
 #include <vector>
 
-#include "decode_fused.cuh"
+#include "megakernel.cuh"
 
 namespace sllm {
 int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_dtype, float* out, void* ws, int layer,
@@ -37,9 +37,12 @@ using namespace sllm;
     } while (0)
 
 struct Matrix {          // a weight matrix (or stack of per-layer matrices) in storage dtype
-    void* w = nullptr;
+    void* w = nullptr;   // final location (row-major; TILED in megakernel mode, see megakernel.cuh)
+    void* rm = nullptr;  // megakernel mode, during loading only: temporary row-major staging copy
     float* sc = nullptr; // int8 group scales
     int64_t rows = 0, cols = 0;   // per layer
+    int64_t layers = 1;
+    int kind = 0;        // PH_* pairing rule of the tiled layout
 };
 
 struct sllm_engine {
@@ -47,6 +50,13 @@ struct sllm_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     bool fused = true, use_graph = true, pdl = true;
+    bool mega = false;            // persistent one-launch-per-token kernel (megakernel.cu)
+    MegaPlan mega_plan_{};
+    MegaParams mega_params{};
+    PhaseDesc* phases_dev = nullptr;
+    float* mega_att = nullptr;
+    unsigned* bar_counter = nullptr;
+    unsigned long long* trace = nullptr;   // development aid: per-CTA phase timeline of the megakernel
     // local (this rank's) dimensions
     int d = 0, hd = 0, L = 0, S = 0, V = 0, H = 0, KVH = 0, I = 0;
     int tp = 1, rank = 0;
@@ -94,10 +104,14 @@ static T* carve(sllm_engine* e, size_t bytes) {
     return e->arena ? reinterpret_cast<T*>(e->arena + off) : nullptr;
 }
 
-static void carve_matrix(sllm_engine* e, Matrix& m, int64_t layers, int64_t rows, int64_t cols) {
+static void carve_matrix(sllm_engine* e, Matrix& m, int64_t layers, int64_t rows, int64_t cols, int kind) {
     m.rows = rows;
     m.cols = cols;
-    m.w = carve<void>(e, wbytes(e->cfg.w_dtype, layers * rows * cols));
+    m.layers = layers;
+    m.kind = kind;
+    const size_t bytes = e->mega ? (size_t)layers * mega_matrix_bytes((int)rows, (int)cols, kind, e->cfg.w_dtype)
+                                 : wbytes(e->cfg.w_dtype, layers * rows * cols);
+    m.w = carve<void>(e, bytes);
     m.sc = (e->cfg.w_dtype == SLLM_INT8) ? carve<float>(e, sizeof(float) * (size_t)(layers * rows * cols / e->cfg.group)) : nullptr;
 }
 
@@ -105,12 +119,12 @@ static void carve_matrix(sllm_engine* e, Matrix& m, int64_t layers, int64_t rows
 static void layout(sllm_engine* e) {
     e->arena_used = 0;
     const int64_t d = e->d, L = e->L, S = e->S;
-    carve_matrix(e, e->emb, 1, e->V, d);
+    carve_matrix(e, e->emb, 1, e->V, d, PH_CLS);
     e->norms = carve<float>(e, sizeof(float) * (size_t)((2 * L + 1) * d));
-    carve_matrix(e, e->wqkv, L, e->q_loc + 2 * e->kv_loc, d);
-    carve_matrix(e, e->wo, L, d, e->q_loc);
-    carve_matrix(e, e->wug, L, 2 * e->I_loc, d);
-    carve_matrix(e, e->wdown, L, d, e->I_loc);
+    carve_matrix(e, e->wqkv, L, e->q_loc + 2 * e->kv_loc, d, PH_QKV);
+    carve_matrix(e, e->wo, L, d, e->q_loc, PH_WO);
+    carve_matrix(e, e->wug, L, 2 * e->I_loc, d, PH_GATEUP);
+    carve_matrix(e, e->wdown, L, d, e->I_loc, PH_DOWN);
     e->key_cache = carve<void>(e, (size_t)e->esz_kv * L * S * e->kv_loc);
     e->value_cache = carve<void>(e, (size_t)e->esz_kv * L * S * e->kv_loc);
     e->sin_t = carve<float>(e, sizeof(float) * (size_t)S * (e->hd / 2));
@@ -131,10 +145,14 @@ static void layout(sllm_engine* e) {
     e->part_b = carve<float>(e, 4 * (size_t)d);
     e->mha_ws = carve<void>(e, mha_workspace_bytes(e->H_loc, e->hd, e->S));
     e->cls_grid = gemv_grid((e->V_loc + 1) / 2, 2);
-    e->blk_val = carve<float>(e, 4 * (size_t)(e->cls_grid + 1));
-    e->blk_idx = carve<int32_t>(e, 4 * (size_t)(e->cls_grid + 1));
+    const size_t nblk = (size_t)std::max(e->cls_grid, sm_count()) + 1;
+    e->blk_val = carve<float>(e, 4 * nblk);
+    e->blk_idx = carve<int32_t>(e, 4 * nblk);
     e->tp_pairs = carve<float>(e, 8 * (size_t)std::max(1, e->tp));
     e->state = carve<StepState>(e, sizeof(StepState));
+    e->mega_att = carve<float>(e, 4 * std::max<size_t>(4, e->mega_plan_.att_part_floats));
+    e->bar_counter = carve<unsigned>(e, 256);
+    e->phases_dev = carve<PhaseDesc>(e, sizeof(PhaseDesc) * (size_t)(4 * L + 1));
     e->prompt_dev = carve<int32_t>(e, 4 * (size_t)S);
     e->history_dev = carve<int32_t>(e, 4 * (size_t)S);
 }
@@ -407,6 +425,13 @@ static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
             if (int rc = enqueue_unfused_step(e, host_pos + i)) return rc;
         return SLLM_OK;
     }
+    if (e->mega) {
+        for (int i = 0; i < n; ++i) {
+            if (int rc = mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream)) return rc;
+            e->total_launches++;
+        }
+        return SLLM_OK;
+    }
     if (e->use_graph) {
         SLLM_REQUIRE(e->graph_exec, SLLM_ESTATE, "decode graph not built (weights or communicator missing)");
         for (int i = 0; i < n; ++i) SLLM_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -440,9 +465,9 @@ static std::vector<ShardSpec> shard_plan(sllm_engine* e) {
     std::vector<ShardSpec> plan;
     const int64_t d = e->d, kv = e->cfg.shape.kv_hidden, I = e->I, L = e->L, r = e->rank;
     const int wd = e->cfg.w_dtype, grp = e->cfg.group;
-    auto off_w = [&](const Matrix& m, int64_t elems) { return (void*)(reinterpret_cast<uint8_t*>(m.w) + wbytes(wd, elems)); };
+    auto off_w = [&](const Matrix& m, int64_t elems) { return (void*)(reinterpret_cast<uint8_t*>(m.rm ? m.rm : m.w) + wbytes(wd, elems)); };
     auto off_s = [&](const Matrix& m, int64_t elems) { return m.sc ? m.sc + elems / grp : nullptr; };
-    plan.push_back({0, 0, e->V, d, 0, d, e->emb.w, e->emb.sc});
+    plan.push_back({0, 0, e->V, d, 0, d, off_w(e->emb, 0), e->emb.sc});
     plan.push_back({1, 0, 2 * L + 1, d, 0, d, e->norms, nullptr});
     for (int64_t l = 0; l < L; ++l) {
         const int64_t qkv_rows = e->q_loc + 2 * e->kv_loc;
@@ -480,10 +505,67 @@ static int maybe_build_graph(sllm_engine* e) {
     return SLLM_OK;
 }
 
+// megakernel mode: weights are generated / uploaded row-major into ONE temporary allocation, then repacked into the
+// tiled arena layout matrix by matrix, and the temporary is freed.
+static int mega_stage_begin(sllm_engine* e) {
+    if (!e->mega) return SLLM_OK;
+    Matrix* ms[5] = {&e->emb, &e->wqkv, &e->wo, &e->wug, &e->wdown};
+    size_t total = 0;
+    for (Matrix* m : ms) total += align_up(wbytes(e->cfg.w_dtype, m->layers * m->rows * m->cols), 256);
+    uint8_t* tmp = nullptr;
+    if (cudaMalloc(&tmp, total) != cudaSuccess) { cudaGetLastError(); set_error("megakernel staging: cudaMalloc(%zu MiB) failed", total >> 20); return SLLM_ENOMEM; }
+    size_t off = 0;
+    for (Matrix* m : ms) { m->rm = tmp + off; off += align_up(wbytes(e->cfg.w_dtype, m->layers * m->rows * m->cols), 256); }
+    return SLLM_OK;
+}
+static int mega_stage_end(sllm_engine* e) {
+    if (!e->mega || !e->emb.rm) return SLLM_OK;
+    Matrix* ms[5] = {&e->emb, &e->wqkv, &e->wo, &e->wug, &e->wdown};
+    int rc = SLLM_OK;
+    for (Matrix* m : ms) {
+        const size_t tiled = mega_matrix_bytes((int)m->rows, (int)m->cols, m->kind, e->cfg.w_dtype);
+        for (int64_t l = 0; l < m->layers && rc == SLLM_OK; ++l)
+            rc = mega_repack(reinterpret_cast<uint8_t*>(m->rm) + wbytes(e->cfg.w_dtype, l * m->rows * m->cols),
+                             reinterpret_cast<uint8_t*>(m->w) + (size_t)l * tiled, (int)m->rows, (int)m->cols, m->kind, e->cfg.w_dtype, e->hd,
+                             e->q_loc, e->kv_loc, e->I_loc, e->stream);
+    }
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    cudaFree(e->emb.rm);
+    for (Matrix* m : ms) m->rm = nullptr;
+    if (rc) return rc;
+    SLLM_CUDA(ce);
+    return SLLM_OK;
+}
+
+static int setup_mega(sllm_engine* e) {
+    std::vector<PhaseDesc> host((size_t)4 * e->L + 1);
+    mega_fill_phases(host.data(), e->L, e->cfg.w_dtype, e->wqkv.w, e->wo.w, e->wug.w, e->wdown.w, e->emb.w, e->d, e->q_loc, e->kv_loc,
+                     e->I_loc, e->V_loc);   // single GPU: the classifier is the whole (tiled) embedding matrix
+    SLLM_CUDA(cudaMemcpyAsync(e->phases_dev, host.data(), sizeof(PhaseDesc) * host.size(), cudaMemcpyHostToDevice, e->stream));
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    MegaParams& p = e->mega_params;
+    p.phases = e->phases_dev;
+    p.d = e->d; p.hd = e->hd; p.L = e->L; p.S = e->S; p.V = e->V; p.V_loc = e->V_loc; p.v0 = e->v0; p.q_loc = e->q_loc; p.kv_loc = e->kv_loc;
+    p.I_loc = e->I_loc; p.H_loc = e->H_loc; p.KVH_loc = e->KVH_loc; p.nsplit = e->mega_plan_.nsplit;
+    p.w_dtype = e->cfg.w_dtype; p.kv_dtype = e->cfg.kv_dtype; p.eps = e->cfg.shape.eps;
+    p.emb = reinterpret_cast<const uint8_t*>(e->emb.w); p.norms = e->norms;
+    p.kc = reinterpret_cast<uint8_t*>(e->key_cache); p.vc = reinterpret_cast<uint8_t*>(e->value_cache);
+    p.sin_t = e->sin_t; p.cos_t = e->cos_t; p.x = e->x; p.h = e->h; p.q = e->q; p.swi = e->swi; p.logits = e->logits;
+    p.att_part = e->mega_att; p.blk_val = e->blk_val; p.blk_idx = e->blk_idx; p.st = e->state; p.prompt = e->prompt_dev;
+    p.history = e->history_dev; p.bar_counter = e->bar_counter; p.trace = nullptr;
+    return SLLM_OK;
+}
+
 static int finish_weights(sllm_engine* e) {
     if (int rc = sllm_rope_tables(e->hd, e->S, e->cfg.shape.theta, e->sin_t, e->cos_t, e->stream)) return rc;
     SLLM_CUDA(cudaStreamSynchronize(e->stream));
     e->weights_loaded = true;
+    if (e->mega) {
+        if (int rc = mega_stage_end(e)) return rc;
+        if (int rc = setup_mega(e)) return rc;
+        e->step_launches = 1;
+        return SLLM_OK;
+    }
     return maybe_build_graph(e);
 }
 
@@ -534,6 +616,10 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     if (e->hd % 16 || e->hd > 256) { set_error("head_dim=%d must be a multiple of 16, <= 256", e->hd); return fail(SLLM_ENOTSUP); }
     if (gemv_smem_bytes(std::max(e->d, e->I_loc)) > (size_t)smem_optin_bytes()) { set_error("activation vector does not fit shared memory"); return fail(SLLM_ENOTSUP); }
 
+    if ((cfg->flags & SLLM_ENGINE_MEGAKERNEL) && e->fused && tp == 1) {
+        e->mega_plan_ = mega_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->H_loc, e->KVH_loc, e->S);
+        e->mega = e->mega_plan_.ok;
+    }
     layout(e);  // measure
     e->arena_bytes = align_up(e->arena_used, 1 << 20);
     size_t free_b = 0, total_b = 0;
@@ -556,12 +642,14 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->comm) ncclCommDestroy(e->comm);
     if (e->h_state) cudaFreeHost(e->h_state);
     if (e->arena) cudaFree(e->arena);
+    if (e->trace) cudaFree(e->trace);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
 int sllm_engine_load_synthetic(sllm_engine* e, uint64_t seed) {
     SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
+    if (int rc = mega_stage_begin(e)) return rc;
     for (const ShardSpec& p : shard_plan(e))
         if (int rc = sllm_synth_fill(&e->cfg.shape, seed, p.seg, p.first_row, p.n_rows, p.src_row_len, p.col0, p.row_len, p.dst,
                                      e->cfg.w_dtype, p.sc, e->cfg.group, e->stream)) return rc;
@@ -573,6 +661,7 @@ int sllm_engine_load_blob_f32(sllm_engine* e, const float* blob, int64_t n_float
     const sllm_shape& s = e->cfg.shape;
     const int64_t need = segment_offset(s, 8) + (int64_t)s.layers * s.hidden * s.inter;
     SLLM_REQUIRE(n_floats >= need, SLLM_EINVAL, "weight blob has %lld floats, the shape needs %lld (model.cpp:340-468 layout)", (long long)n_floats, (long long)need);
+    if (int rc0 = mega_stage_begin(e)) return rc0;
     const size_t stage_bytes = (size_t)64 << 20;
     float* stage = nullptr;
     SLLM_CUDA(cudaMalloc(&stage, stage_bytes));
@@ -700,6 +789,12 @@ int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32
         case 103: *ptr = e->wo.w; *n = (int64_t)e->L * e->wo.rows * e->wo.cols; *dtype = e->cfg.w_dtype; break;
         case 104: *ptr = e->wug.w; *n = (int64_t)e->L * e->wug.rows * e->wug.cols; *dtype = e->cfg.w_dtype; break;
         case 105: *ptr = e->wdown.w; *n = (int64_t)e->L * e->wdown.rows * e->wdown.cols; *dtype = e->cfg.w_dtype; break;
+        case 200: {   // megakernel timeline: allocate on first request, stamps are written from the next step on
+            SLLM_REQUIRE(e->mega, SLLM_ESTATE, "trace needs megakernel mode");
+            const size_t nb = (size_t)e->mega_plan_.grid * 512 * 8 * 8;
+            if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; }
+            *ptr = e->trace; *n = (int64_t)(nb / 4); *dtype = SLLM_F32; break;
+        }
         case 110: *ptr = e->emb.sc; *n = e->emb.sc ? (int64_t)e->V * e->d / e->cfg.group : 0; break;
         case 112: *ptr = e->wqkv.sc; *n = e->wqkv.sc ? (int64_t)e->L * e->wqkv.rows * e->wqkv.cols / e->cfg.group : 0; break;
         default: SLLM_REQUIRE(false, SLLM_EINVAL, "unknown buffer id %d", id);
@@ -719,6 +814,7 @@ int64_t sllm_engine_step_bytes(const sllm_engine* e, int32_t pos) {
 
 int sllm_engine_enqueue_kernel(sllm_engine* e, int32_t kind, int32_t layer) {
     SLLM_REQUIRE(e && e->weights_loaded && e->fused, SLLM_ESTATE, "enqueue_kernel needs a fused engine with weights");
+    SLLM_REQUIRE(!e->mega, SLLM_ESTATE, "enqueue_kernel is not available in megakernel mode (weights are tiled, the step is one kernel)");
     SLLM_REQUIRE(layer >= 0 && layer < e->L, SLLM_EINVAL, "layer %d outside [0,%d)", layer, e->L);
     const int l = (kind == K_CLS) ? -1 : layer;
     switch (e->cfg.w_dtype) {
@@ -743,6 +839,15 @@ int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos
         default: return 0;
     }
 }
+
+const char* sllm_engine_mode(const sllm_engine* e) {
+    if (!e) return "null";
+    if (e->mega) return "megakernel";
+    if (!e->fused) return "unfused";
+    return e->use_graph ? (e->pdl ? "fused+graph+pdl" : "fused+graph") : (e->pdl ? "fused+pdl" : "fused");
+}
+
+int32_t sllm_engine_kv_layout(const sllm_engine* e) { return (e && e->mega) ? 1 : 0; }
 
 int32_t sllm_engine_step_launches(const sllm_engine* e) { return e ? e->step_launches : 0; }
 int64_t sllm_engine_total_launches(const sllm_engine* e) { return e ? e->total_launches : 0; }

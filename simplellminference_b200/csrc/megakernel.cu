@@ -1,0 +1,935 @@
+// csrc/megakernel.cu — the whole decode step as ONE persistent cooperative kernel (sm_100a).
+//
+// Why: with one kernel per fused op (decode_fused.cuh) every launch boundary drains the HBM pipe — measured
+// on B200: 2-5 us of ramp + tail per GEMV kernel x 128 kernels, and a 12 us latency chain per attention launch
+// (profiles/r01_launches.md). Here the step is one launch of `SM count` CTAs (1 per SM, 16 warps) that walks
+// the phases  A qkv | B attention | C wo | D gate_up | E down  of every layer and finally F classifier+argmax,
+// separated by grid barriers, and the WEIGHT STREAM NEVER STOPS:
+//
+//  * every warp owns a private ring of kSlots x kSlotBytes shared-memory slots filled by the TMA bulk-copy
+//    engine (cp.async.bulk global->shared, completion on the slot's mbarrier). Lane 0 of the warp is the
+//    producer: it re-arms a slot the moment the warp has consumed it and runs AHEAD across phase and layer
+//    boundaries — weights do not depend on activations — so while CTAs sit in a grid barrier or in the
+//    latency-bound attention phase, 128 KB per SM (19 MB chip-wide) of the next matrices is already landing.
+//  * a CTA owns a contiguous block of two-row units of the phase's matrix; its 16 warps split K: warp
+//    (ks, rg) streams column slice ks of the rows of row-group rg. A lane therefore multiplies the SAME
+//    columns for every row, so its part of the activation vector lives in registers for the whole phase
+//    (no shared-memory traffic for x at all). Partial dot products go to a small table; at the end of a
+//    round of <= kRoundUnits units the CTA syncs once and thread t finishes unit t (sum over K slices in fixed
+//    order — deterministic) and applies the fused epilogue (RoPE + cache write, residual, sigmoid*up, argmax).
+//  * attention (phase B) takes (kv head, split) items; K/V tiles are TMA-staged exactly like mha.cu; the
+//    merge of the splits is folded into phase C's prologue (every thread merges the partials of the columns
+//    it needs), which removes one grid barrier and the atomic ticket.
+//  * token and position stay in device memory; the last CTA to finish the classifier picks the arg max
+//    (first maximum) and advances the step state, so n tokens = n launches with no host round trip.
+//
+// Numerics are those of the fused path (fp32 activations/accumulators, IEEE divide/sqrt, accurate expf).
+#include <algorithm>
+#include <cmath>
+
+#include "megakernel.cuh"
+
+namespace sllm {
+
+constexpr int kMegaThreads = 512;
+constexpr int kMegaWarps = kMegaThreads / 32;
+constexpr int kSlotBytes = 4096;
+constexpr int kSlots = 2;
+constexpr int kCplMax = 4;        // max 16-byte chunks per lane per row slice (slice <= 2 KB)
+constexpr int kRoundUnits = 128;  // units per partial-table round
+constexpr int kAttTile = 64;
+constexpr unsigned kSpinLimit = 1u << 26;
+#ifndef SLLM_L2_AHEAD
+#define SLLM_L2_AHEAD 0
+#endif
+constexpr int kL2AheadBytes = SLLM_L2_AHEAD;  // per CTA: how much of the next phase is pulled into L2 during a phase gap
+constexpr int kAttRecPad = 4;     // partial record = hd floats of O, then m, l (+2 pad: keeps float4 alignment)
+
+
+struct MegaSmem {
+    size_t bars, red, part, ring, att, total;
+    size_t att_q, att_p, att_misc, att_k, att_v;
+    int kv_stride;
+};
+__host__ __device__ inline int mega_kv_stride(int row_bytes) {
+    int s = (row_bytes / 128) * 128 + 32;
+    if (s < row_bytes) s += 128;
+    return s;
+}
+__host__ __device__ inline MegaSmem mega_smem_layout(int hd, int g, int kv_esz) {
+    MegaSmem L;
+    size_t off = 0;
+    L.bars = off; off += 512;
+    L.red = off; off += 256;
+    L.part = off; off += (size_t)kRoundUnits * 2 * kMegaWarps * 4;
+    off = (off + 127) & ~(size_t)127;
+    L.ring = off; off += (size_t)kMegaWarps * kSlots * kSlotBytes;
+    L.att = off;
+    L.att_q = off; off += (size_t)g * hd * 4;
+    L.att_p = off; off += (size_t)g * kAttTile * 4;
+    L.att_misc = off; off += 256;
+    off = (off + 127) & ~(size_t)127;
+    L.kv_stride = hd * kv_esz;   // dense rows: a tile is one contiguous bulk copy
+    L.att_k = off; off += (size_t)2 * kAttTile * L.kv_stride;
+    L.att_v = off; off += (size_t)2 * kAttTile * L.kv_stride;
+    L.total = off;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------- primitives ----
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    unsigned spins = 0;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > kSpinLimit) __trap();
+    } while (!done);
+}
+__device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
+}
+// HBM -> L2 only (no shared memory needed): extends the effective prefetch depth far beyond the smem rings
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// grid-wide barrier (cooperative launch guarantees co-residency). counter[0] = arrivals (monotonic), counter[32] =
+// released epoch on its own 128-byte line: the last arriver publishes the epoch, everybody else polls that line
+// only, so the polling never collides with the arriving atomics. Wrap-safe compares. No trailing fence: every
+// cross-CTA read in this kernel is an L2 access (ld.global.cg or TMA), never an L1-cached load.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev + 1u == target) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 32), "r"(target) : "memory");
+        } else {
+            unsigned spins = 0;
+            while (true) {
+                unsigned v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter + 32) : "memory");
+                if ((int)(v - target) >= 0) break;
+                if (++spins > kSpinLimit) __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void unit_rows(const MegaParams& p, const PhaseDesc& ph, int u, int& r0, int& r1) {
+    if (ph.kind == PH_QKV) {
+        const int half = p.hd >> 1, rope_units = (p.q_loc + p.kv_loc) >> 1;
+        if (u < rope_units) {
+            const int head = u / half, j = u - head * half;
+            r0 = head * p.hd + j;
+            r1 = r0 + half;
+        } else {
+            r0 = p.q_loc + p.kv_loc + 2 * (u - rope_units);
+            r1 = r0 + 1;
+        }
+    } else if (ph.kind == PH_GATEUP) {
+        r0 = u;
+        r1 = p.I_loc + u;
+    } else {
+        r0 = 2 * u;
+        r1 = min(2 * u + 1, ph.nrows - 1);
+    }
+}
+
+// balanced split of a phase's tile rows over the CTAs
+__device__ __forceinline__ void cta_tiles(const PhaseDesc& ph, int cta, int ncta, int& g0, int& g1) {
+    g0 = (int)(((int64_t)ph.ntr * cta) / ncta);
+    g1 = (int)(((int64_t)ph.ntr * (cta + 1)) / ncta);
+}
+
+template <int KVD> struct MKv;
+template <> struct MKv<SLLM_F32> { static constexpr int ESZ = 4, VEC = 4; };
+template <> struct MKv<SLLM_BF16> { static constexpr int ESZ = 2, VEC = 8; };
+
+template <int KVD>
+__device__ __forceinline__ void kv_unpack(const uint4 v, float* f) {
+    if (KVD == SLLM_F32) {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    } else {
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    }
+}
+
+// 16 bytes of weights (E elements) times E activations held in registers
+template <int WD>
+__device__ __forceinline__ float reg_dot(const uint4 w, const float* x, float acc) {
+    if (WD == SLLM_F32) {
+        acc = fmaf(__uint_as_float(w.x), x[0], acc); acc = fmaf(__uint_as_float(w.y), x[1], acc);
+        acc = fmaf(__uint_as_float(w.z), x[2], acc); acc = fmaf(__uint_as_float(w.w), x[3], acc);
+    } else {
+        acc = fmaf(bf16_lo(w.x), x[0], acc); acc = fmaf(bf16_hi(w.x), x[1], acc);
+        acc = fmaf(bf16_lo(w.y), x[2], acc); acc = fmaf(bf16_hi(w.y), x[3], acc);
+        acc = fmaf(bf16_lo(w.z), x[4], acc); acc = fmaf(bf16_hi(w.z), x[5], acc);
+        acc = fmaf(bf16_lo(w.w), x[6], acc); acc = fmaf(bf16_hi(w.w), x[7], acc);
+    }
+    return acc;
+}
+
+// ----------------------------------------------------------------------------------------- kernel ----
+// Optional per-CTA timeline (tools/mega_trace.py): stamp s of phase slot `ev` -> trace[(cta*kTraceEvents + ev)*8 + s]
+constexpr int kTraceEvents = 512;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MEGA_STAMP(ev, slot)                                                                              \
+    do {                                                                                                  \
+        if (p.trace && threadIdx.x == 0 && (ev) < kTraceEvents) p.trace[((size_t)blockIdx.x * kTraceEvents + (ev)) * 8 + (slot)] = gtime(); \
+    } while (0)
+
+__device__ __noinline__ void mega_timeout(const char* what) {
+    printf("sllm mega: %s timed out (cta %d warp %d)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5));
+    __trap();
+}
+__device__ __forceinline__ void mb_wait_fast(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    unsigned spins = 0;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > kSpinLimit) mega_timeout("mbarrier");
+    } while (!done);
+}
+
+// producer state of one warp (meaningful in lane 0): constants of the phase it is currently feeding
+struct ProdState {
+    int wp, j;                 // phase and next slot index (j < 0: phase not entered yet)
+    unsigned count;            // slots issued so far
+    const uint8_t* W;          // phase matrix + this warp's column offset
+    int row_bytes, sbytes, u0, u1, upp, RG, nslots, kind;
+};
+
+template <int WD, int KVD, int G>
+__global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaParams p) {
+    constexpr int E = WInfo<WD>::E;                 // weights per 16-byte chunk
+    constexpr int KESZ = MKv<KVD>::ESZ, KVEC = MKv<KVD>::VEC;
+    extern __shared__ __align__(128) uint8_t mega_smem[];
+    uint8_t* const smem = mega_smem;
+    const MegaSmem SL = mega_smem_layout(p.hd, G, KESZ);
+    uint64_t* ring_bar = reinterpret_cast<uint64_t*>(smem + SL.bars);            // [16][kSlots]
+    uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;                          // [2]
+    float* red = reinterpret_cast<float*>(smem + SL.red);
+    float* part = reinterpret_cast<float*>(smem + SL.part);                      // [kRoundUnits][2][16]
+    uint8_t* ring = smem + SL.ring;
+    float* xs = reinterpret_cast<float*>(smem + SL.att_k);    // activation staging: aliases the (idle) K/V stages
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const int nwp = 4 * p.L + 1;
+
+    if (tid < kMegaWarps * kSlots + 2) mb_init(ring_bar + tid, 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int pos = p.st->pos;
+    const int token = min(max(p.st->token, 0), p.V - 1);
+    const unsigned bar_base = (unsigned)p.st->pad[0];
+    unsigned bar_idx = 0;
+
+    uint8_t* my_ring = ring + (size_t)warp * kSlots * kSlotBytes;
+    uint64_t* my_bar = ring_bar + warp * kSlots;
+
+    // ---------------- producer (lane 0 of every warp): one tile == one bulk copy -------------------------------
+    int pr_wp = -1, pr_left = 0;          // phase being fed, tiles of it still to request
+    unsigned pr_count = 0;                // slots issued so far
+    const uint8_t* pr_ptr = nullptr;      // next tile of this warp's (ks, rg) sub-stream
+    uint32_t pr_step = 0, pr_bytes = 0;
+    auto produce_one = [&]() {   // lane 0 only: arm the next slot of this warp's stream (if any is left)
+        while (pr_left <= 0) {                            // enter the next phase this warp has work in
+            if (++pr_wp >= nwp) { pr_wp = nwp; return; }
+            const PhaseDesc ph = p.phases[pr_wp];
+            const int ks = warp & (ph.KS - 1), rg = warp / ph.KS, RG = kMegaWarps / ph.KS;
+            int g0, g1;
+            cta_tiles(ph, cta, ncta, g0, g1);
+            pr_left = (g1 - g0 - rg + RG - 1) / RG;       // tile rows g0+rg, g0+rg+RG, ... < g1
+            pr_ptr = ph.W + ((size_t)(g0 + rg) * ph.KS + ks) * ph.tile_bytes;
+            pr_step = (uint32_t)RG * ph.KS * ph.tile_bytes;
+            pr_bytes = (uint32_t)ph.tile_bytes;
+        }
+        const int si = pr_count & (kSlots - 1);
+        mb_expect(my_bar + si, pr_bytes);
+        tma_g2s(my_ring + (size_t)si * kSlotBytes, pr_ptr, pr_bytes, my_bar + si);
+        pr_ptr += pr_step;
+        pr_left--;
+        pr_count++;
+    };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < kSlots; ++s) produce_one();
+    }
+    unsigned cons_count = 0;             // slots consumed so far (warp-uniform)
+    unsigned kv_use0 = 0, kv_use1 = 0;   // how often each K/V stage mbarrier was armed (parity)
+
+#pragma unroll 1
+    for (int wp = 0; wp < nwp; ++wp) {
+        // =============================== weight phase wp ===============================================
+        const PhaseDesc ph = p.phases[wp];
+        const int l = ph.layer;
+        const int ks = warp & (ph.KS - 1), rg = warp / ph.KS, RG = kMegaWarps / ph.KS;
+        const int c0 = ks * ph.SC;
+        const int nsc = max(0, min(ph.SC, ph.nchunks - c0));   // real chunks of this slice (the tile is zero padded to SC)
+        const int cols = ph.nchunks * E;
+        const bool normed = (ph.kind == PH_QKV || ph.kind == PH_GATEUP || ph.kind == PH_CLS);
+        const int ev = wp + l + (ph.kind != PH_QKV && ph.kind != PH_CLS ? 1 : 0) + (ph.kind == PH_CLS ? 0 : 0);   // event slot: weight phases and attention phases in order
+        MEGA_STAMP(ev, 0);
+
+        // norm weights of this lane's columns: constant data, requested before anything that has to wait
+        float nwr[kCplMax][E];
+        if (normed) {
+            const float* nw = p.norms + (size_t)(ph.kind == PH_QKV ? 2 * l : ph.kind == PH_GATEUP ? 2 * l + 1 : 2 * p.L) * p.d;
+#pragma unroll
+            for (int i = 0; i < kCplMax; ++i) {
+                const int c = lane + 32 * i;
+#pragma unroll
+                for (int e4 = 0; e4 < E; e4 += 4) {
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < nsc) g = __ldg(reinterpret_cast<const float4*>(nw + (c0 + c) * E + e4));
+                    nwr[i][e4] = g.x; nwr[i][e4 + 1] = g.y; nwr[i][e4 + 2] = g.z; nwr[i][e4 + 3] = g.w;
+                }
+            }
+        }
+        // ---- 1. stage the activation vector in shared memory (plain loops, all 512 threads) -------------
+        float ss = 0.f;
+        if (ph.kind == PH_QKV && l == 0) {                                   // embedding gather (model.cpp:48)
+            // row `token` of the (tiled) embedding/classifier matrix: tile row token/R, row token%R inside the tile
+            const PhaseDesc em = p.phases[nwp - 1];
+            const uint8_t* trow = p.emb + (size_t)(token / em.R) * em.KS * em.tile_bytes + (size_t)(token % em.R) * em.SC * 16;
+            for (int c = tid; c < ph.nchunks; c += kMegaThreads) {
+                const int eks = c / em.SC, ecc = c - eks * em.SC;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(trow + (size_t)eks * em.tile_bytes + (size_t)ecc * 16));
+                float f[8];
+                if (WD == SLLM_F32) {
+                    f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y); f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
+                } else {
+                    kv_unpack<SLLM_BF16>(raw, f);
+                }
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    xs[c * E + e] = f[e];
+                    ss = fmaf(f[e], f[e], ss);
+                    if (cta == 0) p.x[c * E + e] = f[e];
+                }
+            }
+        } else if (ph.kind == PH_WO) {                                       // merge the attention splits
+            const int rec = p.hd + kAttRecPad;
+            for (int c4 = tid; c4 < cols / 4; c4 += kMegaThreads) {
+                const int col = c4 * 4;
+                const int head = col / p.hd, j = col - head * p.hd;
+                const float* base = p.att_part + (size_t)head * p.nsplit * rec;
+                float M = -INFINITY;
+                for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * rec + p.hd));
+                float Ls = 0.f;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < p.nsplit; ++s) {
+                    const float m = __ldcg(base + (size_t)s * rec + p.hd);
+                    const float w = (m == -INFINITY) ? 0.f : expf(m - M);
+                    Ls = fmaf(__ldcg(base + (size_t)s * rec + p.hd + 1), w, Ls);
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * rec + j));
+                    o.x = fmaf(v.x, w, o.x); o.y = fmaf(v.y, w, o.y); o.z = fmaf(v.z, w, o.z); o.w = fmaf(v.w, w, o.w);
+                }
+                reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+            }
+        } else {
+            const float* src = (ph.kind == PH_GATEUP) ? p.h : (ph.kind == PH_DOWN) ? p.swi : p.x;
+            for (int c4 = tid; c4 < cols / 4; c4 += kMegaThreads) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + c4);
+                reinterpret_cast<float4*>(xs)[c4] = v;
+                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        }
+        float inv = 1.f;
+        if (normed) {                                                        // RMSNorm, rms_kernel.cpp:12-22
+            ss = warp_sum(ss);
+            if (lane == 0) red[warp] = ss;
+            __syncthreads();
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMegaWarps; ++k) tot += red[k];
+            inv = 1.0f / sqrtf(tot / (float)cols + p.eps);
+        } else {
+            __syncthreads();
+        }
+        // ---- this lane's columns -> registers (chunk c = c0 + lane + 32 i  <->  columns c*E .. c*E+E)
+        float xr[kCplMax][E];
+#pragma unroll
+        for (int i = 0; i < kCplMax; ++i) {
+            const int c = lane + 32 * i;
+#pragma unroll
+            for (int e = 0; e < E; ++e) xr[i][e] = 0.f;
+            if (c < nsc) {
+                const int col = (c0 + c) * E;
+#pragma unroll
+                for (int e4 = 0; e4 < E; e4 += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(xs + col + e4);
+                    xr[i][e4] = v.x; xr[i][e4 + 1] = v.y; xr[i][e4 + 2] = v.z; xr[i][e4 + 3] = v.w;
+                }
+                if (normed) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) xr[i][e] = (xr[i][e] * inv) * nwr[i][e];
+                }
+            }
+        }
+
+        if (ph.kind == PH_QKV && cta < p.KVH_loc * p.nsplit) {
+            // The K/V rows this CTA's first attention item needs (all but the row written this step) were stored by
+            // EARLIER launches: start their TMA now, into the K/V stages that only alias the activation staging
+            // buffer (already consumed into registers), so they land while phase A streams its weights.
+            __syncthreads();                    // every lane has read its part of xs
+            if (warp == 0 && lane == 0) {
+                fence_async_smem();
+                const int row_bytes = p.hd * KESZ;
+                const int npos = pos + 1, per = (npos + p.nsplit - 1) / p.nsplit;
+                const int kvh = cta / p.nsplit, split = cta - kvh * p.nsplit;
+                const int t0 = split * per, t1 = min(npos, t0 + per);
+                const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;   // [L][KVH][S][hd]
+                for (int tile = 0; tile < 2; ++tile) {
+                    const int ts = t0 + tile * kAttTile;
+                    const int rows = min(kAttTile, t1 - ts);
+                    if (rows <= 0) break;
+                    const int bulk_rows = max(0, min(rows, pos - ts));
+                    mb_expect(att_bar + tile, (uint32_t)(2 * bulk_rows * row_bytes));
+                    if (bulk_rows > 0) {
+                        tma_g2s(smem + SL.att_k + (size_t)tile * kAttTile * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_v + (size_t)tile * kAttTile * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                    }
+                }
+            }
+        }
+        MEGA_STAMP(ev, 1);   // prologue done
+        // ---- 2. stream this CTA's tile rows through the rings, round by round ------------------------------
+        int g0, g1;
+        cta_tiles(ph, cta, ncta, g0, g1);
+        const int upp = ph.R >> 1;
+        const int u0 = g0 * upp;
+        const int n = max(0, min(ph.nunits, g1 * upp) - u0);   // real units of this CTA
+        const int nslots = g1 - g0;
+        const uint32_t sbytes = (uint32_t)ph.SC * 16;           // row pitch inside a tile
+        const int cpl = (nsc + 31) >> 5;
+        float best_v = -INFINITY;   // classifier only
+        int best_i = 0x7fffffff;
+
+#pragma unroll 1
+        for (int rbase = 0; rbase < n || rbase == 0; rbase += kRoundUnits) {
+            const int jend = min(nslots, (rbase + kRoundUnits) / upp);
+            {
+#pragma unroll 1
+                for (int j = rbase / upp + rg; j < jend; j += RG) {
+                    const int si = cons_count & (kSlots - 1);
+                    mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
+                    const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    if (upp == 2) {
+#pragma unroll
+                        for (int i = 0; i < kCplMax; ++i) {
+                            if (i < cpl && lane + 32 * i < nsc) {
+                                const uint8_t* q = sp + i * 512;
+                                a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
+                                a1 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q + sbytes), xr[i], a1);
+                                a2 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 2 * sbytes), xr[i], a2);
+                                a3 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 3 * sbytes), xr[i], a3);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kCplMax; ++i) {
+                            if (i < cpl && lane + 32 * i < nsc) {
+                                const uint8_t* q = sp + i * 512;
+                                a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
+                                a1 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q + sbytes), xr[i], a1);
+                            }
+                        }
+                    }
+                    // multi-value butterfly: 4 row sums over 32 lanes in 6 shuffles (fixed order => deterministic)
+                    {
+                        const bool hi = lane & 16;
+                        float k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+                        k0 += __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 16);
+                        k1 += __shfl_xor_sync(0xffffffffu, hi ? a1 : a3, 16);
+                        const bool hi8 = lane & 8;
+                        float k = hi8 ? k1 : k0;
+                        k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+                        k += __shfl_xor_sync(0xffffffffu, k, 4);
+                        k += __shfl_xor_sync(0xffffffffu, k, 2);
+                        k += __shfl_xor_sync(0xffffffffu, k, 1);
+                        // lane 0: row 0, lane 8: row 1, lane 16: row 2, lane 24: row 3 (rows 2,3 only when upp == 2)
+                        const int r = (lane >> 4) * 2 + ((lane >> 3) & 1);
+                        const int ul = j * upp + (r >> 1) - rbase;
+                        if ((lane & 7) == 0 && r < 2 * upp && ul + rbase < n)
+                            part[(ul * 2 + (r & 1)) * kMegaWarps + ks] = k;
+                    }
+                    cons_count++;
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_async_smem();
+                        produce_one();
+                    }
+                }
+            }
+            if (rbase + kRoundUnits >= n) MEGA_STAMP(ev, 2);   // this thread-0 warp finished streaming
+            if (kL2AheadBytes > 0 && rbase + kRoundUnits >= n && wp + 1 < nwp) {
+                // This CTA has streamed its share of phase wp. While it finishes the epilogue and waits in the grid
+                // barrier HBM would idle once the rings are full: pull the next kL2AheadBytes of ITS share of the NEXT
+                // phase (one contiguous range in the tiled layout) into L2 now, in large pieces.
+                const PhaseDesc nx = p.phases[wp + 1];
+                int h0, h1;
+                cta_tiles(nx, cta, ncta, h0, h1);
+                const size_t row_bytes = (size_t)nx.KS * nx.tile_bytes;                    // one tile row
+                const size_t skip = (size_t)kSlots * (kMegaWarps / nx.KS) * row_bytes;      // what the rings already hold
+                const size_t total = (size_t)(h1 - h0) * row_bytes;
+                const size_t want = total > skip ? min(total - skip, (size_t)kL2AheadBytes) : 0;
+                const uint8_t* base = nx.W + (size_t)h0 * row_bytes + skip;
+                const size_t piece = 16384;
+                for (size_t off = (size_t)tid * piece; off < want; off += (size_t)kMegaThreads * piece)
+                    l2_prefetch(base + off, (uint32_t)min(piece, want - off));
+            }
+            __syncthreads();
+            if (rbase + kRoundUnits >= n) MEGA_STAMP(ev, 3);   // whole CTA finished streaming
+            // ---- 3. finish the round's units: sum over K slices, fused epilogue -------------------------------
+            const int nround = min(kRoundUnits, n - rbase);
+#pragma unroll 1
+            for (int t = tid; t < nround; t += kMegaThreads) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int k = 0; k < ph.KS; ++k) {
+                    s0 += part[(t * 2 + 0) * kMegaWarps + k];
+                    s1 += part[(t * 2 + 1) * kMegaWarps + k];
+                }
+                const int u = u0 + rbase + t;
+                if (ph.kind == PH_QKV) {
+                    const int half = p.hd >> 1, rope_units = (p.q_loc + p.kv_loc) >> 1;
+                    // head-major cache [L][KVH][S][hd]: element j of kv head h at position pos
+                    auto kv_addr = [&](uint8_t* cache, int idx) -> uint8_t* {
+                        const int h = idx / p.hd, j = idx - h * p.hd;
+                        return cache + ((((size_t)l * p.KVH_loc + h) * p.S + pos) * p.hd + j) * KESZ;
+                    };
+                    auto store_kv = [&](uint8_t* cache, int idx, float v) {
+                        if (KVD == SLLM_BF16) *reinterpret_cast<uint16_t*>(kv_addr(cache, idx)) = f32_to_bf16_bits(v);
+                        else *reinterpret_cast<float*>(kv_addr(cache, idx)) = v;
+                    };
+                    if (u < rope_units) {
+                        const int head = u / half, j = u - head * half;
+                        const float fci = p.sin_t[(size_t)pos * half + j], fcr = p.cos_t[(size_t)pos * half + j];
+                        const float o0 = s0 * fcr - s1 * fci, o1 = s1 * fcr + s0 * fci;   // rope_kernel.cpp:36-37
+                        const int r0 = head * p.hd + j;
+                        if (r0 < p.q_loc) { p.q[r0] = o0; p.q[r0 + half] = o1; }
+                        else { store_kv(p.kc, r0 - p.q_loc, o0); store_kv(p.kc, r0 - p.q_loc + half, o1); }
+                    } else {
+                        const int b2 = 2 * (u - rope_units);
+                        store_kv(p.vc, b2, s0);
+                        store_kv(p.vc, b2 + 1, s1);
+                    }
+                } else if (ph.kind == PH_WO) {
+                    const int r = 2 * u;
+                    p.h[r] = __ldcg(p.x + r) + s0;                            // add_kernel.cpp:10-13
+                    if (r + 1 < ph.nrows) p.h[r + 1] = __ldcg(p.x + r + 1) + s1;
+                } else if (ph.kind == PH_GATEUP) {
+                    p.swi[u] = (1.0f / (1.0f + expf(-s1))) * s0;              // swiglu_kernel.cpp:12-13
+                } else if (ph.kind == PH_DOWN) {
+                    const int r = 2 * u;
+                    p.x[r] = s0 + __ldcg(p.h + r);
+                    if (r + 1 < ph.nrows) p.x[r + 1] = s1 + __ldcg(p.h + r + 1);
+                } else {
+                    const int r = 2 * u;
+                    p.logits[r] = s0;
+                    if (s0 > best_v || (s0 == best_v && p.v0 + r < best_i)) { best_v = s0; best_i = p.v0 + r; }
+                    if (r + 1 < ph.nrows) {
+                        p.logits[r + 1] = s1;
+                        if (s1 > best_v || (s1 == best_v && p.v0 + r + 1 < best_i)) { best_v = s1; best_i = p.v0 + r + 1; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        if (ph.kind == PH_CLS) {   // CTA best -> global; the last CTA picks the arg max and advances the step state
+            float* sv = part;
+            int* si = reinterpret_cast<int*>(part + kMegaThreads);
+            sv[tid] = best_v;
+            si[tid] = best_i;
+            __syncthreads();
+            for (int o = kMegaThreads / 2; o > 0; o >>= 1) {
+                if (tid < o) {
+                    const float ov = sv[tid + o];
+                    const int oi = si[tid + o];
+                    if (ov > sv[tid] || (ov == sv[tid] && oi < si[tid])) { sv[tid] = ov; si[tid] = oi; }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                p.blk_val[cta] = sv[0];
+                p.blk_idx[cta] = si[0];
+                __threadfence();
+                s_last = (atomicAdd(&p.st->ticket, 1) == ncta - 1);
+            }
+            __syncthreads();
+            if (s_last && tid == 0) {
+                __threadfence();
+                float v = -INFINITY;
+                int idx = 0x7fffffff;
+                for (int b = 0; b < ncta; ++b) {
+                    const float ov = __ldcg(p.blk_val + b);
+                    const int oi = __ldcg(p.blk_idx + b);
+                    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+                }
+                if (idx == 0x7fffffff) idx = 0;
+                p.st->ticket = 0;
+                p.st->pad[0] = (int32_t)(bar_base + bar_idx * (unsigned)ncta);   // barrier epoch for the next launch
+                p.blk_val[ncta] = v;
+                p.blk_idx[ncta] = idx;
+                ClsPolicy<SLLM_F32>::step_feedback(p.st, p.prompt, p.history, idx);
+            }
+            break;
+        }
+        MEGA_STAMP(ev, 4);   // epilogue done
+        grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        MEGA_STAMP(ev, 5);   // barrier passed
+        if (ph.kind != PH_QKV) continue;
+        MEGA_STAMP(ev + 1, 0);
+
+        // =============================== attention phase of layer l ======================================
+        {
+            float* q_s = reinterpret_cast<float*>(smem + SL.att_q);
+            float* p_s = reinterpret_cast<float*>(smem + SL.att_p);
+            float* alpha_s = reinterpret_cast<float*>(smem + SL.att_misc);
+            float* ml_s = alpha_s + 16;
+            uint8_t* k_s = smem + SL.att_k;
+            uint8_t* v_s = smem + SL.att_v;
+            const int stride = SL.kv_stride;
+            const int row_bytes = p.hd * KESZ;
+            const int cpr = row_bytes / 16;                    // 16-byte chunks per K/V row
+            const int npos = pos + 1;
+            const int per = (npos + p.nsplit - 1) / p.nsplit;
+            const int nitems = p.KVH_loc * p.nsplit;
+            const float scale = 1.0f / sqrtf((float)p.hd);
+            constexpr int kStripes = 16;
+            const int pv_chunk = tid % cpr, pv_stripe = tid / cpr;
+            const bool pv_active = pv_stripe < kStripes;
+            const int key = tid >> 3, kpart = tid & 7;         // 8 threads per key
+
+#pragma unroll 1
+            for (int item = cta; item < nitems; item += ncta) {
+                const int kvh = item / p.nsplit, split = item - kvh * p.nsplit;
+                const int t0 = split * per, t1 = min(npos, t0 + per);
+                const int ntiles = (t1 > t0) ? (t1 - t0 + kAttTile - 1) / kAttTile : 0;
+                for (int i = tid; i < G * p.hd; i += kMegaThreads) q_s[i] = __ldcg(p.q + (size_t)(kvh * G) * p.hd + i);
+                if (tid < G) { ml_s[2 * tid] = -INFINITY; ml_s[2 * tid + 1] = 0.f; }
+                const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;   // [L][KVH][S][hd]
+                auto issue_tile = [&](int tile) {              // warp 0: TMA for rows written by EARLIER launches;
+                    const int stage = tile & 1;                // the row written this step (pos) is copied by hand
+                    const int ts = t0 + tile * kAttTile;
+                    const int rows = min(kAttTile, t1 - ts);
+                    const int bulk_rows = max(0, min(rows, pos - ts));
+                    if (lane == 0) {
+                        mb_expect(att_bar + stage, (uint32_t)(2 * bulk_rows * row_bytes));
+                        if (bulk_rows > 0) {
+                            tma_g2s(k_s + (size_t)stage * kAttTile * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                            tma_g2s(v_s + (size_t)stage * kAttTile * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                        }
+                    }
+                };
+                fence_async_smem();   // generic accesses to the K/V region (o_s) precede the TMA writes below
+                __syncthreads();      // q_s / ml_s visible; previous readers of this smem are done
+                if (warp == 0 && item != cta) {   // tiles 0/1 of the FIRST item were prefetched during phase A
+                    if (ntiles > 0) issue_tile(0);
+                    if (ntiles > 1) issue_tile(1);
+                }
+                float acc[G][KVEC];
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+                    for (int e = 0; e < KVEC; ++e) acc[gi][e] = 0.f;
+
+#pragma unroll 1
+                for (int tile = 0; tile < ntiles; ++tile) {
+                    const int stage = tile & 1;
+                    const int ts = t0 + tile * kAttTile;
+                    const int rows = min(kAttTile, t1 - ts);
+                    // the newest row (written by phase A of THIS launch with generic stores) bypasses the async proxy
+                    if (pos >= ts && pos < ts + rows && warp == 1) {
+                        const size_t g_off = head_off + (size_t)pos * row_bytes;
+                        for (int c = lane; c < cpr; c += 32) {
+                            *reinterpret_cast<uint4*>(k_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                                __ldcg(reinterpret_cast<const uint4*>(p.kc + g_off + c * 16));
+                            *reinterpret_cast<uint4*>(v_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                                __ldcg(reinterpret_cast<const uint4*>(p.vc + g_off + c * 16));
+                        }
+                    }
+                    if (stage == 0) { mb_wait_fast(att_bar, kv_use0 & 1); kv_use0++; }
+                    else { mb_wait_fast(att_bar + 1, kv_use1 & 1); kv_use1++; }
+                    __syncthreads();
+                    {   // scores
+                        float s[G];
+#pragma unroll
+                        for (int gi = 0; gi < G; ++gi) s[gi] = 0.f;
+                        if (key < rows) {
+                            const uint8_t* krow = k_s + ((size_t)stage * kAttTile + key) * stride;
+                            for (int c = kpart; c < cpr; c += 8) {
+                                float kf[KVEC];
+                                kv_unpack<KVD>(*reinterpret_cast<const uint4*>(krow + c * 16), kf);
+#pragma unroll
+                                for (int gi = 0; gi < G; ++gi) {
+                                    const float* qv = q_s + gi * p.hd + c * KVEC;
+#pragma unroll
+                                    for (int e = 0; e < KVEC; ++e) s[gi] = fmaf(qv[e], kf[e], s[gi]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int gi = 0; gi < G; ++gi) {
+                            s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 1);
+                            s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 2);
+                            s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 4);
+                            if (kpart == 0) p_s[gi * kAttTile + key] = (key < rows) ? s[gi] * scale : -INFINITY;
+                        }
+                    }
+                    __syncthreads();
+                    for (int gi = warp; gi < G; gi += kMegaWarps) {   // online softmax bookkeeping
+                        const float s0 = p_s[gi * kAttTile + lane], s1 = p_s[gi * kAttTile + lane + 32];
+                        const float m_old = ml_s[2 * gi], l_old = ml_s[2 * gi + 1];
+                        const float m_new = fmaxf(m_old, warp_max(fmaxf(s0, s1)));
+                        const float e0 = expf(s0 - m_new), e1 = expf(s1 - m_new);
+                        const float al = expf(m_old - m_new);
+                        const float l_new = l_old * al + warp_sum(e0 + e1);
+                        p_s[gi * kAttTile + lane] = e0;
+                        p_s[gi * kAttTile + lane + 32] = e1;
+                        if (lane == 0) { alpha_s[gi] = al; ml_s[2 * gi] = m_new; ml_s[2 * gi + 1] = l_new; }
+                    }
+                    __syncthreads();
+                    if (pv_active) {
+#pragma unroll
+                        for (int gi = 0; gi < G; ++gi) {
+                            const float al = alpha_s[gi];
+#pragma unroll
+                            for (int e = 0; e < KVEC; ++e) acc[gi][e] *= al;
+                        }
+                        for (int r = pv_stripe; r < rows; r += kStripes) {
+                            float vf[KVEC];
+                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * kAttTile + r) * stride + pv_chunk * 16), vf);
+#pragma unroll
+                            for (int gi = 0; gi < G; ++gi) {
+                                const float pr = p_s[gi * kAttTile + r];
+#pragma unroll
+                                for (int e = 0; e < KVEC; ++e) acc[gi][e] = fmaf(pr, vf[e], acc[gi][e]);
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    __syncthreads();
+                    if (warp == 0 && tile + 2 < ntiles) issue_tile(tile + 2);
+                }
+                // cross-stripe reduction through the (drained) K stages, then the partial record
+                float* o_s = reinterpret_cast<float*>(k_s);   // [kStripes][G][hd]
+                if (pv_active) {
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+                        for (int e = 0; e < KVEC; ++e) o_s[((size_t)pv_stripe * G + gi) * p.hd + pv_chunk * KVEC + e] = acc[gi][e];
+                }
+                __syncthreads();
+                const int rec = p.hd + kAttRecPad;
+                for (int i = tid; i < G * p.hd; i += kMegaThreads) {
+                    float o = 0.f;
+                    for (int s = 0; s < kStripes; ++s) o += o_s[(size_t)s * G * p.hd + i];
+                    const int gi = i / p.hd, j = i - gi * p.hd;
+                    p.att_part[((size_t)(kvh * G + gi) * p.nsplit + split) * rec + j] = o;
+                }
+                if (tid < G) {
+                    float* r = p.att_part + ((size_t)(kvh * G + tid) * p.nsplit + split) * rec + p.hd;
+                    r[0] = ml_s[2 * tid];
+                    r[1] = ml_s[2 * tid + 1];
+                }
+            }
+            fence_async_smem();
+        }
+        MEGA_STAMP(ev + 1, 4);
+        grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        MEGA_STAMP(ev + 1, 5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host ----
+TileGeom mega_tile_geom(int rows_phys, int cols, int w_dtype) {
+    TileGeom g;
+    const int E = w_dtype == SLLM_F32 ? 4 : 8;
+    g.nchunks = cols / E;
+    int KS = 1;
+    while (KS < 16 && (g.nchunks + KS - 1) / KS * 16 > 1024) KS *= 2;
+    g.KS = KS;
+    g.SC = (g.nchunks + KS - 1) / KS;
+    g.R = (g.SC * 16 * 4 <= kSlotBytes) ? 4 : 2;
+    g.ntr = (rows_phys + g.R - 1) / g.R;
+    g.tile_bytes = g.R * g.SC * 16;
+    g.bytes = (size_t)g.ntr * g.KS * g.tile_bytes;
+    return g;
+}
+
+static int phys_rows(int rows, int kind) { return kind == PH_GATEUP ? rows : ((rows + 1) / 2) * 2; }
+
+size_t mega_matrix_bytes(int rows, int cols, int kind, int w_dtype) { return mega_tile_geom(phys_rows(rows, kind), cols, w_dtype).bytes; }
+
+static void fill_desc(PhaseDesc& ds, const void* W, int rows, int cols, int kind, int layer, int w_dtype) {
+    const TileGeom g = mega_tile_geom(phys_rows(rows, kind), cols, w_dtype);
+    ds.W = reinterpret_cast<const uint8_t*>(W);
+    ds.nchunks = g.nchunks;
+    ds.nrows = rows;
+    ds.kind = kind;
+    ds.layer = layer;
+    ds.nunits = (kind == PH_GATEUP) ? rows / 2 : (rows + 1) / 2;
+    ds.KS = g.KS;
+    ds.SC = g.SC;
+    ds.R = g.R;
+    ds.ntr = g.ntr;
+    ds.tile_bytes = g.tile_bytes;
+}
+
+// can the megakernel run this shape? (everything else keeps using the per-kernel fused path)
+MegaPlan mega_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len) {
+    MegaPlan pl;
+    if (w_dtype == SLLM_INT8) { pl.why = "int8 weights"; return pl; }
+    const int E = w_dtype == SLLM_F32 ? 4 : 8;
+    for (int cols : {d, q_loc, I_loc}) {
+        const int nch = cols / E;
+        const int SC = (nch + 15) / 16;
+        if (cols % E) { pl.why = "row length not a multiple of 16 bytes"; return pl; }
+        if (SC * 16 * 2 > kSlotBytes || SC > 32 * kCplMax) { pl.why = "rows longer than 32 KB"; return pl; }
+    }
+    const int g = H_loc / KVH_loc;
+    if (g > 8 || hd % 16 || hd > 256) { pl.why = "head shape"; return pl; }
+    const int kesz = kv_dtype == SLLM_F32 ? 4 : 2;
+    if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
+    const MegaSmem SL = mega_smem_layout(hd, g, kesz);
+    if (SL.total > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
+    if ((size_t)16 * g * hd * 4 > (size_t)2 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }
+    if ((size_t)std::max(d, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
+    if (q_loc % 2 || kv_loc % 2) { pl.why = "odd dims"; return pl; }
+    pl.grid = sm_count();
+    pl.smem = SL.total;
+    // splits: fill the grid once, never more splits than 64-position tiles at full context
+    int ns = pl.grid / KVH_loc;
+    const int by_len = (max_len + kAttTile - 1) / kAttTile;
+    if (ns > by_len) ns = by_len;
+    if (ns > 32) ns = 32;
+    pl.nsplit = ns < 1 ? 1 : ns;
+    (void)V_loc;
+    pl.att_part_floats = (size_t)H_loc * pl.nsplit * (hd + kAttRecPad);
+    pl.ok = true;
+    return pl;
+}
+
+void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, const void* wo, const void* wug, const void* wdown,
+                      const void* cls, int d, int q_loc, int kv_loc, int I_loc, int V_loc) {
+    auto layer_ptr = [&](const void* base, int rows, int cols, int kind, int l) {
+        return reinterpret_cast<const uint8_t*>(base) + (size_t)l * mega_tile_geom(phys_rows(rows, kind), cols, w_dtype).bytes;
+    };
+    for (int l = 0; l < L; ++l) {
+        fill_desc(host[4 * l + 0], layer_ptr(wqkv, q_loc + 2 * kv_loc, d, PH_QKV, l), q_loc + 2 * kv_loc, d, PH_QKV, l, w_dtype);
+        fill_desc(host[4 * l + 1], layer_ptr(wo, d, q_loc, PH_WO, l), d, q_loc, PH_WO, l, w_dtype);
+        fill_desc(host[4 * l + 2], layer_ptr(wug, 2 * I_loc, d, PH_GATEUP, l), 2 * I_loc, d, PH_GATEUP, l, w_dtype);
+        fill_desc(host[4 * l + 3], layer_ptr(wdown, d, I_loc, PH_DOWN, l), d, I_loc, PH_DOWN, l, w_dtype);
+    }
+    fill_desc(host[4 * L], cls, V_loc, d, PH_CLS, L, w_dtype);
+}
+
+// ---- row-major -> tiled, one thread per 16-byte chunk of the destination (padding chunks are zeroed)
+__global__ void repack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int rows, int nchunks, int kind, int KS, int SC, int R,
+                              int ntr, int hd, int q_loc, int kv_loc, int I_loc) {
+    const int64_t total = (int64_t)ntr * KS * R * SC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % SC);
+        const int rr = (int)((i / SC) % R);
+        const int ks = (int)((i / ((int64_t)SC * R)) % KS);
+        const int g = (int)(i / ((int64_t)SC * R * KS));
+        const int pr = g * R + rr;                 // physical row = 2*unit + member
+        const int u = pr >> 1, m = pr & 1;
+        int r0, r1;
+        if (kind == PH_QKV) {
+            const int half = hd >> 1, rope_units = (q_loc + kv_loc) >> 1;
+            if (u < rope_units) { const int head = u / half; r0 = head * hd + (u - head * half); r1 = r0 + half; }
+            else { r0 = q_loc + kv_loc + 2 * (u - rope_units); r1 = r0 + 1; }
+        } else if (kind == PH_GATEUP) { r0 = u; r1 = I_loc + u; }
+        else { r0 = 2 * u; r1 = r0 + 1; }
+        const int row = m ? r1 : r0;
+        const int c = ks * SC + cc;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < rows && c < nchunks) v = src[(int64_t)row * nchunks + c];
+        dst[i] = v;
+    }
+}
+
+int mega_repack(const void* src, void* dst, int rows, int cols, int kind, int w_dtype, int hd, int q_loc, int kv_loc, int I_loc, cudaStream_t st) {
+    const TileGeom g = mega_tile_geom(phys_rows(rows, kind), cols, w_dtype);
+    const int64_t total = (int64_t)g.ntr * g.KS * g.R * g.SC;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    repack_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), rows, g.nchunks, kind, g.KS, g.SC,
+                                          g.R, g.ntr, hd, q_loc, kv_loc, I_loc);
+    g_launches++;
+    SLLM_LAUNCH_CHECK();
+    return SLLM_OK;
+}
+
+template <int WD, int KVD, int G>
+static int mega_launch_t(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        SLLM_CUDA(cudaFuncSetAttribute(mega_step_kernel<WD, KVD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kMegaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SLLM_CUDA(cudaLaunchKernelEx(&cfg, mega_step_kernel<WD, KVD, G>, p));
+    g_launches++;
+    return SLLM_OK;
+}
+
+int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st) {
+#define MEGA_G(GG)                                                                                        \
+    case GG:                                                                                              \
+        if (p.w_dtype == SLLM_F32) {                                                                      \
+            return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_F32, SLLM_F32, GG>(p, grid, smem, st)      \
+                                          : mega_launch_t<SLLM_F32, SLLM_BF16, GG>(p, grid, smem, st);    \
+        }                                                                                                 \
+        return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_BF16, SLLM_F32, GG>(p, grid, smem, st)         \
+                                      : mega_launch_t<SLLM_BF16, SLLM_BF16, GG>(p, grid, smem, st);
+    switch (g) {
+        MEGA_G(1)
+        MEGA_G(2)
+        MEGA_G(4)
+        MEGA_G(8)
+        default: set_error("megakernel: %d query heads per KV head not instantiated", g); return SLLM_ENOTSUP;
+    }
+#undef MEGA_G
+}
+
+}  // namespace sllm

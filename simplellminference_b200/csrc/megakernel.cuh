@@ -1,0 +1,71 @@
+// csrc/megakernel.cuh — host-side interface of the persistent decode-step kernel (megakernel.cu).
+#pragma once
+#include "decode_fused.cuh"
+
+namespace sllm {
+
+// Megakernel weight layout ("tiled"): the rows of a phase's matrix are first put in UNIT ORDER — unit u owns
+// physical rows 2u, 2u+1 = the two logical rows its epilogue needs together (RoPE partners j / j+hd/2 of a q or k
+// head, two consecutive v rows, (up_u, gate_u), or two consecutive rows) — and then cut into tiles of R physical
+// rows x SC 16-byte chunks; tile (g, ks) (row group g, K slice ks) is CONTIGUOUS at (g*KS + ks) * tile_bytes,
+// rows inside a tile SC*16 bytes apart. One ring slot == one tile == ONE cp.async.bulk (measured on B200: a bulk
+// copy costs ~46 cycles of TMA issue per SM whatever its size, so 1 KB copies cap the stream at the HBM rate).
+// K is zero-padded to KS*SC chunks, rows to a multiple of R.
+struct PhaseDesc {       // one weight phase, built on the host
+    const uint8_t* W;    // tiled matrix
+    int32_t nchunks;     // real 16-byte chunks per logical row
+    int32_t nunits;      // two-row units
+    int32_t nrows;       // logical rows
+    int32_t kind, layer;
+    int32_t KS;          // K slices (power of two <= 16); RG = 16 / KS row groups stream concurrently
+    int32_t SC;          // chunks per slice
+    int32_t R;           // physical rows per tile (4 or 2)
+    int32_t ntr;         // tile rows = ceil(2*nunits / R)
+    int32_t tile_bytes;  // R * SC * 16
+};
+
+// geometry of a [rows][cols] matrix in the tiled layout
+struct TileGeom { int nchunks, KS, SC, R, ntr, tile_bytes; size_t bytes; };
+TileGeom mega_tile_geom(int rows_phys, int cols, int w_dtype);
+// bytes of one [rows][cols] matrix of phase kind `kind` in the tiled layout
+size_t mega_matrix_bytes(int rows, int cols, int kind, int w_dtype);
+
+struct MegaParams {
+    const PhaseDesc* phases;   // [4L+1]
+    int32_t d, hd, L, S, V, V_loc, v0, q_loc, kv_loc, I_loc, H_loc, KVH_loc, nsplit;
+    int32_t w_dtype, kv_dtype;
+    float eps;
+    const uint8_t* emb;        // [V][d] storage dtype
+    const float* norms;        // [(2L+1)][d]
+    uint8_t *kc, *vc;          // HEAD-MAJOR cache [L][KVH_loc][S][hd] kv dtype: a tile of positions of one head is contiguous
+    const float *sin_t, *cos_t;
+    float *x, *h, *q, *swi, *logits;
+    float* att_part;           // [H_loc][nsplit][hd+4]
+    float* blk_val;
+    int32_t* blk_idx;
+    StepState* st;
+    const int32_t* prompt;
+    int32_t* history;
+    unsigned* bar_counter;
+    unsigned long long* trace;  // optional [grid][512][8] %globaltimer stamps (nullptr = off)
+};
+
+struct MegaPlan {
+    bool ok = false;
+    int grid = 0;
+    size_t smem = 0;
+    int nsplit = 1;
+    size_t att_part_floats = 0;
+    const char* why = "";
+};
+
+MegaPlan mega_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len);
+void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, const void* wo, const void* wug, const void* wdown,
+                      const void* cls, int d, int q_loc, int kv_loc, int I_loc, int V_loc);
+// row-major [rows][cols] (storage dtype) -> tiled layout in unit order. kind: PH_* (row pairing rule).
+int mega_repack(const void* src_rowmajor, void* dst_tiled, int rows, int cols, int kind, int w_dtype, int hd, int q_loc, int kv_loc,
+                int I_loc, cudaStream_t st);
+enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4 };
+int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st);
+
+}  // namespace sllm

@@ -35,13 +35,15 @@ def logit_tol(want):
 
 
 @pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
-@pytest.mark.parametrize("mode", ["fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
+@pytest.mark.parametrize("mode", ["mega", "fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
 def test_golden_models(golden_models, name, mode):
     """Token streams and final logits recorded from the reference itself (tests/golden/models_ref.npz)."""
     prompt, n_total, wd = mg.MODEL_RUNS[name]
     ms = PRESETS[PRESET_OF[name]]
-    kw = dict(fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
+    kw = dict(mega=dict(mega=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
+    if mode == "mega":
+        assert eng.mode == ("megakernel" if wd != INT8 else "fused+graph"), eng.mode   # int8 falls back, loudly visible
     toks = eng.greedy(prompt, n_total)
     want = golden_models[name + "/tokens"]
     assert np.array_equal(toks, want), (np.flatnonzero(toks != want)[:5], toks[:8], want[:8])
@@ -51,8 +53,7 @@ def test_golden_models(golden_models, name, mode):
     assert err <= logit_tol(want_l), err
     srt = np.sort(want_l)
     assert srt[-1] - srt[-2] >= 20 * err or err < 1e-5
-    kv = ms.kv_hidden
-    k_last = eng.buffer("key_cache")[(n_total - 2) * kv:(n_total - 1) * kv].float().cpu().numpy()
+    k_last = eng.kv_row("k", 0, n_total - 2).float().cpu().numpy()
     want_k = golden_models[name + "/k_l0_last"]
     assert float(np.abs(k_last - want_k).max()) <= logit_tol(want_k)
     x_last, want_x = eng.buffer("emb_output").cpu().numpy(), golden_models[name + "/x_last"]
@@ -74,12 +75,13 @@ def test_blob_loader_equals_synthetic(port):
         a.close(); b.close()
 
 
-def test_forward_api_matches_oracle_per_position(port):
+@pytest.mark.parametrize("mega", [True, False])
+def test_forward_api_matches_oracle_per_position(port, mega):
     """LlamaModel::forward semantics: explicit (token, pos), logits back on the host, every position checked."""
     ms = PRESETS["tiny_mha_hd48"]
     blob = port.fill_blob(oracle_shape(ms), 42)
     om = port.model(oracle_shape(ms), blob)
-    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_blob(blob)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32, mega=mega).load_blob(blob)
     tok = 5
     for pos in range(ms.max_len):
         want = om.forward(tok, pos)
@@ -90,15 +92,16 @@ def test_forward_api_matches_oracle_per_position(port):
     eng.close()
 
 
+@pytest.mark.parametrize("mega", [True, False])
 @pytest.mark.parametrize("wd,kvd", [(BF16, BF16), (INT8, BF16), (F32, BF16)])
-def test_bf16_kv_cache_variant(port, wd, kvd):
+def test_bf16_kv_cache_variant(port, wd, kvd, mega):
     """bf16 KV cache has no reference implementation: its definition is the oracle with cache rows rounded to
     bf16 (orc_set_kv_bf16). Tokens identical, logits within the decode tolerance."""
     ms = PRESETS["tiny_gqa"]
     blob = port.fill_blob(oracle_shape(ms), 7, wd, 64)
     om = port.model(oracle_shape(ms), blob, kv_bf16=True)
     want, want_l = om.greedy([1, 9], 46)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd).load_synthetic(7)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, mega=mega).load_synthetic(7)
     got = eng.greedy([1, 9], 46)
     logits = eng.buffer("model_pred").cpu().numpy()
     err = float(np.abs(logits - want_l).max())
@@ -124,12 +127,13 @@ def test_full_context_and_state_api(port):
     eng.close()
 
 
-def test_medium_shape_tokens(port):
+@pytest.mark.parametrize("mega", [True, False])
+def test_medium_shape_tokens(port, mega):
     """A GQA shape with the production head_dim (128) and a long-ish context, bf16 weights, fp32 KV."""
     ms = ModelShape(4096, 128, 1024, 256, 2816, 160, 4, 8, 2)
     blob = port.fill_blob(oracle_shape(ms), 3, BF16)
     want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1).greedy(list(range(1, 33)), 150)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32).load_synthetic(3)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=mega).load_synthetic(3)
     got = eng.greedy(list(range(1, 33)), 150)
     assert np.array_equal(got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())

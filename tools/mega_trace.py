@@ -1,0 +1,36 @@
+"""tools/mega_trace.py — per-phase time decomposition of the megakernel from its %globaltimer stamps."""
+import argparse, dataclasses, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from simplellminference_b200.config import PRESETS, BF16
+from simplellminference_b200.engine import Engine
+ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4); ap.add_argument("--pos", type=int, default=512)
+a = ap.parse_args()
+ms = dataclasses.replace(PRESETS["llama2-7b"], layers=a.layers)
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True).load_synthetic(1)
+eng.set_state(1, a.pos); eng.enqueue_steps(3); torch.cuda.synchronize()
+tr = eng.buffer(200); torch.cuda.synchronize()
+eng.enqueue_steps(1); torch.cuda.synchronize()
+t = tr.view(torch.int64).cpu().numpy().reshape(-1, 512, 8)
+nev = 5 * a.layers + 1
+names = ["qkv", "att", "wo", "gate_up", "down"]
+t0 = t[:, 0, 0].min()
+print(f"grid={t.shape[0]} step total = {(t[:, nev-1, :5].max() - t0)/1e3:.1f} us")
+agg = {}
+for ev in range(nev):
+    kind = "cls" if ev == nev - 1 else names[ev % 5]
+    s = t[:, ev, :].astype(np.float64)
+    start = s[:, 0]; 
+    row = dict(begin=(start.min() - t0) / 1e3, skew=(start.max() - start.min()) / 1e3)
+    if kind != "att":
+        row.update(prologue=(s[:, 1] - s[:, 0]).mean() / 1e3, stream_mean=(s[:, 3] - s[:, 1]).mean() / 1e3, stream_max=(s[:, 3] - s[:, 1]).max() / 1e3,
+                   stream_min=(s[:, 3] - s[:, 1]).min() / 1e3, epilogue=(s[:, 4] - s[:, 3]).mean() / 1e3)
+    else:
+        row.update(work_mean=(s[:, 4] - s[:, 0]).mean() / 1e3, work_max=(s[:, 4] - s[:, 0]).max() / 1e3)
+    if kind != "cls":
+        row.update(barrier_mean=(s[:, 5] - s[:, 4]).mean() / 1e3, phase_total=(s[:, 5].max() - start.min()) / 1e3)
+    agg.setdefault(kind, []).append(row)
+for kind, rows in agg.items():
+    keys = [k for k in rows[0] if k != "begin"]
+    print(kind.ljust(8), " ".join(f"{k}={np.mean([r[k] for r in rows[1:] or rows]):7.2f}" for k in keys))

@@ -1,0 +1,25 @@
+"""tools/profile_step.py — tiny driver for ncu: a few decode steps of one engine mode at a (possibly layer-cut) shape."""
+import argparse, dataclasses, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from simplellminference_b200.config import PRESETS, BF16, F32, INT8
+from simplellminference_b200.engine import Engine
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="llama2-7b")
+ap.add_argument("--layers", type=int, default=0)
+ap.add_argument("--mode", default="mega", choices=["mega", "fused"])
+ap.add_argument("--pos", type=int, default=512)
+ap.add_argument("--steps", type=int, default=3)
+a = ap.parse_args()
+ms = PRESETS[a.config]
+if a.layers:
+    ms = dataclasses.replace(ms, layers=a.layers)
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega")).load_synthetic(1)
+eng.set_state(1, a.pos)
+eng.enqueue_steps(2); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream); eng.enqueue_steps(a.steps); e1.record(stream); torch.cuda.synchronize()
+msec = e0.elapsed_time(e1) / a.steps
+print(json.dumps({"mode": eng.mode, "layers": ms.layers, "step_ms": round(msec, 4), "GBps": round(eng.step_bytes(a.pos) / msec / 1e6, 0)}))

@@ -13,6 +13,7 @@ ap.add_argument("--ctas", default="0")
 ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--wdtype", default="bf16")
 ap.add_argument("--pdl", action="store_true")
+ap.add_argument("--mega", action="store_true")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 wd = dict(f32=F32, bf16=BF16, int8=INT8)[a.wdtype]
@@ -20,10 +21,10 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 lib = _lib.load()
 for ctas in [int(c) for c in a.ctas.split(",")]:
     lib.sllm_tune(0, ctas)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=a.pdl).load_synthetic(1)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=a.pdl, mega=a.mega).load_synthetic(1)
     eng.set_state(1, a.pos)
-    res = {"ctas_per_sm": ctas, "lib": os.path.basename(_lib.LIB_PATH)}
-    for kind in ("qkv", "mha", "wo", "gate_up", "down"):
+    res = {"ctas_per_sm": ctas, "lib": os.path.basename(_lib.LIB_PATH), "mode": eng.mode}
+    for kind in ([] if a.mega else ("qkv", "mha", "wo", "gate_up", "down")):
         for l in range(ms.layers): eng.enqueue_kernel(kind, l)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,6 +40,7 @@ for ctas in [int(c) for c in a.ctas.split(",")]:
     e0.record(stream); eng.enqueue_steps(32); e1.record(stream); torch.cuda.synchronize()
     res["step_ms"] = round(e0.elapsed_time(e1) / 32, 4)
     res["tok_s"] = round(1e3 / res["step_ms"], 1)
-    res["sum_kernels_ms"] = round(sum(res[k]["us"] for k in ("qkv", "mha", "wo", "gate_up", "down")) * ms.layers / 1e3, 4)
+    if not a.mega: res["sum_kernels_ms"] = round(sum(res[k]["us"] for k in ("qkv", "mha", "wo", "gate_up", "down")) * ms.layers / 1e3, 4)
+    res["step_GBps"] = round(eng.step_bytes(a.pos) / res["step_ms"] / 1e6, 0)
     print(json.dumps(res), flush=True)
     eng.close()
