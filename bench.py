@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--no-mega", action="store_true", help="use the per-kernel fused CUDA-graph path instead of the persistent megakernel")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
     return ap.parse_args()
 
@@ -218,7 +219,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
-                 graph=not (args.no_graph or args.unfused), pdl=args.pdl)
+                 graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused))
     eng.load_synthetic(1234)
     if world > 1:
         eng.init_comm(dist)
@@ -291,10 +292,19 @@ def run_ours(args):
     e2e = {"value": Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4,
            "steps": Ke, "api": "Engine.forward(token,pos) == sllm_engine_forward: LlamaModel::forward semantics + device argmax"}
 
-    # ---- the dominant kernel alone (gate_up: RMSNorm + [Wup;Wgate] GEMV + sigmoid*up), cycling over layers
+    # ---- roofline of the dominant kernel. Megakernel mode: the step IS one kernel (100 % of the timed region), so
+    # achieved = B(p) / its launch duration over the timed region. Per-kernel mode: the largest kernel (gate_up:
+    # RMSNorm + [Wup;Wgate] GEMV + sigmoid*up) timed alone, cycling over the layers so weights come from HBM.
     roof = None
     peak, peak_src = peaks()
-    if not args.unfused:
+    mode = eng.mode
+    if mode == "megakernel":
+        ach = step_bytes / (ms_total * 1e-3 / K) / 1e9
+        roof = {"bound": "hbm", "kernel": "mega_step_kernel (persistent: all layers' qkv|attention|wo|gate_up|down + classifier/argmax)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": step_bytes,
+                "us_per_launch": 1e3 * ms_total / K, "peak_source": peak_src,
+                "how": f"{K} launches = the timed region itself, CUDA events on the launching stream; B(p) per SURVEY.md 8d"}
+    elif not args.unfused:
         eng.set_state(tok, min(pos, ms.max_len - 1))
         reps = max(2, 64 // ms.layers)
         for l in range(ms.layers):
@@ -338,7 +348,7 @@ def run_ours(args):
         "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
         "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
-        "mode": {"fused": not args.unfused, "graph": not (args.no_graph or args.unfused), "pdl": args.pdl},
+        "mode": mode,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
