@@ -1,0 +1,3 @@
+// compat/add.h — forwarding header: code written against the reference includes "add.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

@@ -1,0 +1,3 @@
+// compat/argmax.h — forwarding header: code written against the reference includes "argmax.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

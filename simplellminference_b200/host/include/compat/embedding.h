@@ -1,0 +1,3 @@
+// compat/embedding.h — forwarding header: code written against the reference includes "embedding.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

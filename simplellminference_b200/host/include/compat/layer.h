@@ -1,0 +1,3 @@
+// compat/layer.h — forwarding header: code written against the reference includes "layer.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

@@ -1,0 +1,3 @@
+// compat/matmul_kernel.cuh — forwarding header: code written against the reference includes "matmul_kernel.cuh"; here it lives in sllm/kernel.h.
+#pragma once
+#include "../sllm/kernel.h"

@@ -1,0 +1,3 @@
+// compat/mha.h — forwarding header: code written against the reference includes "mha.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

@@ -1,0 +1,3 @@
+// compat/rmsnorm.h — forwarding header: code written against the reference includes "rmsnorm.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

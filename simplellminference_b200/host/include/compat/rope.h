@@ -1,0 +1,3 @@
+// compat/rope.h — forwarding header: code written against the reference includes "rope.h"; here it lives in sllm/op.h.
+#pragma once
+#include "../sllm/op.h"

@@ -1,0 +1,3 @@
+// compat/rope_kernel.cuh — forwarding header: code written against the reference includes "rope_kernel.cuh"; here it lives in sllm/kernel.h.
+#pragma once
+#include "../sllm/kernel.h"

@@ -1,0 +1,3 @@
+// compat/swiglu_kernel.cuh — forwarding header: code written against the reference includes "swiglu_kernel.cuh"; here it lives in sllm/kernel.h.
+#pragma once
+#include "../sllm/kernel.h"
