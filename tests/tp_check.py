@@ -20,9 +20,15 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     port = loader.Port()
     os.chdir("/tmp")
-    cases = [("tiny_gqa", PRESETS["tiny_gqa"], F32, F32, [1, 7, 300], 40),
-             ("medium_gqa_bf16", ModelShape(4096, 128, 1024, 512, 2816, 160, 4, 8, 4), BF16, BF16, list(range(1, 17)), 120)]
-    for name, ms, wd, kvd, prompt, n_total in cases:
+    medium = ModelShape(4096, 128, 1024, 512, 2816, 160, 4, 8, 4)
+    # (name, shape, weights, kv, prompt, n_total, teacher_forced)
+    # fp32 KV: the greedy stream must be IDENTICAL to the oracle's. bf16 KV: a cache value that sits on a bf16 rounding
+    # boundary may round the other way when the reduction order changes (all-reduce), which can flip a low-margin
+    # token many steps later — so that case is teacher-forced with the oracle's own tokens and judged on the logits.
+    cases = [("tiny_gqa f32", PRESETS["tiny_gqa"], F32, F32, [1, 7, 300], 40, False),
+             ("medium bf16 weights, f32 kv", medium, BF16, F32, list(range(1, 17)), 120, False),
+             ("medium bf16 weights, bf16 kv (teacher forced)", medium, BF16, BF16, list(range(1, 17)), 120, True)]
+    for name, ms, wd, kvd, prompt, n_total, forced in cases:
         if ms.kv_heads % world or ms.heads % world:
             continue
         shape = loader.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, ms.layers, ms.heads, ms.kv_heads, ms.eps, ms.theta)
@@ -31,16 +37,22 @@ def main():
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream).load_synthetic(1234).init_comm(dist)
-        got = eng.greedy(prompt, n_total)
-        assert np.array_equal(got, want), (name, rank, got[:10], want[:10])
+        if forced:
+            got = eng.greedy([prompt[0]] + [int(t) for t in want[:-1]], n_total)   # every input token = the oracle's
+            assert np.array_equal(got[:-1], want[:-1])                              # echo of the forced tokens
+        else:
+            got = eng.greedy(prompt, n_total)
+            assert np.array_equal(got, want), (name, rank, int(np.flatnonzero(got != want)[0]))
         v_loc = ms.vocab // world
         logits = eng.buffer("model_pred").cpu().numpy()
         err = float(np.abs(logits - want_l[rank * v_loc:(rank + 1) * v_loc]).max())
-        tol = (5e-3 if kvd == BF16 else 3e-4) * max(1.0, float(np.abs(want_l).max()))
+        # bf16 KV after 120 teacher-forced tokens: 2e-2 (measured on ONE GPU, tools/kv_bf16_sensitivity.py: 1.2e-2 for both
+        # single-GPU paths, while bf16-vs-fp32 KV itself moves this gain-4 model's logits by 1.2e-1)
+        tol = (2e-2 if kvd == BF16 else 3e-4) * max(1.0, float(np.abs(want_l).max()))
         assert err <= tol, (name, rank, err, tol)
         eng.close()
         if rank == 0:
-            print(f"tp{world} {name}: {n_total - 1} tokens identical on every rank, max|dlogit|={err:.2e}", flush=True)
+            print(f"tp{world} {name}: {n_total - 1} tokens ok on every rank, max|dlogit|={err:.2e} (tol {tol:.1e})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
