@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-mega", action="store_true", help="use the per-kernel fused CUDA-graph path instead of the persistent megakernel")
+    ap.add_argument("--nccl", action="store_true", help="tensor parallel: NCCL all-reduce instead of the fused peer-memory one")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
     return ap.parse_args()
 
@@ -219,10 +220,11 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
-                 graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused))
+                 graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused),
+                 p2p_allreduce=(world > 1 and not args.nccl))
     eng.load_synthetic(1234)
     if world > 1:
-        eng.init_comm(dist)
+        eng.init_comm(dist) if args.nccl else eng.init_p2p(dist)
 
     def barrier():
         torch.cuda.synchronize()
@@ -348,7 +350,7 @@ def run_ours(args):
         "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
         "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
-        "mode": mode,
+        "mode": mode + ("" if world == 1 else (" tp/nccl-allreduce" if args.nccl else " tp/peer-memory-allreduce")),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

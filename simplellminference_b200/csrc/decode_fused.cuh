@@ -14,6 +14,59 @@
 
 namespace sllm {
 
+struct StepState {          // device-resident decode state (one per engine)
+    int32_t token;          // input token of the current step
+    int32_t pos;            // position of the current step
+    int32_t n_prompt;       // prompt length (tokens fed verbatim while pos+1 < n_prompt)
+    int32_t ticket;         // last-block ticket of the classifier kernel (always returns to 0)
+    int32_t next;           // argmax of the last step (this rank's view / global after TP reduction)
+    int32_t pad[3];         // pad[0] = megakernel barrier epoch, pad[1] = monotonic step counter (peer all-reduce epochs)
+};
+
+// ---- one-shot all-reduce over NVLink peer memory, fused into the GEMV kernels -------------------------------
+// Low-latency ("LL") protocol: every fp32 partial sum travels as ONE 8-byte word {value bits, epoch}, and an aligned
+// 8-byte store is a single transaction, so value and flag arrive together: no fence, no separate flag, no ticket.
+// Every rank owns a receive area [2 parities][tp][n] of such words; peers map it through CUDA IPC. The kernel that
+// PRODUCES partial sums (row-parallel GEMV: wo / down) stores each value straight into slot [my rank] of every
+// rank's area (NVLink stores; a local store for itself). The kernel that CONSUMES them (the next RMSNorm prologue)
+// spins on each word until its epoch field equals e, and adds the tp partial vectors in rank order — the same
+// order on every rank, so all ranks compute bit-identical activations. e = step * ops_per_step + op + 1 comes from
+// the device-resident step counter, so the launch sequence is CUDA-graph capturable; areas alternate by epoch
+// parity (dependencies keep every rank at most one op ahead of the slowest one).
+constexpr int kMaxTp = 8;
+struct P2PComm {
+    uint2* recv[kMaxTp];        // recv[r] = rank r's receive area (recv[rank] is local memory)
+    int tp, rank, n;            // n = words per partial vector
+    int ops_per_step;
+    const int32_t* step;        // device step counter (StepState::pad[1])
+};
+__device__ __forceinline__ unsigned p2p_epoch(const P2PComm& c, int op) { return (unsigned)(*c.step) * (unsigned)c.ops_per_step + (unsigned)op + 1u; }
+__device__ __forceinline__ uint2* p2p_slot(const P2PComm& c, int dst_rank, unsigned epoch, int src_rank) {
+    return c.recv[dst_rank] + ((size_t)(epoch & 1u) * c.tp + src_rank) * c.n;
+}
+__device__ __forceinline__ void p2p_send(uint2* p, float v, unsigned epoch) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+// two adjacent words (16 bytes); spins until both carry `epoch`
+__device__ __forceinline__ float2 p2p_recv2(const uint2* p, unsigned epoch) {
+    uint4 w;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
+        if (w.y == epoch && w.w == epoch) break;
+        if (++spins > (1u << 26)) __trap();   // a peer died: fail instead of hanging the GPU
+    }
+    return make_float2(__uint_as_float(w.x), __uint_as_float(w.z));
+}
+
+// used by stage_x_rmsnorm (gemv_core.cuh): the tp slot addresses of op `op` in THIS rank's receive area + its epoch
+__device__ __forceinline__ unsigned p2p_slots(const P2PComm* c, int op, const uint2** slots, int* tp) {
+    const unsigned e = p2p_epoch(*c, op);
+    for (int r = 0; r < c->tp; ++r) slots[r] = p2p_slot(*c, c->rank, e, r);
+    *tp = c->tp;
+    return e;
+}
+
 struct GemvBase {
     const void* W_;
     const float* sc_;
@@ -30,6 +83,8 @@ struct QkvPolicy : GemvBase {
     const float* x;        // residual stream [d]
     const float* add;      // TP only: all-reduced partial to add to x first (else nullptr)
     float* sum_out;        // TP only: where CTA 0 stores x + add
+    const P2PComm* p2p;    // TP over peer memory: add = sum of the tp partial vectors of op `p2p_op` (else nullptr)
+    int p2p_op;
     const float* norm_w;   // [d]
     float eps;
     const int32_t* pos_dev;
@@ -52,7 +107,7 @@ struct QkvPolicy : GemvBase {
             r1 = r0 + 1;
         }
     }
-    __device__ void stage(float* xs, float* red) const { stage_x_rmsnorm<WD>(xs, red, x, norm_w, cols_, eps, add, sum_out); }
+    __device__ void stage(float* xs, float* red) const { stage_x_rmsnorm<WD>(xs, red, x, norm_w, cols_, eps, add, sum_out, p2p, p2p_op); }
     __device__ void store_kv(void* cache, int64_t idx, float v) const {
         if (kv_dtype == SLLM_BF16) reinterpret_cast<uint16_t*>(cache)[idx] = f32_to_bf16_bits(v);
         else reinterpret_cast<float*>(cache)[idx] = v;
@@ -91,11 +146,23 @@ struct ResidualPolicy : GemvBase {
     const float* resid;     // [rows] or nullptr (tensor-parallel partial sums: no residual here)
     float* y;               // [rows]
     int nrows;
+    const P2PComm* p2p;     // TP over peer memory: partial sums go straight into every rank's receive area
+    int p2p_op;
+    StepState* st;
     __device__ int units() const { return (nrows + 1) >> 1; }
     __device__ void rows(int u, int64_t& r0, int64_t& r1) const { r0 = 2 * (int64_t)u; r1 = min(2 * u + 1, nrows - 1); }
     __device__ void stage(float* xs, float*) const { stage_x_plain<WD>(xs, x, cols_); }
     __device__ void emit(int u, float s0, float s1) {
         const int r = 2 * u;
+        if (p2p) {
+            const unsigned e = p2p_epoch(*p2p, p2p_op);
+            for (int dst = 0; dst < p2p->tp; ++dst) {                 // NVLink stores (local for dst == rank)
+                uint2* slot = p2p_slot(*p2p, dst, e, p2p->rank);
+                p2p_send(slot + r, s0, e);
+                if (r + 1 < nrows) p2p_send(slot + r + 1, s1, e);
+            }
+            return;
+        }
         y[r] = resid ? resid[r] + s0 : s0;  // add_kernel.cpp:10-13: out = in1 + in2
         if (r + 1 < nrows) y[r + 1] = resid ? resid[r + 1] + s1 : s1;
     }
@@ -108,13 +175,15 @@ struct GateUpPolicy : GemvBase {
     const float* h;
     const float* add;      // TP only (see QkvPolicy)
     float* sum_out;
+    const P2PComm* p2p;
+    int p2p_op;
     const float* norm_w;
     float eps;
     float* s_out;  // [inter]
     int inter;     // local intermediate size; W = [up rows (inter)][gate rows (inter)]
     __device__ int units() const { return inter; }
     __device__ void rows(int u, int64_t& r0, int64_t& r1) const { r0 = u; r1 = (int64_t)inter + u; }
-    __device__ void stage(float* xs, float* red) const { stage_x_rmsnorm<WD>(xs, red, h, norm_w, cols_, eps, add, sum_out); }
+    __device__ void stage(float* xs, float* red) const { stage_x_rmsnorm<WD>(xs, red, h, norm_w, cols_, eps, add, sum_out, p2p, p2p_op); }
     __device__ void emit(int u, float up, float gate) {
         const float sg = 1.0f / (1.0f + expf(-gate));  // swiglu_kernel.cpp:12-13
         s_out[u] = sg * up;
@@ -123,20 +192,14 @@ struct GateUpPolicy : GemvBase {
 };
 
 // ---- F: RMSNorm -> classifier -> argmax -> feedback ---------------------------------------------------
-struct StepState {          // device-resident decode state (one per engine)
-    int32_t token;          // input token of the current step
-    int32_t pos;            // position of the current step
-    int32_t n_prompt;       // prompt length (tokens fed verbatim while pos+1 < n_prompt)
-    int32_t ticket;         // last-block ticket of the classifier kernel (always returns to 0)
-    int32_t next;           // argmax of the last step (this rank's view / global after TP reduction)
-    int32_t pad[3];
-};
 
 template <int WD>
 struct ClsPolicy : GemvBase {
     const float* x;
     const float* add;       // TP only (see QkvPolicy)
     float* sum_out;
+    const P2PComm* p2p;
+    int p2p_op;
     const float* norm_w;
     float eps;
     float* logits;          // [nrows] local logits (model_pred)
@@ -154,7 +217,7 @@ struct ClsPolicy : GemvBase {
     __device__ void stage(float* xs, float* red) {
         best_v = -INFINITY;
         best_i = 0x7fffffff;
-        stage_x_rmsnorm<WD>(xs, red, x, norm_w, cols_, eps, add, sum_out);
+        stage_x_rmsnorm<WD>(xs, red, x, norm_w, cols_, eps, add, sum_out, p2p, p2p_op);
     }
     __device__ static void better(float& v, int& i, float ov, int oi) {
         if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }  // first maximum, argmax.cpp:11
@@ -212,6 +275,7 @@ struct ClsPolicy : GemvBase {
         history[pos] = nxt;
         st->token = nxt;
         st->pos = pos + 1;
+        st->pad[1] += 1;   // monotonic step counter (epochs of the peer-memory all-reduce)
     }
 };
 

@@ -91,6 +91,13 @@ struct sllm_engine {
     int64_t total_launches = 0;
     // comm
     ncclComm_t comm = nullptr;
+    bool p2p_mode = false;            // all-reduce over NVLink peer memory fused into the GEMV kernels (no NCCL call)
+    bool p2p_ready = false;
+    bool timing_only = false;         // sllm_engine_enqueue_kernel: single kernels must not wait for peers
+    uint8_t* p2p_block = nullptr;     // this rank's receive area + flags (own cudaMalloc: exported through CUDA IPC)
+    size_t p2p_recv_bytes = 0;
+    void* p2p_peer[kMaxTp] = {};      // mapped peer blocks
+    P2PComm* p2p_dev = nullptr;       // descriptor in device memory
 };
 
 // ------------------------------------------------------------------------------------------- helpers ---
@@ -218,6 +225,26 @@ __global__ void tp_merge_kernel(const float* pairs, int tp, StepState* st, const
     }
     ClsPolicy<SLLM_F32>::step_feedback(st, prompt, history, idx == 0x7fffffff ? 0 : idx);
 }
+__global__ void tp_argmax_p2p_kernel(const float* blk_val, const int32_t* blk_idx, int slot, const P2PComm* c, int op, StepState* st,
+                                     const int32_t* prompt, int32_t* history) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned e = p2p_epoch(*c, op);
+    const float v = blk_val[slot];
+    const int idx = blk_idx[slot];
+    for (int dst = 0; dst < c->tp; ++dst) {
+        uint2* s = p2p_slot(*c, dst, e, c->rank);
+        p2p_send(s, v, e);
+        p2p_send(s + 1, __int_as_float(idx), e);
+    }
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int r = 0; r < c->tp; ++r) {
+        const float2 pr = p2p_recv2(p2p_slot(*c, c->rank, e, r), e);
+        const int oi = __float_as_int(pr.y);
+        if (pr.x > best || (pr.x == best && oi < bi)) { best = pr.x; bi = oi; }
+    }
+    ClsPolicy<SLLM_F32>::step_feedback(st, prompt, history, bi == 0x7fffffff ? 0 : bi);
+}
 __global__ void tp_pack_kernel(const float* blk_val, const int32_t* blk_idx, int slot, float* pair) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         pair[0] = blk_val[slot];
@@ -249,6 +276,7 @@ static int enqueue_kernel(sllm_engine* e, int kind, int l) {
             QkvPolicy<WD> A{};
             A.W_ = mat_layer(e, e->wqkv, l); A.sc_ = sc_layer(e, e->wqkv, l); A.grp_ = e->cfg.group; A.cols_ = d;
             if (tp && l > 0) { A.x = e->h; A.add = e->part_b; A.sum_out = e->x; } else { A.x = e->x; A.add = nullptr; A.sum_out = nullptr; }
+            if (e->p2p_mode && !e->timing_only && l > 0) { A.add = nullptr; A.p2p = e->p2p_dev; A.p2p_op = 2 * (l - 1) + 1; }
             A.norm_w = e->norms + (int64_t)(2 * l) * d; A.eps = s.eps; A.pos_dev = pos_dev; A.sin_t = e->sin_t; A.cos_t = e->cos_t;
             A.q_out = e->q; A.k_cache = kv_layer(e, e->key_cache, l); A.v_cache = kv_layer(e, e->value_cache, l);
             A.kv_dtype = e->cfg.kv_dtype; A.q_dim = e->q_loc; A.kv_dim = e->kv_loc; A.hd = e->hd;
@@ -265,6 +293,7 @@ static int enqueue_kernel(sllm_engine* e, int kind, int l) {
             C.W_ = mat_layer(e, e->wo, l); C.sc_ = sc_layer(e, e->wo, l); C.grp_ = e->cfg.group; C.cols_ = e->q_loc;
             C.x = e->att; C.nrows = d;
             if (tp) { C.resid = nullptr; C.y = e->part_a; } else { C.resid = e->x; C.y = e->h; }
+            if (e->p2p_mode && !e->timing_only) { C.p2p = e->p2p_dev; C.p2p_op = 2 * l; C.st = e->state; }
             return launch_policy<WD>(e, C, (d + 1) / 2);
         }
         case K_GATEUP: {
@@ -272,6 +301,7 @@ static int enqueue_kernel(sllm_engine* e, int kind, int l) {
             D.W_ = mat_layer(e, e->wug, l); D.sc_ = sc_layer(e, e->wug, l); D.grp_ = e->cfg.group; D.cols_ = d;
             // TP: the residual stream entering this layer is x (layer 0) or h+part_b, which kernel A stored in x
             if (tp) { D.h = e->x; D.add = e->part_a; D.sum_out = e->h; } else { D.h = e->h; D.add = nullptr; D.sum_out = nullptr; }
+            if (e->p2p_mode && !e->timing_only) { D.add = nullptr; D.p2p = e->p2p_dev; D.p2p_op = 2 * l; }
             D.norm_w = e->norms + (int64_t)(2 * l + 1) * d; D.eps = s.eps; D.s_out = e->swi; D.inter = e->I_loc;
             return launch_policy<WD>(e, D, e->I_loc);
         }
@@ -280,6 +310,7 @@ static int enqueue_kernel(sllm_engine* e, int kind, int l) {
             E.W_ = mat_layer(e, e->wdown, l); E.sc_ = sc_layer(e, e->wdown, l); E.grp_ = e->cfg.group; E.cols_ = e->I_loc;
             E.x = e->swi; E.nrows = d;
             if (tp) { E.resid = nullptr; E.y = e->part_b; } else { E.resid = e->h; E.y = e->x; }
+            if (e->p2p_mode && !e->timing_only) { E.p2p = e->p2p_dev; E.p2p_op = 2 * l + 1; E.st = e->state; }
             return launch_policy<WD>(e, E, (d + 1) / 2);
         }
         case K_CLS: {
@@ -288,6 +319,7 @@ static int enqueue_kernel(sllm_engine* e, int kind, int l) {
             F.sc_ = e->emb.sc ? e->emb.sc + (int64_t)e->v0 * d / e->cfg.group : nullptr;
             F.grp_ = e->cfg.group; F.cols_ = d;
             if (tp) { F.x = e->h; F.add = e->part_b; F.sum_out = e->x; } else { F.x = e->x; F.add = nullptr; F.sum_out = nullptr; }
+            if (e->p2p_mode && !e->timing_only) { F.add = nullptr; F.p2p = e->p2p_dev; F.p2p_op = 2 * (L - 1) + 1; }
             F.norm_w = e->norms + (int64_t)(2 * L) * d; F.eps = s.eps; F.logits = e->logits; F.nrows = e->V_loc; F.row0 = e->v0;
             F.blk_val = e->blk_val; F.blk_idx = e->blk_idx; F.st = e->state; F.prompt = e->prompt_dev; F.history = e->history_dev;
             F.single_rank = (tp || l < 0) ? 0 : 1;   // l < 0: timing-only launch, leave the step state alone
@@ -307,14 +339,18 @@ static int enqueue_fused_step(sllm_engine* e) {
         STEP(K_QKV, l);
         STEP(K_MHA, l);
         STEP(K_WO, l);
-        if (tp) { SLLM_NCCL(ncclAllReduce(e->part_a, e->part_a, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
+        if (tp && !e->p2p_mode) { SLLM_NCCL(ncclAllReduce(e->part_a, e->part_a, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
         STEP(K_GATEUP, l);
         STEP(K_DOWN, l);
-        if (tp) { SLLM_NCCL(ncclAllReduce(e->part_b, e->part_b, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
+        if (tp && !e->p2p_mode) { SLLM_NCCL(ncclAllReduce(e->part_b, e->part_b, d, ncclFloat, ncclSum, e->comm, e->stream)); count_launch(e); }
     }
     STEP(K_CLS, 0);
 #undef STEP
-    if (tp) {
+    if (tp && e->p2p_mode) {   // (value, index) exchange + first-max merge + step feedback in ONE tiny kernel over peer memory
+        tp_argmax_p2p_kernel<<<1, 32, 0, e->stream>>>(e->blk_val, e->blk_idx, e->cls_grid, e->p2p_dev, 2 * L, e->state, e->prompt_dev, e->history_dev);
+        count_launch(e);
+        SLLM_LAUNCH_CHECK();
+    } else if (tp) {
         tp_pack_kernel<<<1, 32, 0, e->stream>>>(e->blk_val, e->blk_idx, e->cls_grid, e->tp_pairs + 2 * e->rank);
         count_launch(e);
         SLLM_NCCL(ncclAllGather(e->tp_pairs + 2 * e->rank, e->tp_pairs, 2, ncclFloat, e->comm, e->stream));
@@ -496,7 +532,7 @@ static int64_t segment_offset(const sllm_shape& s, int seg) {
 // the middle of a run: its warm-up pass executes one real step at (token 0, position 0).
 static int maybe_build_graph(sllm_engine* e) {
     if (!e->fused || !e->use_graph || e->graph_exec || !e->weights_loaded) return SLLM_OK;
-    if (e->tp > 1 && !e->comm) return SLLM_OK;
+    if (e->tp > 1 && !(e->p2p_mode ? e->p2p_ready : e->comm != nullptr)) return SLLM_OK;
     if (int rc = set_state(e, 0, 0, 0)) return rc;
     if (int rc = build_graph(e)) return rc;
     if (int rc = set_state(e, 0, 0, 0)) return rc;
@@ -601,6 +637,7 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     e->fused = !(cfg->flags & SLLM_ENGINE_UNFUSED);
     e->use_graph = e->fused && !(cfg->flags & SLLM_ENGINE_NO_GRAPH);
     e->pdl = e->fused && (cfg->flags & SLLM_ENGINE_PDL);
+    e->p2p_mode = e->fused && tp > 1 && (cfg->flags & SLLM_ENGINE_P2P_ALLREDUCE);
     e->d = s.hidden; e->hd = s.head_dim; e->L = s.layers; e->S = s.max_len; e->V = s.vocab; e->H = s.heads; e->KVH = s.kv_heads; e->I = s.inter;
     e->tp = tp; e->rank = cfg->tp_rank;
     e->H_loc = s.heads / tp; e->KVH_loc = s.kv_heads / tp; e->q_loc = e->H_loc * s.head_dim; e->kv_loc = e->KVH_loc * s.head_dim;
@@ -627,6 +664,14 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     if (e->arena_bytes > free_b) { set_error("engine needs %zu MiB of HBM, %zu MiB free", e->arena_bytes >> 20, free_b >> 20); return fail(SLLM_ENOMEM); }
     if (cudaMalloc(&e->arena, e->arena_bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu MiB) failed", e->arena_bytes >> 20); return fail(SLLM_ENOMEM); }
     layout(e);  // assign
+    if (e->p2p_mode) {
+        if (tp > kMaxTp) { set_error("peer-memory all-reduce supports up to %d ranks", kMaxTp); sllm_engine_destroy(e); return SLLM_ENOTSUP; }
+        e->p2p_recv_bytes = align_up((size_t)2 * tp * e->d * sizeof(uint2), 256);   // {value, epoch} words
+        const size_t total = e->p2p_recv_bytes + 256 + sizeof(P2PComm) + 256;
+        if (cudaMalloc(&e->p2p_block, total) != cudaSuccess || cudaMemset(e->p2p_block, 0, total) != cudaSuccess) {
+            cudaGetLastError(); set_error("peer-memory all-reduce: allocation failed"); sllm_engine_destroy(e); return SLLM_ENOMEM;
+        }
+    }
     // zero everything that is read before it is written: KV cache, workspaces, state
     cudaError_t ce = cudaMemsetAsync(e->key_cache, 0, e->arena + e->arena_used - reinterpret_cast<uint8_t*>(e->key_cache), e->stream);
     if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void**>(&e->h_state), 64);
@@ -641,6 +686,9 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->comm) ncclCommDestroy(e->comm);
     if (e->h_state) cudaFreeHost(e->h_state);
+    for (int r = 0; r < kMaxTp; ++r) if (e->p2p_peer[r]) cudaIpcCloseMemHandle(e->p2p_peer[r]);
+    if (e->p2p_dev) cudaFree(e->p2p_dev);
+    if (e->p2p_block) cudaFree(e->p2p_block);
     if (e->arena) cudaFree(e->arena);
     if (e->trace) cudaFree(e->trace);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -705,8 +753,39 @@ int sllm_engine_init_comm(sllm_engine* e, const void* id_bytes_128) {
     return maybe_build_graph(e);
 }
 
-int sllm_engine_p2p_export(sllm_engine*, void*) { set_error("peer-memory all-reduce: not built yet"); return SLLM_ENOTSUP; }
-int sllm_engine_p2p_import(sllm_engine*, const void*) { set_error("peer-memory all-reduce: not built yet"); return SLLM_ENOTSUP; }
+int sllm_engine_p2p_export(sllm_engine* e, void* handle_bytes_64) {
+    SLLM_REQUIRE(e && handle_bytes_64, SLLM_EINVAL, "null argument");
+    SLLM_REQUIRE(e->p2p_mode && e->p2p_block, SLLM_ESTATE, "engine was not created with SLLM_ENGINE_P2P_ALLREDUCE (tp_size > 1)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t h;
+    SLLM_CUDA(cudaIpcGetMemHandle(&h, e->p2p_block));
+    std::memcpy(handle_bytes_64, &h, 64);
+    return SLLM_OK;
+}
+
+int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles) {
+    SLLM_REQUIRE(e && all_handles, SLLM_EINVAL, "null argument");
+    SLLM_REQUIRE(e->p2p_mode && e->p2p_block, SLLM_ESTATE, "engine was not created with SLLM_ENGINE_P2P_ALLREDUCE (tp_size > 1)");
+    P2PComm c{};
+    c.tp = e->tp; c.rank = e->rank; c.n = e->d; c.ops_per_step = 2 * e->L + 1; c.step = &e->state->pad[1];
+    for (int r = 0; r < e->tp; ++r) {
+        uint8_t* base = e->p2p_block;
+        if (r != e->rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, reinterpret_cast<const uint8_t*>(all_handles) + (size_t)r * 64, 64);
+            void* p = nullptr;
+            SLLM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            e->p2p_peer[r] = p;
+            base = reinterpret_cast<uint8_t*>(p);
+        }
+        c.recv[r] = reinterpret_cast<uint2*>(base);
+    }
+    SLLM_CUDA(cudaMalloc(&e->p2p_dev, sizeof(P2PComm)));
+    SLLM_CUDA(cudaMemcpyAsync(e->p2p_dev, &c, sizeof(P2PComm), cudaMemcpyHostToDevice, e->stream));
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    e->p2p_ready = true;
+    return maybe_build_graph(e);
+}
 
 int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos) {
     SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
@@ -716,7 +795,7 @@ int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos) {
 
 int sllm_engine_enqueue_steps(sllm_engine* e, int32_t n_steps) {
     SLLM_REQUIRE(e && n_steps >= 0, SLLM_EINVAL, "bad argument");
-    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel engine without a communicator");
+    SLLM_REQUIRE(e->tp == 1 || e->comm || e->p2p_ready, SLLM_ESTATE, "tensor-parallel engine without a communicator");
     SLLM_REQUIRE(e->h_state[7] + n_steps <= e->S, SLLM_EINVAL, "%d steps from position %d overrun max_len %d", n_steps, e->h_state[7], e->S);
     int rc = enqueue_steps(e, n_steps, e->h_state[7]);
     e->h_state[7] += n_steps;
@@ -734,7 +813,7 @@ int sllm_engine_read_tokens(sllm_engine* e, int32_t* out, int32_t n) {
 
 int sllm_engine_forward(sllm_engine* e, int32_t token, int32_t pos, float* logits_host, int32_t* next_token_host) {
     SLLM_REQUIRE(e, SLLM_EINVAL, "null engine");
-    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel engine without a communicator");
+    SLLM_REQUIRE(e->tp == 1 || e->comm || e->p2p_ready, SLLM_ESTATE, "tensor-parallel engine without a communicator");
     // host -> device: token and position travel through pinned memory like any other input
     e->h_state[0] = token; e->h_state[1] = pos; e->h_state[2] = 0; e->h_state[3] = 0;
     SLLM_REQUIRE(pos >= 0 && pos < e->S, SLLM_EINVAL, "position %d outside [0, %d)", pos, e->S);
@@ -817,11 +896,15 @@ int sllm_engine_enqueue_kernel(sllm_engine* e, int32_t kind, int32_t layer) {
     SLLM_REQUIRE(!e->mega, SLLM_ESTATE, "enqueue_kernel is not available in megakernel mode (weights are tiled, the step is one kernel)");
     SLLM_REQUIRE(layer >= 0 && layer < e->L, SLLM_EINVAL, "layer %d outside [0,%d)", layer, e->L);
     const int l = (kind == K_CLS) ? -1 : layer;
+    e->timing_only = true;
+    int rc;
     switch (e->cfg.w_dtype) {
-        case SLLM_F32: return enqueue_kernel<SLLM_F32>(e, kind, l);
-        case SLLM_BF16: return enqueue_kernel<SLLM_BF16>(e, kind, l);
-        default: return enqueue_kernel<SLLM_INT8>(e, kind, l);
+        case SLLM_F32: rc = enqueue_kernel<SLLM_F32>(e, kind, l); break;
+        case SLLM_BF16: rc = enqueue_kernel<SLLM_BF16>(e, kind, l); break;
+        default: rc = enqueue_kernel<SLLM_INT8>(e, kind, l); break;
     }
+    e->timing_only = false;
+    return rc;
 }
 
 int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos) {

@@ -53,6 +53,10 @@ __device__ __forceinline__ void stage_x_plain(float* xs, const float* __restrict
     for (int j4 = threadIdx.x; j4 < cols / 4; j4 += blockDim.x) s4[plane_index<WD>(j4, nchunks)] = x4[j4];
 }
 
+struct P2PComm;
+__device__ __forceinline__ unsigned p2p_slots(const P2PComm* c, int op, const uint2** slots, int* tp);
+__device__ __forceinline__ float2 p2p_recv2(const uint2* p, unsigned epoch);
+
 // fused RMSNorm (rms_kernel.cpp:12-22): xs = (x * 1/sqrt(mean(x^2)+eps)) * w, recomputed by every CTA from
 // the L2-resident residual stream. `red` = 33 floats of shared scratch. Optional fused residual add for the
 // tensor-parallel path: the vector normalised is x + add (add = all-reduced partial sums of the previous
@@ -60,8 +64,13 @@ __device__ __forceinline__ void stage_x_plain(float* xs, const float* __restrict
 template <int WD>
 __device__ __forceinline__ void stage_x_rmsnorm(float* xs, float* red, const float* __restrict__ x,
                                                 const float* __restrict__ w, int cols, float eps,
-                                                const float* __restrict__ add = nullptr, float* __restrict__ sum_out = nullptr) {
+                                                const float* __restrict__ add = nullptr, float* __restrict__ sum_out = nullptr,
+                                                const P2PComm* p2p = nullptr, int p2p_op = 0) {
     const int nchunks = cols / WInfo<WD>::E;
+    const uint2* slots[8];
+    int ntp = 0;
+    unsigned epoch = 0;
+    if (p2p) epoch = p2p_slots(p2p, p2p_op, slots, &ntp);   // peer-memory all-reduce: partial vectors of op p2p_op
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* a4 = reinterpret_cast<const float4*>(add);
     const float4* w4 = reinterpret_cast<const float4*>(w);
@@ -70,7 +79,15 @@ __device__ __forceinline__ void stage_x_rmsnorm(float* xs, float* red, const flo
     float ss = 0.0f;
     for (int j4 = threadIdx.x; j4 < cols / 4; j4 += blockDim.x) {
         float4 v = x4[j4];
-        if (add) {
+        if (p2p) {   // spin on the {value, epoch} words themselves; sum in rank order (identical on every rank)
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < ntp; ++r) {
+                const float2 lo = p2p_recv2(slots[r] + 4 * j4, epoch), hi = p2p_recv2(slots[r] + 4 * j4 + 2, epoch);
+                a = (r == 0) ? make_float4(lo.x, lo.y, hi.x, hi.y) : make_float4(a.x + lo.x, a.y + lo.y, a.z + hi.x, a.w + hi.y);
+            }
+            v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+            if (sum_out && blockIdx.x == 0) o4[j4] = v;
+        } else if (add) {
             const float4 a = a4[j4];
             v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
             if (sum_out && blockIdx.x == 0) o4[j4] = v;

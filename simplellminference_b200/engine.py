@@ -63,6 +63,24 @@ class Engine:
         _lib.check(self.lib.sllm_engine_init_comm(self.h, raw))
         return self
 
+    def init_p2p(self, dist=None) -> "Engine":
+        """Peer-memory all-reduce (engine created with p2p_allreduce=True): exchange the 64-byte CUDA IPC handles of the
+        ranks' receive areas; torch.distributed is only the messenger."""
+        import torch.distributed as td
+        dist = dist or td
+        buf = (C.c_uint8 * 64)()
+        _lib.check(self.lib.sllm_engine_p2p_export(self.h, buf))
+        mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        allh = [torch.zeros_like(mine) for _ in range(self.tp_size)]
+        dist.all_gather(allh, mine)
+        raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        dist.barrier()
+        _lib.check(self.lib.sllm_engine_p2p_import(self.h, raw))
+        dist.barrier()
+        return self
+
     # -- LlamaModel::forward: one token at one position; returns (logits np.float32[V_local], next_token) --
     def forward(self, token: int, pos: int, want_logits: bool = True):
         n_loc = self.shape.vocab // self.tp_size
