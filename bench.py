@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-mega", action="store_true", help="use the per-kernel fused CUDA-graph path instead of the persistent megakernel")
+    ap.add_argument("--mega-ll", action="store_true", help="single GPU: the barrier-free {value,epoch}-word megakernel instead of the grid-barrier one")
     ap.add_argument("--nccl", action="store_true", help="tensor parallel: NCCL all-reduce instead of the fused peer-memory one")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
     return ap.parse_args()
@@ -220,7 +221,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
-                 graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused),
+                 graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused), mega_ll=args.mega_ll,
                  p2p_allreduce=(world > 1 and not args.nccl))
     eng.load_synthetic(1234)
     if world > 1:
@@ -300,7 +301,7 @@ def run_ours(args):
     roof = None
     peak, peak_src = peaks()
     mode = eng.mode
-    if mode == "megakernel":
+    if mode.startswith("megakernel"):
         ach = step_bytes / (ms_total * 1e-3 / K) / 1e9
         roof = {"bound": "hbm", "kernel": "mega_step_kernel (persistent: all layers' qkv|attention|wo|gate_up|down + classifier/argmax)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": step_bytes,
@@ -359,6 +360,12 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything a library prints there while we run (NCCL's version banner, ...)
+    # is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:

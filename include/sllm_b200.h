@@ -151,6 +151,10 @@ typedef struct {
 #define SLLM_ENGINE_MEGAKERNEL 16u /* whole decode step as ONE persistent cooperative kernel whose TMA weight rings
                                     keep streaming across phases (single GPU; shapes it cannot take fall back to the
                                     per-kernel fused path — sllm_engine_mode() tells which one runs) */
+#define SLLM_ENGINE_MEGA_LL 32u   /* with MEGAKERNEL on one GPU: the barrier-free {value, epoch}-word version
+                                    (megakernel_ll.cu) instead of the grid-barrier one (megakernel.cu, faster on one GPU).
+                                    Under tensor parallelism (MEGAKERNEL | P2P_ALLREDUCE) the word version is the only
+                                    one: it carries the all-reduce inside the kernel */
 #define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
 
 typedef struct sllm_engine sllm_engine;

@@ -29,7 +29,7 @@ class EngineConfig(C.Structure):
                 ("tp_rank", C.c_int32), ("tp_size", C.c_int32), ("flags", C.c_int32)]
 
 
-ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE, ENGINE_MEGAKERNEL = 1, 2, 4, 8, 16
+ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE, ENGINE_MEGAKERNEL, ENGINE_MEGA_LL = 1, 2, 4, 8, 16, 32
 
 _P = C.c_void_p
 _I = C.c_int32

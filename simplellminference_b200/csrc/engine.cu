@@ -50,7 +50,12 @@ struct sllm_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     bool fused = true, use_graph = true, pdl = true;
-    bool mega = false;            // persistent one-launch-per-token kernel (megakernel.cu)
+    bool mega = false;            // persistent one-launch-per-token kernel (megakernel.cu / megakernel_ll.cu)
+    bool mega_ll = false;         // barrier-free {value, epoch}-word version (also the tensor-parallel one)
+    MegaLLPlan ll_plan{};
+    MegaLLParams ll_params{};
+    uint8_t* ll_block = nullptr;  // this rank's word area (own cudaMalloc: exported through CUDA IPC under TP)
+    bool ll_ready = false;
     MegaPlan mega_plan_{};
     MegaParams mega_params{};
     PhaseDesc* phases_dev = nullptr;
@@ -462,8 +467,11 @@ static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
         return SLLM_OK;
     }
     if (e->mega) {
+        SLLM_REQUIRE(!e->mega_ll || e->ll_ready, SLLM_ESTATE, "tensor-parallel megakernel: peer areas not exchanged yet (sllm_engine_p2p_import)");
         for (int i = 0; i < n; ++i) {
-            if (int rc = mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream)) return rc;
+            const int rc = e->mega_ll ? mega_ll_launch(e->ll_params, e->H_loc / e->KVH_loc, e->ll_plan.grid, e->ll_plan.smem, e->stream)
+                                      : mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream);
+            if (rc) return rc;
             e->total_launches++;
         }
         return SLLM_OK;
@@ -575,8 +583,25 @@ static int mega_stage_end(sllm_engine* e) {
 
 static int setup_mega(sllm_engine* e) {
     std::vector<PhaseDesc> host((size_t)4 * e->L + 1);
-    mega_fill_phases(host.data(), e->L, e->cfg.w_dtype, e->wqkv.w, e->wo.w, e->wug.w, e->wdown.w, e->emb.w, e->d, e->q_loc, e->kv_loc,
-                     e->I_loc, e->V_loc);   // single GPU: the classifier is the whole (tiled) embedding matrix
+    // the classifier streams this rank's vocab rows [v0, v0+V_loc) of the (tiled, full) embedding matrix
+    const TileGeom eg = mega_tile_geom(((e->V + 1) / 2) * 2, e->d, e->cfg.w_dtype);
+    const uint8_t* cls = reinterpret_cast<const uint8_t*>(e->emb.w) + (size_t)(e->v0 / eg.R) * eg.KS * eg.tile_bytes;
+    mega_fill_phases(host.data(), e->L, e->cfg.w_dtype, e->wqkv.w, e->wo.w, e->wug.w, e->wdown.w, cls, e->d, e->q_loc, e->kv_loc,
+                     e->I_loc, e->V_loc);
+    if (e->mega_ll) {
+        MegaLLParams& q = e->ll_params;
+        q.phases = e->phases_dev;
+        q.d = e->d; q.hd = e->hd; q.L = e->L; q.S = e->S; q.V = e->V; q.V_loc = e->V_loc; q.v0 = e->v0; q.q_loc = e->q_loc; q.kv_loc = e->kv_loc;
+        q.I_loc = e->I_loc; q.H_loc = e->H_loc; q.KVH_loc = e->KVH_loc; q.nsplit = e->ll_plan.nsplit;
+        q.w_dtype = e->cfg.w_dtype; q.kv_dtype = e->cfg.kv_dtype; q.eps = e->cfg.shape.eps;
+        q.emb = reinterpret_cast<const uint8_t*>(e->emb.w); q.norms = e->norms;
+        q.kc = reinterpret_cast<uint8_t*>(e->key_cache); q.vc = reinterpret_cast<uint8_t*>(e->value_cache);
+        q.sin_t = e->sin_t; q.cos_t = e->cos_t; q.logits = e->logits; q.x_out = e->x; q.blk_val = e->blk_val; q.blk_idx = e->blk_idx; q.st = e->state;
+        q.prompt = e->prompt_dev; q.history = e->history_dev; q.tp = e->tp; q.rank = e->rank;
+        q.area[e->rank] = reinterpret_cast<uint2*>(e->ll_block);
+        q.off_wop = e->ll_plan.off_wop; q.off_dnp = e->ll_plan.off_dnp; q.off_qv = e->ll_plan.off_qv; q.off_kvn = e->ll_plan.off_kvn;
+        q.off_att = e->ll_plan.off_att; q.off_swi = e->ll_plan.off_swi; q.off_arg = e->ll_plan.off_arg;
+    }
     SLLM_CUDA(cudaMemcpyAsync(e->phases_dev, host.data(), sizeof(PhaseDesc) * host.size(), cudaMemcpyHostToDevice, e->stream));
     SLLM_CUDA(cudaStreamSynchronize(e->stream));
     MegaParams& p = e->mega_params;
@@ -653,9 +678,16 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     if (e->hd % 16 || e->hd > 256) { set_error("head_dim=%d must be a multiple of 16, <= 256", e->hd); return fail(SLLM_ENOTSUP); }
     if (gemv_smem_bytes(std::max(e->d, e->I_loc)) > (size_t)smem_optin_bytes()) { set_error("activation vector does not fit shared memory"); return fail(SLLM_ENOTSUP); }
 
-    if ((cfg->flags & SLLM_ENGINE_MEGAKERNEL) && e->fused && tp == 1) {
-        e->mega_plan_ = mega_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->H_loc, e->KVH_loc, e->S);
-        e->mega = e->mega_plan_.ok;
+    if ((cfg->flags & SLLM_ENGINE_MEGAKERNEL) && e->fused) {
+        if (tp == 1 ? (cfg->flags & SLLM_ENGINE_MEGA_LL) != 0 : (cfg->flags & SLLM_ENGINE_P2P_ALLREDUCE) != 0) {
+            e->ll_plan = mega_ll_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->v0, e->H_loc, e->KVH_loc, e->S, tp);
+            e->mega_ll = e->mega = e->ll_plan.ok;
+        }
+        if (!e->mega && tp == 1) {
+            e->mega_plan_ = mega_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->H_loc, e->KVH_loc, e->S);
+            e->mega = e->mega_plan_.ok;
+        }
+        if (e->mega) e->p2p_mode = false;   // the megakernel carries its own in-kernel all-reduce
     }
     layout(e);  // measure
     e->arena_bytes = align_up(e->arena_used, 1 << 20);
@@ -664,6 +696,13 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     if (e->arena_bytes > free_b) { set_error("engine needs %zu MiB of HBM, %zu MiB free", e->arena_bytes >> 20, free_b >> 20); return fail(SLLM_ENOMEM); }
     if (cudaMalloc(&e->arena, e->arena_bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu MiB) failed", e->arena_bytes >> 20); return fail(SLLM_ENOMEM); }
     layout(e);  // assign
+    if (e->mega_ll) {
+        const size_t bytes = (size_t)e->ll_plan.area_words * sizeof(uint2);
+        if (cudaMalloc(&e->ll_block, bytes) != cudaSuccess || cudaMemset(e->ll_block, 0, bytes) != cudaSuccess) {
+            cudaGetLastError(); set_error("megakernel word area: allocation failed"); sllm_engine_destroy(e); return SLLM_ENOMEM;
+        }
+        e->ll_ready = (tp == 1);
+    }
     if (e->p2p_mode) {
         if (tp > kMaxTp) { set_error("peer-memory all-reduce supports up to %d ranks", kMaxTp); sllm_engine_destroy(e); return SLLM_ENOTSUP; }
         e->p2p_recv_bytes = align_up((size_t)2 * tp * e->d * sizeof(uint2), 256);   // {value, epoch} words
@@ -689,6 +728,7 @@ void sllm_engine_destroy(sllm_engine* e) {
     for (int r = 0; r < kMaxTp; ++r) if (e->p2p_peer[r]) cudaIpcCloseMemHandle(e->p2p_peer[r]);
     if (e->p2p_dev) cudaFree(e->p2p_dev);
     if (e->p2p_block) cudaFree(e->p2p_block);
+    if (e->ll_block) cudaFree(e->ll_block);
     if (e->arena) cudaFree(e->arena);
     if (e->trace) cudaFree(e->trace);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -755,9 +795,14 @@ int sllm_engine_init_comm(sllm_engine* e, const void* id_bytes_128) {
 
 int sllm_engine_p2p_export(sllm_engine* e, void* handle_bytes_64) {
     SLLM_REQUIRE(e && handle_bytes_64, SLLM_EINVAL, "null argument");
-    SLLM_REQUIRE(e->p2p_mode && e->p2p_block, SLLM_ESTATE, "engine was not created with SLLM_ENGINE_P2P_ALLREDUCE (tp_size > 1)");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
     cudaIpcMemHandle_t h;
+    if (e->mega_ll && e->tp > 1) {
+        SLLM_CUDA(cudaIpcGetMemHandle(&h, e->ll_block));
+        std::memcpy(handle_bytes_64, &h, 64);
+        return SLLM_OK;
+    }
+    SLLM_REQUIRE(e->p2p_mode && e->p2p_block, SLLM_ESTATE, "engine was not created with SLLM_ENGINE_P2P_ALLREDUCE (tp_size > 1)");
     SLLM_CUDA(cudaIpcGetMemHandle(&h, e->p2p_block));
     std::memcpy(handle_bytes_64, &h, 64);
     return SLLM_OK;
@@ -765,6 +810,20 @@ int sllm_engine_p2p_export(sllm_engine* e, void* handle_bytes_64) {
 
 int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles) {
     SLLM_REQUIRE(e && all_handles, SLLM_EINVAL, "null argument");
+    if (e->mega_ll && e->tp > 1) {
+        for (int r = 0; r < e->tp; ++r) {
+            if (r == e->rank) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, reinterpret_cast<const uint8_t*>(all_handles) + (size_t)r * 64, 64);
+            void* pp = nullptr;
+            SLLM_CUDA(cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess));
+            e->p2p_peer[r] = pp;
+            e->ll_params.area[r] = reinterpret_cast<uint2*>(pp);
+        }
+        e->ll_ready = true;
+        e->p2p_ready = true;
+        return SLLM_OK;
+    }
     SLLM_REQUIRE(e->p2p_mode && e->p2p_block, SLLM_ESTATE, "engine was not created with SLLM_ENGINE_P2P_ALLREDUCE (tp_size > 1)");
     P2PComm c{};
     c.tp = e->tp; c.rank = e->rank; c.n = e->d; c.ops_per_step = 2 * e->L + 1; c.step = &e->state->pad[1];
@@ -925,7 +984,7 @@ int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos
 
 const char* sllm_engine_mode(const sllm_engine* e) {
     if (!e) return "null";
-    if (e->mega) return "megakernel";
+    if (e->mega) return e->mega_ll ? "megakernel(ll)" : "megakernel";
     if (!e->fused) return "unfused";
     return e->use_graph ? (e->pdl ? "fused+graph+pdl" : "fused+graph") : (e->pdl ? "fused+pdl" : "fused");
 }

@@ -27,163 +27,9 @@
 #include <algorithm>
 #include <cmath>
 
-#include "megakernel.cuh"
+#include "mega_common.cuh"
 
 namespace sllm {
-
-constexpr int kMegaThreads = 512;
-constexpr int kMegaWarps = kMegaThreads / 32;
-constexpr int kSlotBytes = 4096;
-constexpr int kSlots = 2;
-constexpr int kCplMax = 4;        // max 16-byte chunks per lane per row slice (slice <= 2 KB)
-constexpr int kRoundUnits = 128;  // units per partial-table round
-constexpr int kAttTile = 64;
-constexpr unsigned kSpinLimit = 1u << 26;
-#ifndef SLLM_L2_AHEAD
-#define SLLM_L2_AHEAD 0
-#endif
-constexpr int kL2AheadBytes = SLLM_L2_AHEAD;  // per CTA: how much of the next phase is pulled into L2 during a phase gap
-constexpr int kAttRecPad = 4;     // partial record = hd floats of O, then m, l (+2 pad: keeps float4 alignment)
-
-
-struct MegaSmem {
-    size_t bars, red, part, ring, att, total;
-    size_t att_q, att_p, att_misc, att_k, att_v;
-    int kv_stride;
-};
-__host__ __device__ inline int mega_kv_stride(int row_bytes) {
-    int s = (row_bytes / 128) * 128 + 32;
-    if (s < row_bytes) s += 128;
-    return s;
-}
-__host__ __device__ inline MegaSmem mega_smem_layout(int hd, int g, int kv_esz) {
-    MegaSmem L;
-    size_t off = 0;
-    L.bars = off; off += 512;
-    L.red = off; off += 256;
-    L.part = off; off += (size_t)kRoundUnits * 2 * kMegaWarps * 4;
-    off = (off + 127) & ~(size_t)127;
-    L.ring = off; off += (size_t)kMegaWarps * kSlots * kSlotBytes;
-    L.att = off;
-    L.att_q = off; off += (size_t)g * hd * 4;
-    L.att_p = off; off += (size_t)g * kAttTile * 4;
-    L.att_misc = off; off += 256;
-    off = (off + 127) & ~(size_t)127;
-    L.kv_stride = hd * kv_esz;   // dense rows: a tile is one contiguous bulk copy
-    L.att_k = off; off += (size_t)2 * kAttTile * L.kv_stride;
-    L.att_v = off; off += (size_t)2 * kAttTile * L.kv_stride;
-    L.total = off;
-    return L;
-}
-
-// ------------------------------------------------------------------------------------- primitives ----
-__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mb_expect(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    unsigned spins = 0;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > kSpinLimit) __trap();
-    } while (!done);
-}
-__device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
-}
-// HBM -> L2 only (no shared memory needed): extends the effective prefetch depth far beyond the smem rings
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// grid-wide barrier (cooperative launch guarantees co-residency). counter[0] = arrivals (monotonic), counter[32] =
-// released epoch on its own 128-byte line: the last arriver publishes the epoch, everybody else polls that line
-// only, so the polling never collides with the arriving atomics. Wrap-safe compares. No trailing fence: every
-// cross-CTA read in this kernel is an L2 access (ld.global.cg or TMA), never an L1-cached load.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(counter, 1u);
-        if (prev + 1u == target) {
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 32), "r"(target) : "memory");
-        } else {
-            unsigned spins = 0;
-            while (true) {
-                unsigned v;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter + 32) : "memory");
-                if ((int)(v - target) >= 0) break;
-                if (++spins > kSpinLimit) __trap();
-            }
-        }
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void unit_rows(const MegaParams& p, const PhaseDesc& ph, int u, int& r0, int& r1) {
-    if (ph.kind == PH_QKV) {
-        const int half = p.hd >> 1, rope_units = (p.q_loc + p.kv_loc) >> 1;
-        if (u < rope_units) {
-            const int head = u / half, j = u - head * half;
-            r0 = head * p.hd + j;
-            r1 = r0 + half;
-        } else {
-            r0 = p.q_loc + p.kv_loc + 2 * (u - rope_units);
-            r1 = r0 + 1;
-        }
-    } else if (ph.kind == PH_GATEUP) {
-        r0 = u;
-        r1 = p.I_loc + u;
-    } else {
-        r0 = 2 * u;
-        r1 = min(2 * u + 1, ph.nrows - 1);
-    }
-}
-
-// balanced split of a phase's tile rows over the CTAs
-__device__ __forceinline__ void cta_tiles(const PhaseDesc& ph, int cta, int ncta, int& g0, int& g1) {
-    g0 = (int)(((int64_t)ph.ntr * cta) / ncta);
-    g1 = (int)(((int64_t)ph.ntr * (cta + 1)) / ncta);
-}
-
-template <int KVD> struct MKv;
-template <> struct MKv<SLLM_F32> { static constexpr int ESZ = 4, VEC = 4; };
-template <> struct MKv<SLLM_BF16> { static constexpr int ESZ = 2, VEC = 8; };
-
-template <int KVD>
-__device__ __forceinline__ void kv_unpack(const uint4 v, float* f) {
-    if (KVD == SLLM_F32) {
-        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
-    } else {
-        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-    }
-}
-
-// 16 bytes of weights (E elements) times E activations held in registers
-template <int WD>
-__device__ __forceinline__ float reg_dot(const uint4 w, const float* x, float acc) {
-    if (WD == SLLM_F32) {
-        acc = fmaf(__uint_as_float(w.x), x[0], acc); acc = fmaf(__uint_as_float(w.y), x[1], acc);
-        acc = fmaf(__uint_as_float(w.z), x[2], acc); acc = fmaf(__uint_as_float(w.w), x[3], acc);
-    } else {
-        acc = fmaf(bf16_lo(w.x), x[0], acc); acc = fmaf(bf16_hi(w.x), x[1], acc);
-        acc = fmaf(bf16_lo(w.y), x[2], acc); acc = fmaf(bf16_hi(w.y), x[3], acc);
-        acc = fmaf(bf16_lo(w.z), x[4], acc); acc = fmaf(bf16_hi(w.z), x[5], acc);
-        acc = fmaf(bf16_lo(w.w), x[6], acc); acc = fmaf(bf16_hi(w.w), x[7], acc);
-    }
-    return acc;
-}
 
 // ----------------------------------------------------------------------------------------- kernel ----
 // Optional per-CTA timeline (tools/mega_trace.py): stamp s of phase slot `ev` -> trace[(cta*kTraceEvents + ev)*8 + s]
@@ -197,23 +43,6 @@ __device__ __forceinline__ unsigned long long gtime() {
     do {                                                                                                  \
         if (p.trace && threadIdx.x == 0 && (ev) < kTraceEvents) p.trace[((size_t)blockIdx.x * kTraceEvents + (ev)) * 8 + (slot)] = gtime(); \
     } while (0)
-
-__device__ __noinline__ void mega_timeout(const char* what) {
-    printf("sllm mega: %s timed out (cta %d warp %d)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5));
-    __trap();
-}
-__device__ __forceinline__ void mb_wait_fast(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    unsigned spins = 0;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > kSpinLimit) mega_timeout("mbarrier");
-    } while (!done);
-}
 
 // producer state of one warp (meaningful in lane 0): constants of the phase it is currently feeding
 struct ProdState {

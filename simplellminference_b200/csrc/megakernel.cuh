@@ -50,6 +50,39 @@ struct MegaParams {
     unsigned long long* trace;  // optional [grid][512][8] %globaltimer stamps (nullptr = off)
 };
 
+// ---- barrier-free {value, epoch}-word version (megakernel_ll.cu), single GPU and tensor parallel -------------
+struct MegaLLParams {
+    const PhaseDesc* phases;   // [4L+1]
+    int32_t d, hd, L, S, V, V_loc, v0, q_loc, kv_loc, I_loc, H_loc, KVH_loc, nsplit;
+    int32_t w_dtype, kv_dtype;
+    float eps;
+    const uint8_t* emb;        // full tiled [V][d] (gather); the classifier phase points at this rank's vocab rows
+    const float* norms;
+    uint8_t *kc, *vc;          // head-major cache [L][KVH_loc][S][hd]
+    const float *sin_t, *cos_t;
+    float* logits;
+    float* x_out;              // introspection only: CTA 0 stores the final residual stream here (emb_output)
+    float* blk_val;
+    int32_t* blk_idx;
+    StepState* st;
+    const int32_t* prompt;
+    int32_t* history;
+    int32_t tp, rank;
+    uint2* area[8];            // area[r] = rank r's word area (area[rank] is local memory, the others CUDA-IPC mappings)
+    int64_t off_wop, off_dnp, off_qv, off_kvn, off_att, off_swi, off_arg;   // word offsets inside an area
+};
+struct MegaLLPlan {
+    bool ok = false;
+    int grid = 0;
+    size_t smem = 0;
+    int nsplit = 1;
+    int64_t off_wop = 0, off_dnp = 0, off_qv = 0, off_kvn = 0, off_att = 0, off_swi = 0, off_arg = 0, area_words = 0;
+    const char* why = "";
+};
+MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0, int H_loc, int KVH_loc,
+                        int max_len, int tp);
+int mega_ll_launch(const MegaLLParams& p, int g, int grid, size_t smem, cudaStream_t st);
+
 struct MegaPlan {
     bool ok = false;
     int grid = 0;

@@ -35,15 +35,16 @@ def logit_tol(want):
 
 
 @pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
-@pytest.mark.parametrize("mode", ["mega", "fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
+@pytest.mark.parametrize("mode", ["mega", "mega_ll", "fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
 def test_golden_models(golden_models, name, mode):
     """Token streams and final logits recorded from the reference itself (tests/golden/models_ref.npz)."""
     prompt, n_total, wd = mg.MODEL_RUNS[name]
     ms = PRESETS[PRESET_OF[name]]
-    kw = dict(mega=dict(mega=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
+    kw = dict(mega=dict(mega=True), mega_ll=dict(mega=True, mega_ll=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
-    if mode == "mega":
-        assert eng.mode == ("megakernel" if wd != INT8 else "fused+graph"), eng.mode   # int8 falls back, loudly visible
+    if mode.startswith("mega"):
+        want_mode = "fused+graph" if wd == INT8 else ("megakernel" if mode == "mega" else "megakernel(ll)")
+        assert eng.mode == want_mode, eng.mode   # int8 falls back, loudly visible
     toks = eng.greedy(prompt, n_total)
     want = golden_models[name + "/tokens"]
     assert np.array_equal(toks, want), (np.flatnonzero(toks != want)[:5], toks[:8], want[:8])

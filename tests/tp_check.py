@@ -30,16 +30,21 @@ def main():
              ("medium bf16 weights, bf16 kv (teacher forced)", medium, BF16, BF16, list(range(1, 17)), 120, True),
              ("mha8 bf16 weights, f32 kv", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, F32, list(range(1, 9)), 80, False)]
     import itertools
-    for (name, ms, wd, kvd, prompt, n_total, forced), p2p in itertools.product(cases, (False, True)):
+    for (name, ms, wd, kvd, prompt, n_total, forced), comm in itertools.product(cases, ("nccl", "p2p", "mega")):
+        p2p = comm != "nccl"
         if ms.kv_heads % world or ms.heads % world or ms.inter % world or ms.vocab % world:
             continue
-        name += " [peer-memory all-reduce]" if p2p else " [NCCL]"
+        name += {"nccl": " [NCCL]", "p2p": " [peer-memory all-reduce]", "mega": " [megakernel, in-kernel all-reduce]"}[comm]
         shape = loader.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, ms.layers, ms.heads, ms.kv_heads, ms.eps, ms.theta)
         blob = port.fill_blob(shape, 1234, wd, 64)
         want, want_l = port.model(shape, blob, threads=4, kv_bf16=(kvd == BF16)).greedy(prompt, n_total)
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
-        eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=p2p).load_synthetic(1234)
+        eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=p2p, mega=(comm == "mega")).load_synthetic(1234)
+        if comm == "mega":   # fp32 K/V tiles of 128-wide heads do not fit next to the weight rings: that case falls back, visibly
+            fits = not (kvd == F32 and ms.head_dim > 64)
+            assert eng.mode == ("megakernel(ll)" if fits else "fused+graph"), eng.mode
+            name += f" -> {eng.mode}"
         eng = eng.init_p2p(dist) if p2p else eng.init_comm(dist)
         if forced:
             got = eng.greedy([prompt[0]] + [int(t) for t in want[:-1]], n_total)   # every input token = the oracle's

@@ -14,6 +14,7 @@ ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--wdtype", default="bf16")
 ap.add_argument("--pdl", action="store_true")
 ap.add_argument("--mega", action="store_true")
+ap.add_argument("--ll", action="store_true")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 wd = dict(f32=F32, bf16=BF16, int8=INT8)[a.wdtype]
@@ -21,7 +22,7 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 lib = _lib.load()
 for ctas in [int(c) for c in a.ctas.split(",")]:
     lib.sllm_tune(0, ctas)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=a.pdl, mega=a.mega).load_synthetic(1)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, stream=stream, pdl=a.pdl, mega=a.mega, mega_ll=a.ll).load_synthetic(1)
     eng.set_state(1, a.pos)
     res = {"ctas_per_sm": ctas, "lib": os.path.basename(_lib.LIB_PATH), "mode": eng.mode}
     for kind in ([] if a.mega else ("qkv", "mha", "wo", "gate_up", "down")):
