@@ -196,9 +196,28 @@ int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos);
 int sllm_engine_enqueue_steps(sllm_engine* e, int32_t n_steps);
 int sllm_engine_read_tokens(sllm_engine* e, int32_t* tokens_out_host, int32_t n);
 
-/* Batched prefill of prompt[0..n) at positions start_pos.. : fills the KV cache, leaves the last token's
- * logits in model_pred and its argmax as the current token (tcgen05/TMEM GEMMs; bf16 operands). */
+/* Batched prefill of prompt[0..n) at positions start_pos..: the layer loop of LlamaModel::forward
+ * (source/model/model.cpp:50-128) for all prompt rows at once — dense contractions as tcgen05/TMEM tensor-core
+ * GEMMs fed by TMA (bf16 operands, fp32 accumulators), causal attention over the block — instead of the
+ * reference's one forward() per prompt token (model.cpp:157-166). Fills the KV cache for start_pos..start_pos+n-1,
+ * leaves the LAST prompt token's logits in model_pred, its arg-max as the current token and the position at
+ * start_pos+n, exactly as the token-by-token loop would (the last token runs as one ordinary decode step).
+ * Needs SLLM_ENGINE_MEGAKERNEL, bf16 weights and head_dim 64/128: otherwise SLLM_ENOTSUP (feed the prompt through
+ * sllm_engine_greedy / sllm_engine_forward, which is what the reference does); sllm_engine_prefill_supported
+ * returns 1/0 (0: reason in sllm_last_error). Tensor parallel: also needs sllm_engine_init_comm (NCCL all-reduce of
+ * the row-parallel partial sums, one per wo/down GEMM). */
 int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt_host, int32_t n, int32_t start_pos);
+int sllm_engine_prefill_supported(const sllm_engine* e);
+
+/* The two prefill kernels on their own (device pointers), for op-level parity tests:
+ * C[T][N] (fp32) = A[T][K] (bf16) . W[N][K]^T (bf16, row-major) on tcgen05; bn = 0 (auto), 128 or 256 = N tile. */
+int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, int32_t T, int32_t N, int32_t K, int32_t bn,
+                           sllm_stream_t stream);
+/* causal attention of T queries (bf16 [T][heads*head_dim]) at positions pos0.. over a HEAD-MAJOR cache
+ * [kv_heads][max_len][head_dim] (kv_dtype f32 or bf16), rows 0..pos0+T-1 valid; out bf16 like q. */
+int sllm_prefill_attention(const void* q, const void* key_cache, const void* value_cache, int32_t kv_dtype, void* out,
+                           int32_t T, int32_t pos0, int32_t max_len, int32_t head_dim, int32_t heads, int32_t kv_heads,
+                           sllm_stream_t stream);
 
 /* Introspection for parity tests and the roofline: named buffers follow the reference's ModelBufferType
  * numbering (include/model/model.h:14-34); returns a device pointer and its element count/dtype. */

@@ -69,6 +69,9 @@ SIGNATURES = {
     "sllm_engine_enqueue_steps": (C.c_int, [_P, _I]),
     "sllm_engine_read_tokens": (C.c_int, [_P, _P, _I]),
     "sllm_engine_prefill": (C.c_int, [_P, _P, _I, _I]),
+    "sllm_engine_prefill_supported": (C.c_int, [_P]),
+    "sllm_prefill_gemm_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "sllm_prefill_attention": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "sllm_engine_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_engine_step_bytes": (_L, [_P, _I]),
     "sllm_engine_enqueue_kernel": (C.c_int, [_P, _I, _I]),

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "megakernel.cuh"
+#include "prefill.cuh"
 
 namespace sllm {
 int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_dtype, float* out, void* ws, int layer,
@@ -103,6 +104,14 @@ struct sllm_engine {
     size_t p2p_recv_bytes = 0;
     void* p2p_peer[kMaxTp] = {};      // mapped peer blocks
     P2PComm* p2p_dev = nullptr;       // descriptor in device memory
+    // batched prefill (prefill.cuh): tensor-map cache + a workspace allocated on first use, sized for pf_rows prompt rows
+    PfCache* pf = nullptr;
+    uint8_t* pf_ws = nullptr;
+    int pf_rows = 0;
+    float *pf_x = nullptr, *pf_part = nullptr;
+    uint16_t *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_s = nullptr;
+    int32_t* pf_ids = nullptr;
+    int64_t pf_gemm_launches = 0;
 };
 
 // ------------------------------------------------------------------------------------------- helpers ---
@@ -729,6 +738,8 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->p2p_dev) cudaFree(e->p2p_dev);
     if (e->p2p_block) cudaFree(e->p2p_block);
     if (e->ll_block) cudaFree(e->ll_block);
+    if (e->pf_ws) cudaFree(e->pf_ws);
+    if (e->pf) pf_cache_destroy(e->pf);
     if (e->arena) cudaFree(e->arena);
     if (e->trace) cudaFree(e->trace);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -899,7 +910,108 @@ int sllm_engine_greedy(sllm_engine* e, const int32_t* prompt, int32_t n_prompt, 
     return sllm_engine_read_tokens(e, tokens_out, n_total - 1);
 }
 
-int sllm_engine_prefill(sllm_engine*, const int32_t*, int32_t, int32_t) { set_error("batched prefill: not built yet"); return SLLM_ENOTSUP; }
+// ---- batched prefill ------------------------------------------------------------------------------------------
+static const char* prefill_unsupported(const sllm_engine* e) {
+    if (!e->mega) return "batched prefill reads the megakernel's tiled weights and head-major KV cache (create the engine with SLLM_ENGINE_MEGAKERNEL)";
+    return pf_unsupported_reason(e->cfg.w_dtype, e->hd, e->d, e->q_loc, e->I_loc);
+}
+
+static int prefill_workspace(sllm_engine* e, int rows) {
+    if (rows <= e->pf_rows) return SLLM_OK;
+    if (e->pf_ws) { SLLM_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(e->pf_ws); e->pf_ws = nullptr; e->pf_rows = 0; }
+    if (!e->pf) e->pf = pf_cache_create();
+    const size_t T = (size_t)rows;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    const size_t o_x = take(4 * T * e->d), o_part = take(4 * T * e->d), o_xn = take(2 * T * e->d), o_q = take(2 * T * e->q_loc),
+                 o_att = take(2 * T * e->q_loc), o_s = take(2 * T * e->I_loc), o_ids = take(4 * T);
+    if (cudaMalloc(&e->pf_ws, off) != cudaSuccess) { cudaGetLastError(); set_error("prefill workspace: cudaMalloc(%zu MiB) failed", off >> 20); return SLLM_ENOMEM; }
+    e->pf_x = reinterpret_cast<float*>(e->pf_ws + o_x); e->pf_part = reinterpret_cast<float*>(e->pf_ws + o_part);
+    e->pf_xn = reinterpret_cast<uint16_t*>(e->pf_ws + o_xn); e->pf_q = reinterpret_cast<uint16_t*>(e->pf_ws + o_q);
+    e->pf_att = reinterpret_cast<uint16_t*>(e->pf_ws + o_att); e->pf_s = reinterpret_cast<uint16_t*>(e->pf_ws + o_s);
+    e->pf_ids = reinterpret_cast<int32_t*>(e->pf_ws + o_ids);
+    e->pf_rows = rows;
+    return SLLM_OK;
+}
+
+// One block of T prompt rows at positions pos0.. through all layers; the last layer stops after its K/V rows are in the
+// cache (its attention/FFN output would only feed logits nobody reads, model.cpp:159-165).
+static int prefill_block(sllm_engine* e, int T, int pos0) {
+    const sllm_shape& s = e->cfg.shape;
+    const int d = e->d, L = e->L;
+    const bool tp = e->tp > 1;
+    cudaStream_t st = e->stream;
+    const int64_t before = g_launches;
+    auto tiled_layer = [&](const Matrix& m, int l) {
+        return reinterpret_cast<const uint8_t*>(m.w) + (size_t)l * mega_matrix_bytes((int)m.rows, (int)m.cols, m.kind, e->cfg.w_dtype);
+    };
+    const size_t kv_layer_bytes = (size_t)e->esz_kv * e->S * e->kv_loc;
+#define PF(call) do { if (int rc = (call)) return rc; } while (0)
+    PF(pf_embed(e->pf_ids, e->emb.w, e->V, d, e->pf_x, T, st));
+    for (int l = 0; l < L; ++l) {
+        uint8_t* kc = reinterpret_cast<uint8_t*>(e->key_cache) + (size_t)l * kv_layer_bytes;
+        uint8_t* vc = reinterpret_cast<uint8_t*>(e->value_cache) + (size_t)l * kv_layer_bytes;
+        // attention norm (+ under TP the all-reduced down partial of the previous layer)
+        PF(pf_rmsnorm(e->pf_x, (tp && l > 0) ? e->pf_part : nullptr, e->norms + (size_t)(2 * l) * d, e->pf_xn, T, d, s.eps, st));
+        PfGemmArgs a{};
+        a.A = e->pf_xn; a.W = tiled_layer(e->wqkv, l); a.T = T; a.N = e->q_loc + 2 * e->kv_loc; a.K = d; a.tiled = 1; a.epilogue = PF_EPI_QKV;
+        a.q_out = e->pf_q; a.k_cache = kc; a.v_cache = vc; a.kv_dtype = e->cfg.kv_dtype; a.q_loc = e->q_loc; a.kv_loc = e->kv_loc; a.hd = e->hd;
+        a.S = e->S; a.pos0 = pos0; a.sin_t = e->sin_t; a.cos_t = e->cos_t;
+        PF(pf_gemm(e->pf, a, st));
+        if (l == L - 1) break;
+        PF(pf_attention(e->pf_q, kc, vc, e->cfg.kv_dtype, e->pf_att, T, pos0, e->S, e->hd, e->H_loc, e->KVH_loc, st));
+        PfGemmArgs c{};
+        c.A = e->pf_att; c.W = tiled_layer(e->wo, l); c.T = T; c.N = ((d + 1) / 2) * 2; c.K = e->q_loc; c.tiled = 1;
+        c.epilogue = tp ? PF_EPI_STORE : PF_EPI_RESID; c.out = tp ? e->pf_part : e->pf_x; c.ld_out = d; c.n_valid = d;
+        PF(pf_gemm(e->pf, c, st));
+        if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+        PF(pf_rmsnorm(e->pf_x, tp ? e->pf_part : nullptr, e->norms + (size_t)(2 * l + 1) * d, e->pf_xn, T, d, s.eps, st));
+        PfGemmArgs g{};
+        g.A = e->pf_xn; g.W = tiled_layer(e->wug, l); g.T = T; g.N = 2 * e->I_loc; g.K = d; g.tiled = 1; g.epilogue = PF_EPI_GATEUP;
+        g.s_out = e->pf_s; g.I_loc = e->I_loc;
+        PF(pf_gemm(e->pf, g, st));
+        PfGemmArgs dn = c;
+        dn.A = e->pf_s; dn.W = tiled_layer(e->wdown, l); dn.K = e->I_loc;
+        PF(pf_gemm(e->pf, dn, st));
+        if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+    }
+#undef PF
+    e->total_launches += g_launches - before;
+    return SLLM_OK;
+}
+
+int sllm_engine_prefill_supported(const sllm_engine* e) {
+    if (!e) return 0;
+    const char* why = prefill_unsupported(e);
+    if (why) { set_error("%s", why); return 0; }
+    return 1;
+}
+
+int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt, int32_t n, int32_t start_pos) {
+    SLLM_REQUIRE(e && prompt && n >= 1, SLLM_EINVAL, "bad argument");
+    SLLM_REQUIRE(e->weights_loaded, SLLM_ESTATE, "weights not loaded");
+    SLLM_REQUIRE(start_pos >= 0 && start_pos + n <= e->S, SLLM_EINVAL, "prompt of %d tokens at position %d overruns max_len %d", n, start_pos, e->S);
+    for (int i = 0; i < n; ++i) SLLM_REQUIRE(prompt[i] >= 0 && prompt[i] < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", prompt[i], e->V);
+    if (const char* why = prefill_unsupported(e)) { set_error("%s", why); return SLLM_ENOTSUP; }
+    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel prefill needs the NCCL communicator (sllm_engine_init_comm)");
+    SLLM_REQUIRE(e->tp == 1 || e->ll_ready, SLLM_ESTATE, "tensor-parallel engine: peer areas not exchanged yet");
+    // rows 0..n-2 in blocks through the tensor-core path (KV cache only); the LAST prompt token runs as one ordinary
+    // decode step, which leaves logits, arg-max and the step state exactly as the token-by-token loop would
+    const int nb = n - 1;
+    constexpr int kBlock = 1024;
+    if (nb > 0) {
+        if (int rc = prefill_workspace(e, std::min(nb, kBlock))) return rc;
+        for (int b0 = 0; b0 < nb; b0 += kBlock) {
+            const int T = std::min(kBlock, nb - b0);
+            SLLM_CUDA(cudaMemcpyAsync(e->pf_ids, prompt + b0, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, e->stream));
+            if (int rc = prefill_block(e, T, start_pos + b0)) return rc;
+        }
+        SLLM_CUDA(cudaMemcpyAsync(e->history_dev + start_pos, prompt + 1, sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (int rc = set_state(e, prompt[n - 1], start_pos + n - 1, 0)) return rc;
+    e->h_state[7] = start_pos + n - 1;
+    return sllm_engine_enqueue_steps(e, 1);
+}
 
 int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32_t* dtype) {
     SLLM_REQUIRE(e && ptr && n && dtype, SLLM_EINVAL, "null argument");

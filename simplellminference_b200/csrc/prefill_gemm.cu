@@ -1,0 +1,472 @@
+// csrc/prefill_gemm.cu — the prefill GEMM on the 5th-generation tensor cores (sm_100a only).
+//
+//   C[T][N] = A[T][K] . W[N][K]^T      A = bf16 activations, W = bf16 weights, C = fp32 accumulators in TMEM
+//
+// One persistent CTA per SM, 192 threads, three roles (no role ever blocks another with __syncthreads):
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor of a 128 x 64 A box and a BN x 64 W box per k-block into a
+//                      ring of 128B-swizzled stages, completion counted on the stage's "full" mbarrier;
+//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per stage, both operands
+//                      through shared-memory descriptors; tcgen05.commit frees the stage / publishes the accumulator;
+//   warps 2-5          epilogue: tcgen05.ld 32 columns at a time (one accumulator row per thread), fused epilogue
+//                      (RoPE + KV-cache write, sigmoid(gate)*up, residual add), while the issuer already fills the
+//                      second accumulator (TMEM holds two: 2 x BN columns).
+// W is read straight from the megakernel's TILED decode layout (megakernel.cuh) through a 4-D tensor map
+// {k inside a K slice, row inside a tile, K slice, tile row}: prefill and decode share one copy of the weights.
+// Rows of the tiled layout are in unit order, so the two values an epilogue needs together (RoPE partners,
+// (up, gate)) sit in ADJACENT accumulator columns of the same thread.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "mega_common.cuh"
+#include "prefill.cuh"
+
+namespace sllm {
+
+constexpr int kPfBM = 128, kPfBK = 64, kPfThreads = 192;
+constexpr uint32_t kPfABytes = kPfBM * kPfBK * 2;
+template <int BN> struct PfCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t kBBytes = BN * kPfBK * 2;
+    static constexpr uint32_t kStageBytes = kPfABytes + kBBytes;
+    static constexpr uint32_t kTmemCols = 2 * BN;
+    static constexpr size_t kSmem = 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers + tmem slot*/;
+};
+
+struct PfDev {           // kernel-side view of PfGemmArgs
+    int32_t T, N, m_tiles, n_tiles;
+    int32_t nkb, kb_per_seg, seg_elems, R, tiled;
+    int32_t epilogue;
+    float* out; int32_t ld_out, n_valid;
+    uint16_t* q_out; uint8_t *kc, *vc; int32_t kv_dtype, q_loc, kv_loc, hd, S, pos0;
+    const float *sin_t, *cos_t;
+    uint16_t* s_out; int32_t I_loc;
+};
+
+// ------------------------------------------------------------------------------------------ PTX -------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_addr(dst)), "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(s_addr(dst)), "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory"); }
+
+__device__ __forceinline__ void tc_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// all tcgen05.mma issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand tile, rows of 64 bf16 = 128 bytes, 128B swizzle (what TMA wrote),
+// 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version 1<<46 | layout 2<<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* tile) {
+    uint64_t d = (uint64_t)((s_addr(tile) & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::f16: D = fp32 (1<<4), A = B = bf16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return (uint32_t)f32_to_bf16_bits(lo) | ((uint32_t)f32_to_bf16_bits(hi) << 16); }
+
+// ------------------------------------------------------------------------------- fused epilogues ------
+// v[0..31] = accumulator columns n0 .. n0+31 of token row t (n0 is a multiple of 32)
+__device__ __forceinline__ void epi_store(const PfDev& p, int t, int n0, const uint32_t* v, bool add) {
+    float* dst = p.out + (size_t)t * p.ld_out + n0;
+    if (n0 + 32 <= p.n_valid && (p.ld_out & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            if (add) {
+                const float4 r = *reinterpret_cast<const float4*>(dst + i);
+                o = make_float4(r.x + o.x, r.y + o.y, r.z + o.z, r.w + o.w);   // residual + projection (add_kernel.cpp:10-13)
+            }
+            *reinterpret_cast<float4*>(dst + i) = o;
+        }
+    } else {
+        for (int i = 0; i < 32; ++i)
+            if (n0 + i < p.n_valid) dst[i] = (add ? dst[i] : 0.f) + __uint_as_float(v[i]);
+    }
+}
+
+__device__ __forceinline__ void epi_gateup(const PfDev& p, int t, int n0, const uint32_t* v) {
+    const int u0 = n0 >> 1;
+    float s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float up = __uint_as_float(v[2 * i]), gate = __uint_as_float(v[2 * i + 1]);
+        s[i] = (1.0f / (1.0f + expf(-gate))) * up;   // swiglu_kernel.cpp:12-13
+    }
+    uint16_t* dst = p.s_out + (size_t)t * p.I_loc + u0;
+    if (u0 + 16 <= p.I_loc && (p.I_loc & 7) == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(s[8], s[9]), pack_bf16x2(s[10], s[11]), pack_bf16x2(s[12], s[13]), pack_bf16x2(s[14], s[15]));
+    } else {
+        for (int i = 0; i < 16; ++i)
+            if (u0 + i < p.I_loc) dst[i] = f32_to_bf16_bits(s[i]);
+    }
+}
+
+__device__ __forceinline__ void kv_store16(uint8_t* cache, int kv_dtype, size_t elem, const float* x) {   // 16 consecutive elements
+    if (kv_dtype == SLLM_BF16) {
+        uint4* d = reinterpret_cast<uint4*>(cache + elem * 2);
+        d[0] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+        d[1] = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
+    } else {
+        float4* d = reinterpret_cast<float4*>(cache + elem * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    }
+}
+__device__ __forceinline__ void kv_store1(uint8_t* cache, int kv_dtype, size_t elem, float x) {
+    if (kv_dtype == SLLM_BF16) reinterpret_cast<uint16_t*>(cache)[elem] = f32_to_bf16_bits(x);
+    else reinterpret_cast<float*>(cache)[elem] = x;
+}
+
+__device__ __forceinline__ void epi_qkv(const PfDev& p, int t, int n0, const uint32_t* v) {
+    const int half = p.hd >> 1, rope_units = (p.q_loc + p.kv_loc) >> 1, nunits = (p.q_loc + 2 * p.kv_loc) >> 1;
+    const int u0 = n0 >> 1;
+    const int pos = p.pos0 + t;
+    if (u0 >= nunits) return;
+    if ((half & 15) == 0 && u0 + 16 <= nunits) {
+        // 16 units = 16 consecutive j of ONE head (half is a multiple of 16) or 32 consecutive V elements
+        if (u0 < rope_units) {
+            const int head = u0 / half, j0 = u0 - head * half;
+            const float4* sp = reinterpret_cast<const float4*>(p.sin_t + (size_t)pos * half + j0);
+            const float4* cp = reinterpret_cast<const float4*>(p.cos_t + (size_t)pos * half + j0);
+            float lo[16], hi[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 s4 = sp[i4], c4 = cp[i4];
+                const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * i4 + k;
+                    const float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+                    lo[i] = a * cc[k] - b * ss[k];   // rope_kernel.cpp:36-37
+                    hi[i] = b * cc[k] + a * ss[k];
+                }
+            }
+            const int r0 = head * p.hd + j0;
+            if (r0 < p.q_loc) {
+                uint16_t* q = p.q_out + (size_t)t * p.q_loc + r0;
+                uint4* a = reinterpret_cast<uint4*>(q);
+                uint4* b = reinterpret_cast<uint4*>(q + half);
+                a[0] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                a[1] = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+                b[0] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+                b[1] = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+            } else {
+                const int kvh = (r0 - p.q_loc) / p.hd;
+                const size_t e0 = ((size_t)kvh * p.S + pos) * p.hd + j0;
+                kv_store16(p.kc, p.kv_dtype, e0, lo);
+                kv_store16(p.kc, p.kv_dtype, e0 + half, hi);
+            }
+        } else {
+            const int b2 = 2 * (u0 - rope_units);
+            const int kvh = b2 / p.hd, j = b2 - kvh * p.hd;
+            const size_t e0 = ((size_t)kvh * p.S + pos) * p.hd + j;
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+            kv_store16(p.vc, p.kv_dtype, e0, x);
+            kv_store16(p.vc, p.kv_dtype, e0 + 16, x + 16);
+        }
+        return;
+    }
+    for (int i = 0; i < 16; ++i) {   // generic shapes: unit by unit
+        const int u = u0 + i;
+        if (u >= nunits) break;
+        const float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+        if (u < rope_units) {
+            const int head = u / half, j = u - head * half;
+            const float s = p.sin_t[(size_t)pos * half + j], c = p.cos_t[(size_t)pos * half + j];
+            const float o0 = a * c - b * s, o1 = b * c + a * s;
+            const int r0 = head * p.hd + j;
+            if (r0 < p.q_loc) {
+                p.q_out[(size_t)t * p.q_loc + r0] = f32_to_bf16_bits(o0);
+                p.q_out[(size_t)t * p.q_loc + r0 + half] = f32_to_bf16_bits(o1);
+            } else {
+                const int kvh = (r0 - p.q_loc) / p.hd;
+                const size_t e0 = ((size_t)kvh * p.S + pos) * p.hd + j;
+                kv_store1(p.kc, p.kv_dtype, e0, o0);
+                kv_store1(p.kc, p.kv_dtype, e0 + half, o1);
+            }
+        } else {
+            const int b2 = 2 * (u - rope_units);
+            const int kvh = b2 / p.hd, j = b2 - kvh * p.hd;
+            const size_t e0 = ((size_t)kvh * p.S + pos) * p.hd + j;
+            kv_store1(p.vc, p.kv_dtype, e0, a);
+            kv_store1(p.vc, p.kv_dtype, e0 + 1, b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kernel ----
+template <int BN>
+__global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                const PfDev p) {
+    using Cfg = PfCfg<BN>;
+    constexpr int ST = Cfg::kStages;
+    extern __shared__ uint8_t pf_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 tiles: 1024-byte aligned
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)ST * kPfABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)ST * Cfg::kBBytes);
+    uint64_t* empty = full + ST;
+    uint64_t* tfull = empty + ST;     // [2] accumulator ready for the epilogue
+    uint64_t* tempty = tfull + 2;     // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < ST; ++s) { mb_init(full + s, 1); mb_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mb_init(tfull + a, 1); mb_init(tempty + a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tc_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;   // consecutive CTAs share the weight tile (L2)
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mb_wait(empty + stage, phase ^ 1);
+                    mb_expect(full + stage, Cfg::kStageBytes);
+                    const int ks = kb / p.kb_per_seg, kk = kb - ks * p.kb_per_seg;
+                    tma_load_2d(sA + (size_t)stage * kPfABytes, &tmA, ks * p.seg_elems + kk * kPfBK, m_tile * kPfBM, full + stage);
+                    if (p.tiled) tma_load_4d(sB + (size_t)stage * Cfg::kBBytes, &tmB, kk * kPfBK, 0, ks, n_tile * (BN / p.R), full + stage);
+                    else tma_load_4d(sB + (size_t)stage * Cfg::kBBytes, &tmB, kk * kPfBK, n_tile * BN, 0, 0, full + stage);
+                    if (++stage == ST) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(kPfBM, BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mb_wait(tempty + acc, acc_phase ^ 1);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mb_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_sw128(sA + (size_t)stage * kPfABytes);
+                    const uint64_t bd = umma_desc_sw128(sB + (size_t)stage * Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kPfBK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+                        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    tc_commit(empty + stage);            // stage reusable once these MMAs have read it
+                    if (++stage == ST) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull + acc);                  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {               // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+            const int t = m_tile * kPfBM + row;
+            mb_wait(tfull + acc, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                const int n0 = n_tile * BN + c0;
+                if (t < p.T && n0 < p.N) {
+                    if (p.epilogue == PF_EPI_QKV) epi_qkv(p, t, n0, v);
+                    else if (p.epilogue == PF_EPI_GATEUP) epi_gateup(p, t, n0, v);
+                    else epi_store(p, t, n0, v, p.epilogue == PF_EPI_RESID);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mb_arrive(tempty + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// -------------------------------------------------------------------------------------------- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct PfCache {
+    std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> weights;   // (W, N, K, tiled, BN)
+};
+PfCache* pf_cache_create() { return new PfCache(); }
+void pf_cache_destroy(PfCache* c) { delete c; }
+
+static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    SLLM_REQUIRE(fn, SLLM_ESTATE, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SLLM_REQUIRE(r == CUDA_SUCCESS, SLLM_EINVAL, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return SLLM_OK;
+}
+
+const char* pf_unsupported_reason(int w_dtype, int hd, int d, int q_loc, int I_loc) {
+    if (w_dtype != SLLM_BF16) return "batched prefill needs bf16 weights (tensor-core operands)";
+    if (hd != 64 && hd != 128) return "batched prefill attention is instantiated for head_dim 64 and 128";
+    if (d % 8 || q_loc % 8 || I_loc % 8) return "row lengths must be multiples of 8 elements (16-byte TMA strides)";
+    return nullptr;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const PfDev& p, cudaStream_t st) {
+    using Cfg = PfCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SLLM_CUDA(cudaFuncSetAttribute(pf_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        configured = true;
+    }
+    const int grid = std::min(sm_count(), p.m_tiles * p.n_tiles);
+    pf_gemm_kernel<BN><<<grid, kPfThreads, Cfg::kSmem, st>>>(tmA, tmB, p);
+    g_launches++;
+    SLLM_LAUNCH_CHECK();
+    return SLLM_OK;
+}
+
+int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
+    SLLM_REQUIRE(cache && a.A && a.W && a.T > 0 && a.N > 0 && a.K > 0, SLLM_EINVAL, "pf_gemm: bad argument");
+    SLLM_REQUIRE(a.K % 8 == 0, SLLM_ENOTSUP, "pf_gemm: K=%d must be a multiple of 8", a.K);
+    PfDev p{};
+    p.T = a.T; p.N = a.N; p.tiled = a.tiled; p.epilogue = a.epilogue;
+    p.m_tiles = (a.T + kPfBM - 1) / kPfBM;
+    TileGeom g{};
+    if (a.tiled) {
+        g = mega_tile_geom(a.N, a.K, SLLM_BF16);
+        p.seg_elems = g.SC * 8; p.R = g.R;
+        p.kb_per_seg = (p.seg_elems + kPfBK - 1) / kPfBK;
+        p.nkb = g.KS * p.kb_per_seg;
+    } else {
+        p.seg_elems = a.K; p.R = 1;
+        p.kb_per_seg = (a.K + kPfBK - 1) / kPfBK;
+        p.nkb = p.kb_per_seg;
+    }
+    // N tile: fewer, fuller waves win (a 128 x 128 tile pays ~10 % for its higher shared-memory traffic per flop)
+    int bn = a.bn;
+    if (bn != 128 && bn != 256) {
+        const int sms = sm_count();
+        auto cost = [&](int b) {
+            const long tiles = (long)p.m_tiles * ((a.N + b - 1) / b);
+            return (double)((tiles + sms - 1) / sms) * b * (b == 128 ? 1.1 : 1.0);
+        };
+        bn = cost(128) <= cost(256) ? 128 : 256;
+    }
+    p.n_tiles = (a.N + bn - 1) / bn;
+    p.out = a.out; p.ld_out = a.ld_out; p.n_valid = a.n_valid;
+    p.q_out = a.q_out; p.kc = a.k_cache; p.vc = a.v_cache; p.kv_dtype = a.kv_dtype; p.q_loc = a.q_loc; p.kv_loc = a.kv_loc; p.hd = a.hd; p.S = a.S;
+    p.pos0 = a.pos0; p.sin_t = a.sin_t; p.cos_t = a.cos_t; p.s_out = a.s_out; p.I_loc = a.I_loc;
+
+    CUtensorMap tmA;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.T};
+        const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+        const cuuint32_t box[2] = {kPfBK, kPfBM};
+        if (int rc = encode(&tmA, a.A, 2, dims, strides, box)) return rc;
+    }
+    const auto key = std::make_tuple(a.W, a.N, a.K, a.tiled, bn);
+    auto it = cache->weights.find(key);
+    if (it == cache->weights.end()) {
+        CUtensorMap tmB;
+        if (a.tiled) {
+            const cuuint64_t dims[4] = {(cuuint64_t)p.seg_elems, (cuuint64_t)g.R, (cuuint64_t)g.KS, (cuuint64_t)g.ntr};
+            const cuuint64_t strides[3] = {(cuuint64_t)g.SC * 16, (cuuint64_t)g.tile_bytes, (cuuint64_t)g.KS * g.tile_bytes};
+            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)g.R, 1, (cuuint32_t)(bn / g.R)};
+            if (int rc = encode(&tmB, a.W, 4, dims, strides, box)) return rc;
+        } else {
+            const cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.N, 1, 1};
+            const cuuint64_t strides[3] = {(cuuint64_t)a.K * 2, (cuuint64_t)a.K * 2 * a.N, (cuuint64_t)a.K * 2 * a.N};
+            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)bn, 1, 1};
+            if (int rc = encode(&tmB, a.W, 4, dims, strides, box)) return rc;
+        }
+        it = cache->weights.emplace(key, tmB).first;
+    }
+    return bn == 128 ? launch<128>(tmA, it->second, p, st) : launch<256>(tmA, it->second, p, st);
+}
+
+}  // namespace sllm
+
+extern "C" int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, int32_t T, int32_t N, int32_t K, int32_t bn, sllm_stream_t stream) {
+    using namespace sllm;
+    SLLM_REQUIRE(A && W && C, SLLM_EINVAL, "null argument");
+    static PfCache* cache = pf_cache_create();
+    cache->weights.clear();   // callers may reuse addresses for different matrices
+    PfGemmArgs a{};
+    a.A = A; a.W = W; a.T = T; a.N = N; a.K = K; a.tiled = 0; a.epilogue = PF_EPI_STORE; a.out = C; a.ld_out = N; a.n_valid = N; a.bn = bn;
+    return pf_gemm(cache, a, as_stream(stream));
+}

@@ -109,8 +109,14 @@ class Engine:
         return out
 
     def prefill(self, prompt, start_pos: int = 0) -> None:
+        """Batched prompt processing on the tensor cores (sllm_engine_prefill): KV cache filled for the whole prompt, the
+        last prompt token's logits in model_pred, its arg-max as the current token. Asynchronous on the engine's stream."""
         prompt = np.ascontiguousarray(prompt, dtype=np.int32)
         _lib.check(self.lib.sllm_engine_prefill(self.h, prompt.ctypes.data, prompt.size, start_pos))
+
+    @property
+    def prefill_supported(self) -> bool:
+        return bool(self.lib.sllm_engine_prefill_supported(self.h))
 
     # -- introspection --
     def buffer(self, name_or_id) -> torch.Tensor:

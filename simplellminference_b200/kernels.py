@@ -110,3 +110,25 @@ def convert_weights(w_f32, w_dtype, group=64):
     scales = torch.empty(rows, cols // group, dtype=torch.float32, device=w_f32.device) if w_dtype == INT8 else None
     _lib.check(_lib.load().sllm_convert_weights(_p(_f32(w_f32)), _p(dst), w_dtype, _p(scales), group, rows, cols, _stream()))
     return dst, scales
+
+
+def prefill_gemm(a_bf16: torch.Tensor, w_bf16: torch.Tensor, bn: int = 0) -> torch.Tensor:
+    """C[T][N] fp32 = A[T][K] . W[N][K]^T on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM)."""
+    assert a_bf16.dtype == torch.bfloat16 and w_bf16.dtype == torch.bfloat16 and a_bf16.is_contiguous() and w_bf16.is_contiguous()
+    T, K = a_bf16.shape
+    N, K2 = w_bf16.shape
+    assert K == K2
+    out = torch.empty(T, N, dtype=torch.float32, device=a_bf16.device)
+    _lib.check(_lib.load().sllm_prefill_gemm_bf16(_p(a_bf16), _p(w_bf16), _p(out), T, N, K, bn, _stream()))
+    return out
+
+
+def prefill_attention(q_bf16: torch.Tensor, key_cache: torch.Tensor, value_cache: torch.Tensor, pos0: int, heads: int, kv_heads: int) -> torch.Tensor:
+    """Causal attention of T queries at positions pos0.. over a head-major cache [kv_heads][max_len][head_dim]."""
+    T = q_bf16.shape[0]
+    kvh, max_len, hd = key_cache.shape
+    assert kvh == kv_heads and q_bf16.shape[1] == heads * hd and q_bf16.dtype == torch.bfloat16
+    kvd = F32 if key_cache.dtype == torch.float32 else BF16
+    out = torch.empty_like(q_bf16)
+    _lib.check(_lib.load().sllm_prefill_attention(_p(q_bf16), _p(key_cache), _p(value_cache), kvd, _p(out), T, pos0, max_len, hd, heads, kv_heads, _stream()))
+    return out
