@@ -56,6 +56,21 @@ def parse():
     return ap.parse_args()
 
 
+def tensor_peak():
+    """(dense bf16 TFLOP/s sustained, source) for the prefill tensor-pipe fraction."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1350.0, "fallback (B200_PROFILING.md sustained cuBLAS bf16)"
+
+
+def prefill_flops(ms, T):
+    """GEMM flops of T prompt rows + last-row classifier + causal attention."""
+    d, kv, I, L, V = ms.hidden, ms.kv_hidden, ms.inter, ms.layers, ms.vocab
+    return 2.0 * T * L * (2 * d * d + 2 * kv * d + 3 * I * d) + 2.0 * V * d + 2.0 * L * d * T * T
+
+
 def peaks():
     """(HBM GB/s, source) — MEASURED_PEAKS.json when the driver wrote it, else the profiling guide's fallback."""
     try:
@@ -226,6 +241,8 @@ def run_ours(args):
     eng.load_synthetic(1234)
     if world > 1:
         eng.init_comm(dist) if args.nccl else eng.init_p2p(dist)
+        if not args.nccl and eng.prefill_supported:
+            eng.init_comm(dist)   # batched prefill all-reduces its [T][d] partial sums with NCCL
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,9 +266,30 @@ def run_ours(args):
         print(json.dumps({"kernel_only": args.kernel_only, "launches": 3 * ms.layers}))
         return
 
-    # ---- prompt: fed token by token through the same decode step (the reference has no batched prefill,
-    # model.cpp:157-166), untimed; it leaves the KV cache filled for positions 0..P-1
     ids = prompt_ids(P, ms.vocab)
+    # ---- batched prefill of the same prompt on the tensor cores (tcgen05 GEMMs), timed on its own: prompt tokens/s and
+    # the fraction of the measured dense-bf16 peak. Host ids -> device inside the timed region (it is the public call).
+    prefill = None
+    if eng.prefill_supported:
+        for _ in range(2):
+            eng.prefill(ids)
+        barrier()
+        R = 5
+        evp = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+        evp[0].record(stream)
+        for r in range(R):
+            eng.prefill(ids)
+            evp[r + 1].record(stream)
+        barrier()
+        pf_ms = max_over_ranks(float(np.median([evp[r].elapsed_time(evp[r + 1]) for r in range(R)])))
+        tpeak, tsrc = tensor_peak()
+        tf = prefill_flops(ms, P) / (pf_ms * 1e-3) / 1e12
+        prefill = {"tokens": P, "ms": pf_ms, "tokens_per_sec": P / (pf_ms * 1e-3), "tflops": tf, "peak_tflops": tpeak * world,
+                   "tensor_pipe_frac": tf / (tpeak * world), "peak_source": tsrc, "reps": R,
+                   "what": "sllm_engine_prefill: all layers over the whole prompt (tcgen05/TMEM GEMMs + block attention) + last-row logits/arg-max; "
+                           "algorithmic flops per SURVEY.md 8d"}
+    # ---- prompt for the decode measurement: fed token by token through the decode step exactly as the reference does
+    # (model.cpp:157-166), untimed; it leaves the KV cache filled for positions 0..P-1 with fp32-activation values
     barrier()
     t_prompt0 = time.perf_counter()
     toks = eng.greedy(ids, P + 1)            # P forwards: positions 0..P-1; state is now (argmax, pos=P)
@@ -350,7 +388,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.wdtype, "data": "synthetic",
         "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
-        "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
+        "prefill": prefill, "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
         "mode": mode + ("" if world == 1 else (" tp/nccl-allreduce" if args.nccl else " tp/peer-memory-allreduce")),
     }
     print(json.dumps(line), flush=True)

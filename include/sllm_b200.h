@@ -201,7 +201,7 @@ int sllm_engine_read_tokens(sllm_engine* e, int32_t* tokens_out_host, int32_t n)
  * GEMMs fed by TMA (bf16 operands, fp32 accumulators), causal attention over the block — instead of the
  * reference's one forward() per prompt token (model.cpp:157-166). Fills the KV cache for start_pos..start_pos+n-1,
  * leaves the LAST prompt token's logits in model_pred, its arg-max as the current token and the position at
- * start_pos+n, exactly as the token-by-token loop would (the last token runs as one ordinary decode step).
+ * start_pos+n, exactly as the token-by-token loop would (the last row's classifier is a T = 1 GEMM + arg-max).
  * Needs SLLM_ENGINE_MEGAKERNEL, bf16 weights and head_dim 64/128: otherwise SLLM_ENOTSUP (feed the prompt through
  * sllm_engine_greedy / sllm_engine_forward, which is what the reference does); sllm_engine_prefill_supported
  * returns 1/0 (0: reason in sllm_last_error). Tensor parallel: also needs sllm_engine_init_comm (NCCL all-reduce of

@@ -934,9 +934,18 @@ static int prefill_workspace(sllm_engine* e, int rows) {
     return SLLM_OK;
 }
 
-// One block of T prompt rows at positions pos0.. through all layers; the last layer stops after its K/V rows are in the
-// cache (its attention/FFN output would only feed logits nobody reads, model.cpp:159-165).
-static int prefill_block(sllm_engine* e, int T, int pos0) {
+__global__ void pf_pack_pair_kernel(const float* logits, const int32_t* idx, int v0, float* pair) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        pair[0] = logits[*idx];
+        pair[1] = __int_as_float(v0 + *idx);
+    }
+}
+
+// One block of T prompt rows at positions pos0.. through all layers. Not the last block: the last layer stops after its
+// K/V rows are in the cache (its attention/FFN output would only feed logits nobody reads, model.cpp:159-165). Last block:
+// the last row goes on through the final norm and the classifier (a T = 1 GEMM over this rank's vocab rows), arg-max, and
+// the step state advances exactly like after a decode step.
+static int prefill_block(sllm_engine* e, int T, int pos0, bool last_block) {
     const sllm_shape& s = e->cfg.shape;
     const int d = e->d, L = e->L;
     const bool tp = e->tp > 1;
@@ -958,7 +967,7 @@ static int prefill_block(sllm_engine* e, int T, int pos0) {
         a.q_out = e->pf_q; a.k_cache = kc; a.v_cache = vc; a.kv_dtype = e->cfg.kv_dtype; a.q_loc = e->q_loc; a.kv_loc = e->kv_loc; a.hd = e->hd;
         a.S = e->S; a.pos0 = pos0; a.sin_t = e->sin_t; a.cos_t = e->cos_t;
         PF(pf_gemm(e->pf, a, st));
-        if (l == L - 1) break;
+        if (l == L - 1 && !last_block) break;
         PF(pf_attention(e->pf_q, kc, vc, e->cfg.kv_dtype, e->pf_att, T, pos0, e->S, e->hd, e->H_loc, e->KVH_loc, st));
         PfGemmArgs c{};
         c.A = e->pf_att; c.W = tiled_layer(e->wo, l); c.T = T; c.N = ((d + 1) / 2) * 2; c.K = e->q_loc; c.tiled = 1;
@@ -974,6 +983,27 @@ static int prefill_block(sllm_engine* e, int T, int pos0) {
         dn.A = e->pf_s; dn.W = tiled_layer(e->wdown, l); dn.K = e->I_loc;
         PF(pf_gemm(e->pf, dn, st));
         if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+    }
+    if (last_block) {
+        const size_t last = (size_t)(T - 1) * d;
+        PF(pf_rmsnorm(e->pf_x + last, tp ? e->pf_part + last : nullptr, e->norms + (size_t)(2 * L) * d, e->pf_xn, 1, d, s.eps, st));
+        SLLM_CUDA(cudaMemcpyAsync(e->x, e->pf_x + last, sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice, st));   // emb_output: final residual
+        const TileGeom eg = mega_tile_geom(((e->V + 1) / 2) * 2, d, e->cfg.w_dtype);
+        PfGemmArgs c{};
+        c.A = e->pf_xn; c.W = reinterpret_cast<const uint8_t*>(e->emb.w) + (size_t)(e->v0 / eg.R) * eg.KS * eg.tile_bytes;
+        c.T = 1; c.N = ((e->V_loc + 1) / 2) * 2; c.K = d; c.tiled = 1; c.epilogue = PF_EPI_STORE; c.out = e->logits; c.ld_out = e->V_loc; c.n_valid = e->V_loc;
+        PF(pf_gemm(e->pf, c, st));
+        PF(sllm_argmax_f32(e->logits, e->V_loc, e->blk_idx, st));
+        if (tp) {
+            pf_pack_pair_kernel<<<1, 32, 0, st>>>(e->logits, e->blk_idx, e->v0, e->tp_pairs + 2 * e->rank);
+            SLLM_NCCL(ncclAllGather(e->tp_pairs + 2 * e->rank, e->tp_pairs, 2, ncclFloat, e->comm, st));
+            tp_merge_kernel<<<1, 32, 0, st>>>(e->tp_pairs, e->tp, e->state, e->prompt_dev, e->history_dev);
+            g_launches += 2;
+        } else {
+            feedback_kernel<<<1, 1, 0, st>>>(e->state, e->blk_idx, e->prompt_dev, e->history_dev);
+            g_launches++;
+        }
+        SLLM_LAUNCH_CHECK();
     }
 #undef PF
     e->total_launches += g_launches - before;
@@ -995,22 +1025,19 @@ int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt, int32_t n, int32_
     if (const char* why = prefill_unsupported(e)) { set_error("%s", why); return SLLM_ENOTSUP; }
     SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel prefill needs the NCCL communicator (sllm_engine_init_comm)");
     SLLM_REQUIRE(e->tp == 1 || e->ll_ready, SLLM_ESTATE, "tensor-parallel engine: peer areas not exchanged yet");
-    // rows 0..n-2 in blocks through the tensor-core path (KV cache only); the LAST prompt token runs as one ordinary
-    // decode step, which leaves logits, arg-max and the step state exactly as the token-by-token loop would
-    const int nb = n - 1;
+    // blocks of up to kBlock rows through the tensor-core path; the last block also produces the last row's logits,
+    // the arg-max and the step-state update (token = arg-max, position = start_pos + n, history)
     constexpr int kBlock = 1024;
-    if (nb > 0) {
-        if (int rc = prefill_workspace(e, std::min(nb, kBlock))) return rc;
-        for (int b0 = 0; b0 < nb; b0 += kBlock) {
-            const int T = std::min(kBlock, nb - b0);
-            SLLM_CUDA(cudaMemcpyAsync(e->pf_ids, prompt + b0, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, e->stream));
-            if (int rc = prefill_block(e, T, start_pos + b0)) return rc;
-        }
-        SLLM_CUDA(cudaMemcpyAsync(e->history_dev + start_pos, prompt + 1, sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, e->stream));
-    }
+    if (int rc = prefill_workspace(e, std::min(n, kBlock))) return rc;
+    if (n > 1) SLLM_CUDA(cudaMemcpyAsync(e->history_dev + start_pos, prompt + 1, sizeof(int32_t) * (size_t)(n - 1), cudaMemcpyHostToDevice, e->stream));
     if (int rc = set_state(e, prompt[n - 1], start_pos + n - 1, 0)) return rc;
-    e->h_state[7] = start_pos + n - 1;
-    return sllm_engine_enqueue_steps(e, 1);
+    for (int b0 = 0; b0 < n; b0 += kBlock) {
+        const int T = std::min(kBlock, n - b0);
+        SLLM_CUDA(cudaMemcpyAsync(e->pf_ids, prompt + b0, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, e->stream));
+        if (int rc = prefill_block(e, T, start_pos + b0, b0 + T == n)) return rc;
+    }
+    e->h_state[7] = start_pos + n;
+    return SLLM_OK;
 }
 
 int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32_t* dtype) {

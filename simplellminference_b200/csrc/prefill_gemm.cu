@@ -24,6 +24,7 @@
 
 namespace sllm {
 
+extern int g_tune_pf_bn;
 constexpr int kPfBM = 128, kPfBK = 64, kPfThreads = 192;
 constexpr uint32_t kPfABytes = kPfBM * kPfBK * 2;
 template <int BN> struct PfCfg {
@@ -417,15 +418,16 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
         p.kb_per_seg = (a.K + kPfBK - 1) / kPfBK;
         p.nkb = p.kb_per_seg;
     }
-    // N tile: fewer, fuller waves win (a 128 x 128 tile pays ~10 % for its higher shared-memory traffic per flop)
-    int bn = a.bn;
+    // N tile: the kernel is L2->SM bandwidth bound (measured: ~10 TB/s whatever the tile), so a tile costs (BM + BN) * K
+    // operand bytes; pick the shape with the least waves x bytes
+    int bn = a.bn ? a.bn : g_tune_pf_bn;
     if (bn != 128 && bn != 256) {
         const int sms = sm_count();
         auto cost = [&](int b) {
             const long tiles = (long)p.m_tiles * ((a.N + b - 1) / b);
-            return (double)((tiles + sms - 1) / sms) * b * (b == 128 ? 1.1 : 1.0);
+            return (double)((tiles + sms - 1) / sms) * (kPfBM + b);
         };
-        bn = cost(128) <= cost(256) ? 128 : 256;
+        bn = cost(128) < cost(256) ? 128 : 256;
     }
     p.n_tiles = (a.N + bn - 1) / bn;
     p.out = a.out; p.ld_out = a.ld_out; p.n_valid = a.n_valid;

@@ -9,6 +9,7 @@ namespace sllm {
 static thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
 int g_tune_ctas_per_sm = 0;
+int g_tune_pf_bn = 0;   // prefill GEMM: force the N tile (128 / 256), 0 = heuristic
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -54,6 +55,7 @@ int sllm_abi_version(void) { return 1; }
 int sllm_tune(int32_t key, int32_t value) {
     switch (key) {
         case 0: sllm::g_tune_ctas_per_sm = value; return SLLM_OK;
+        case 1: sllm::g_tune_pf_bn = value; return SLLM_OK;
         default: sllm::set_error("unknown tunable %d", key); return SLLM_EINVAL;
     }
 }

@@ -176,7 +176,7 @@ def test_prefill_in_two_blocks_equals_one(port):
     two.prefill(ids[77:], start_pos=77)
     torch.cuda.synchronize()
     a, b = one.buffer("model_pred").cpu().numpy(), two.buffer("model_pred").cpu().numpy()
-    # position 76 went through the decode step (fp32 activations) instead of the bf16 block path: tiny difference allowed
+    # different block boundaries = different tile shapes / summation order in attention: tiny difference allowed
     assert float(np.abs(a - b).max()) <= 2e-2 * max(1.0, float(np.abs(a).max()))
     one.close(); two.close()
 
