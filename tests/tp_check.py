@@ -62,6 +62,43 @@ def main():
         eng.close()
         if rank == 0:
             print(f"tp{world} {name}: {n_total - 1} tokens ok on every rank, max|dlogit|={err:.2e} (tol {tol:.1e})", flush=True)
+    # ---- batched prefill under tensor parallelism (tcgen05 GEMMs per rank + NCCL all-reduce of the [T][d] partial sums):
+    # last-position logits against the oracle's token-by-token loop on the gain-1 blob (tests/test_prefill_gpu.py explains
+    # why), then the decode that follows must agree on every rank.
+    ms = ModelShape(4096, 128, 1024, 1024, 2816, 400, 4, 8, 8)
+    if not (ms.kv_heads % world or ms.inter % world or ms.vocab % world):
+        shape = loader.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, ms.layers, ms.heads, ms.kv_heads, ms.eps, ms.theta)
+        blob = port.fill_blob(shape, 21, BF16)
+        for seg in range(2, 9):
+            off, cnt = port.segment(shape, seg)[:2]
+            blob[off:off + cnt] *= 0.25
+        n = 300
+        ids = np.random.default_rng(5).integers(1, ms.vocab, size=n, dtype=np.int32)
+        om = port.model(shape, blob, threads=4, kv_bf16=True)
+        for p in range(n - 1):
+            om.step(int(ids[p]), p)
+        want_l = om.forward(int(ids[n - 1]), n - 1)
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=True, mega=True).load_blob(blob)
+        assert eng.mode == "megakernel(ll)" and eng.prefill_supported, eng.mode
+        eng.init_p2p(dist).init_comm(dist)
+        eng.prefill(ids)
+        torch.cuda.synchronize()
+        v_loc = ms.vocab // world
+        logits = eng.buffer("model_pred").cpu().numpy()
+        err = float(np.abs(logits - want_l[rank * v_loc:(rank + 1) * v_loc]).max())
+        tol = 3e-2 * max(1.0, float(np.abs(want_l).max()))
+        assert err <= tol, ("prefill", rank, err, tol)
+        eng.enqueue_steps(5)
+        toks = torch.tensor(eng.read_tokens(6), device="cuda")
+        assert int(toks[0]) == int(np.argmax(want_l)), (int(toks[0]), int(np.argmax(want_l)))
+        allt = [torch.zeros_like(toks) for _ in range(world)]
+        dist.all_gather(allt, toks)
+        assert all(torch.equal(t, allt[0]) for t in allt), "ranks disagree on the tokens decoded after a prefill"
+        eng.close()
+        if rank == 0:
+            print(f"tp{world} batched prefill of {n} tokens: max|dlogit|={err:.2e} (tol {tol:.1e}), next token and 5 decoded tokens agree on every rank", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
