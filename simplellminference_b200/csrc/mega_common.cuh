@@ -17,6 +17,15 @@ constexpr unsigned kSpinLimit = 1u << 26;
 #define SLLM_L2_AHEAD 0
 #endif
 constexpr int kL2AheadBytes = SLLM_L2_AHEAD;  // per CTA: how much of the next phase is pulled into L2 during a phase gap
+#ifndef SLLM_L2_START
+#define SLLM_L2_START 0
+#endif
+#ifndef SLLM_L2_ATT
+#define SLLM_L2_ATT 0
+#endif
+// per CTA: bytes of a weight phase pulled into L2 right AFTER the grid barrier that precedes it (HBM is idle while every CTA
+// builds its activation vector), and bytes of the wo phase pulled in when the (latency-bound) attention phase starts
+constexpr int kL2StartBytes = SLLM_L2_START, kL2AttBytes = SLLM_L2_ATT;
 constexpr int kAttRecPad = 4;     // partial record = hd floats of O, then m, l (+2 pad: keeps float4 alignment)
 
 

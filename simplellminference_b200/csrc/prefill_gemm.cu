@@ -24,19 +24,22 @@
 
 namespace sllm {
 
-extern int g_tune_pf_bn;
+extern int g_tune_pf_bn, g_tune_pf_pair;
 constexpr int kPfBM = 128, kPfBK = 64, kPfThreads = 192;
 constexpr uint32_t kPfABytes = kPfBM * kPfBK * 2;
-template <int BN> struct PfCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
-    static constexpr uint32_t kBBytes = BN * kPfBK * 2;
-    static constexpr uint32_t kStageBytes = kPfABytes + kBBytes;
-    static constexpr uint32_t kTmemCols = 2 * BN;
-    static constexpr size_t kSmem = 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers + tmem slot*/;
-};
+// PAIR = true: two CTAs of a cluster (the two SMs of a TPC) work on ONE 256 x BN tile with tcgen05.mma.cta_group::2 — each
+// CTA stages its own 128 rows of A and its own BN/2 rows of W, so shared-memory traffic (TMA writes + tensor-core reads) and
+// L2->SM traffic per flop are 2/3 of the single-CTA 128 x BN tile's (measured bound of the single-CTA kernel: 55 % tensor
+// pipe inside a tile, profiles/r01_prefill_ncu_raw.md).
+// The N extent of a tile (BN) is a RUN-TIME multiple of 32 up to 256 (one tcgen05.mma takes any N that is a multiple of 16):
+// the host picks the BN that fills the last wave best, e.g. 192 instead of 256 for a 512 x 12288 output on 74 SM pairs.
+constexpr int kPfMaxStages = 12;
+constexpr uint32_t kPfRingBytes = 192 * 1024;          // operand ring; stages = ring / (A box + this CTA's W box)
+constexpr uint32_t kPfTmemCols = 512;                  // two accumulators of up to 256 fp32 columns
+constexpr size_t kPfSmem = 1024 /*alignment slack*/ + kPfRingBytes + 512 /*barriers + tmem slot*/;
 
 struct PfDev {           // kernel-side view of PfGemmArgs
-    int32_t T, N, m_tiles, n_tiles;
+    int32_t T, N, m_tiles, n_tiles, BN;
     int32_t nkb, kb_per_seg, seg_elems, R, tiled;
     int32_t epilogue;
     float* out; int32_t ld_out, n_valid;
@@ -53,6 +56,46 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(s_addr(dst)), "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// cta_group::2 forms: the destination is this CTA's shared memory, the mbarrier may live in the peer CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_addr(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(s_addr(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t cta) {   // shared::cluster address of `local` in CTA `cta`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(s_addr(local)), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mb_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_alloc_pair(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_addr(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
 __device__ __forceinline__ void mb_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory"); }
@@ -241,18 +284,23 @@ __device__ __forceinline__ void epi_qkv(const PfDev& p, int t, int n0, const uin
 }
 
 // ------------------------------------------------------------------------------------------ kernel ----
-template <int BN>
+template <bool PAIR>
 __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const PfDev p) {
-    using Cfg = PfCfg<BN>;
-    constexpr int ST = Cfg::kStages;
+    constexpr int BM = PAIR ? 2 * kPfBM : kPfBM;          // rows of the (pair's) tile
+    const int BN = p.BN;
+    const int b_rows = PAIR ? BN / 2 : BN;                 // W rows staged by one CTA
+    const uint32_t b_bytes = (uint32_t)b_rows * kPfBK * 2, stage_bytes = kPfABytes + b_bytes;
+    const int ST = min((int)(kPfRingBytes / stage_bytes), kPfMaxStages);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader: issues the MMAs of the pair
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t pf_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 tiles: 1024-byte aligned
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)ST * kPfABytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)ST * Cfg::kBBytes);
-    uint64_t* empty = full + ST;
-    uint64_t* tfull = empty + ST;     // [2] accumulator ready for the epilogue
+    uint8_t* sA = smem;                                    // [ST] 128 x 64 bf16, 16 KB each
+    uint8_t* sB = smem + (size_t)ST * kPfABytes;           // [ST] b_rows x 64 bf16 (multiples of 1024 bytes: b_rows % 8 == 0)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPfRingBytes);
+    uint64_t* empty = full + kPfMaxStages;
+    uint64_t* tfull = empty + kPfMaxStages;     // [2] accumulator ready for the epilogue
     uint64_t* tempty = tfull + 2;     // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -261,12 +309,12 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < ST; ++s) { mb_init(full + s, 1); mb_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mb_init(tfull + a, 1); mb_init(tempty + a, 4); }
+        for (int a = 0; a < 2; ++a) { mb_init(tfull + a, 1); mb_init(tempty + a, PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tc_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 1) { if (PAIR) tc_alloc_pair(tmem_slot, kPfTmemCols); else tc_alloc(tmem_slot, kPfTmemCols); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int ntiles = p.m_tiles * p.n_tiles;
@@ -275,40 +323,55 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
         if (lane == 0) {   // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;   // consecutive CTAs share the weight tile (L2)
+            for (int tile = worker; tile < ntiles; tile += nworkers) {
+                const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;   // consecutive workers share the weight tile (L2)
+                const int row0 = m_tile * BM + (int)rank * kPfBM;                  // this CTA's 128 rows of A
+                const int n0 = n_tile * BN + (int)rank * b_rows;                   // this CTA's rows of W
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mb_wait(empty + stage, phase ^ 1);
-                    mb_expect(full + stage, Cfg::kStageBytes);
                     const int ks = kb / p.kb_per_seg, kk = kb - ks * p.kb_per_seg;
-                    tma_load_2d(sA + (size_t)stage * kPfABytes, &tmA, ks * p.seg_elems + kk * kPfBK, m_tile * kPfBM, full + stage);
-                    if (p.tiled) tma_load_4d(sB + (size_t)stage * Cfg::kBBytes, &tmB, kk * kPfBK, 0, ks, n_tile * (BN / p.R), full + stage);
-                    else tma_load_4d(sB + (size_t)stage * Cfg::kBBytes, &tmB, kk * kPfBK, n_tile * BN, 0, 0, full + stage);
+                    uint8_t* a_dst = sA + (size_t)stage * kPfABytes;
+                    uint8_t* b_dst = sB + (size_t)stage * b_bytes;
+                    if (PAIR) {
+                        // both CTAs' bytes are counted on the LEADER's barrier (it is the leader that issues the MMAs)
+                        if (rank == 0) mb_expect(full + stage, 2 * stage_bytes);
+                        const uint32_t bar = mapa_u32(full + stage, 0);
+                        tma_load_2d_pair(a_dst, &tmA, ks * p.seg_elems + kk * kPfBK, row0, bar);
+                        if (p.tiled) tma_load_4d_pair(b_dst, &tmB, kk * kPfBK, 0, ks, n0 / p.R, bar);
+                        else tma_load_4d_pair(b_dst, &tmB, kk * kPfBK, n0, 0, 0, bar);
+                    } else {
+                        mb_expect(full + stage, stage_bytes);
+                        tma_load_2d(a_dst, &tmA, ks * p.seg_elems + kk * kPfBK, row0, full + stage);
+                        if (p.tiled) tma_load_4d(b_dst, &tmB, kk * kPfBK, 0, ks, n0 / p.R, full + stage);
+                        else tma_load_4d(b_dst, &tmB, kk * kPfBK, n0, 0, 0, full + stage);
+                    }
                     if (++stage == ST) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_bf16(kPfBM, BN);
+        if (lane == 0 && rank == 0) {   // ===== MMA issuer (pair: the leader CTA only) =====
+            const uint32_t idesc = umma_idesc_bf16(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = worker; tile < ntiles; tile += nworkers) {
                 mb_wait(tempty + acc, acc_phase ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mb_wait(full + stage, phase);
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(sA + (size_t)stage * kPfABytes);
-                    const uint64_t bd = umma_desc_sw128(sB + (size_t)stage * Cfg::kBBytes);
+                    const uint64_t bd = umma_desc_sw128(sB + (size_t)stage * b_bytes);
 #pragma unroll
-                    for (int k = 0; k < kPfBK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
-                        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    tc_commit(empty + stage);            // stage reusable once these MMAs have read it
+                    for (int k = 0; k < kPfBK / 16; ++k) {   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+                        if (PAIR) tc_mma_bf16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    if (PAIR) tc_commit_pair(empty + stage); else tc_commit(empty + stage);   // stage reusable once these MMAs have read it
                     if (++stage == ST) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull + acc);                  // accumulator complete
+                if (PAIR) tc_commit_pair(tfull + acc); else tc_commit(tfull + acc);           // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -317,15 +380,16 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
         const int row = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t tempty_leader[2] = {PAIR ? mapa_u32(tempty, 0) : 0u, PAIR ? mapa_u32(tempty + 1, 0) : 0u};
+        for (int tile = worker; tile < ntiles; tile += nworkers) {
             const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-            const int t = m_tile * kPfBM + row;
+            const int t = m_tile * BM + (int)rank * kPfBM + row;
             mb_wait(tfull + acc, acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
                 const int n0 = n_tile * BN + c0;
                 if (t < p.T && n0 < p.N) {
                     if (p.epilogue == PF_EPI_QKV) epi_qkv(p, t, n0, v);
@@ -335,15 +399,15 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mb_arrive(tempty + acc);
+            if (lane == 0) { if (PAIR) mb_arrive_cluster(tempty_leader[acc]); else mb_arrive(tempty + acc); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: nobody leaves while the peer may still signal its barriers / read its operands
     if (warp == 1) {
         tc_fence_after();
-        tc_dealloc(tmem_base, Cfg::kTmemCols);
+        if (PAIR) tc_dealloc_pair(tmem_base, kPfTmemCols); else tc_dealloc(tmem_base, kPfTmemCols);
     }
 }
 
@@ -362,7 +426,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct PfCache {
-    std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> weights;   // (W, N, K, tiled, BN)
+    std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> weights;   // (W, N, K, tiled, rows per box)
 };
 PfCache* pf_cache_create() { return new PfCache(); }
 void pf_cache_destroy(PfCache* c) { delete c; }
@@ -386,18 +450,28 @@ const char* pf_unsupported_reason(int w_dtype, int hd, int d, int q_loc, int I_l
     return nullptr;
 }
 
-template <int BN>
+template <bool PAIR>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const PfDev& p, cudaStream_t st) {
-    using Cfg = PfCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        SLLM_CUDA(cudaFuncSetAttribute(pf_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        SLLM_CUDA(cudaFuncSetAttribute(pf_gemm_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem));
         configured = true;
     }
-    const int grid = std::min(sm_count(), p.m_tiles * p.n_tiles);
-    pf_gemm_kernel<BN><<<grid, kPfThreads, Cfg::kSmem, st>>>(tmA, tmB, p);
+    const int workers = std::min(PAIR ? sm_count() / 2 : sm_count(), p.m_tiles * p.n_tiles);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
+    cfg.blockDim = dim3(kPfThreads);
+    cfg.dynamicSmemBytes = kPfSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SLLM_CUDA(cudaLaunchKernelEx(&cfg, pf_gemm_kernel<PAIR>, tmA, tmB, p));
     g_launches++;
-    SLLM_LAUNCH_CHECK();
     return SLLM_OK;
 }
 
@@ -406,7 +480,10 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
     SLLM_REQUIRE(a.K % 8 == 0, SLLM_ENOTSUP, "pf_gemm: K=%d must be a multiple of 8", a.K);
     PfDev p{};
     p.T = a.T; p.N = a.N; p.tiled = a.tiled; p.epilogue = a.epilogue;
-    p.m_tiles = (a.T + kPfBM - 1) / kPfBM;
+    // more than one 128-row block of tokens: two SMs share a 256-row tile (tcgen05 cta_group::2)
+    const bool pair = g_tune_pf_pair >= 0 ? (g_tune_pf_pair != 0) : (a.T > kPfBM);
+    const int BM = pair ? 2 * kPfBM : kPfBM;
+    p.m_tiles = (a.T + BM - 1) / BM;
     TileGeom g{};
     if (a.tiled) {
         g = mega_tile_geom(a.N, a.K, SLLM_BF16);
@@ -418,17 +495,19 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
         p.kb_per_seg = (a.K + kPfBK - 1) / kPfBK;
         p.nkb = p.kb_per_seg;
     }
-    // N tile: the kernel is L2->SM bandwidth bound (measured: ~10 TB/s whatever the tile), so a tile costs (BM + BN) * K
-    // operand bytes; pick the shape with the least waves x bytes
+    // N extent of a tile: any multiple of 32 up to 256. A tile costs ~BN tensor-core time (plus a fixed per-tile part, here 32
+    // columns' worth: pipeline fill + epilogue tail); the step takes ceil(tiles / workers) waves of it. Pick the cheapest.
     int bn = a.bn ? a.bn : g_tune_pf_bn;
-    if (bn != 128 && bn != 256) {
-        const int sms = sm_count();
-        auto cost = [&](int b) {
+    if (bn < 32 || bn > 256 || bn % 32) {
+        const int workers = pair ? sm_count() / 2 : sm_count();
+        double best = 1e30;
+        for (int b = 256; b >= 64; b -= 32) {
             const long tiles = (long)p.m_tiles * ((a.N + b - 1) / b);
-            return (double)((tiles + sms - 1) / sms) * (kPfBM + b);
-        };
-        bn = cost(128) < cost(256) ? 128 : 256;
+            const double c = (double)((tiles + workers - 1) / workers) * (b + 32);
+            if (c < best - 1e-9) { best = c; bn = b; }
+        }
     }
+    p.BN = bn;
     p.n_tiles = (a.N + bn - 1) / bn;
     p.out = a.out; p.ld_out = a.ld_out; p.n_valid = a.n_valid;
     p.q_out = a.q_out; p.kc = a.k_cache; p.vc = a.v_cache; p.kv_dtype = a.kv_dtype; p.q_loc = a.q_loc; p.kv_loc = a.kv_loc; p.hd = a.hd; p.S = a.S;
@@ -441,24 +520,25 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
         const cuuint32_t box[2] = {kPfBK, kPfBM};
         if (int rc = encode(&tmA, a.A, 2, dims, strides, box)) return rc;
     }
-    const auto key = std::make_tuple(a.W, a.N, a.K, a.tiled, bn);
+    const int box_rows = pair ? bn / 2 : bn;   // W rows one CTA stages per k-block
+    const auto key = std::make_tuple(a.W, a.N, a.K, a.tiled, box_rows);
     auto it = cache->weights.find(key);
     if (it == cache->weights.end()) {
         CUtensorMap tmB;
         if (a.tiled) {
             const cuuint64_t dims[4] = {(cuuint64_t)p.seg_elems, (cuuint64_t)g.R, (cuuint64_t)g.KS, (cuuint64_t)g.ntr};
             const cuuint64_t strides[3] = {(cuuint64_t)g.SC * 16, (cuuint64_t)g.tile_bytes, (cuuint64_t)g.KS * g.tile_bytes};
-            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)g.R, 1, (cuuint32_t)(bn / g.R)};
+            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)g.R, 1, (cuuint32_t)(box_rows / g.R)};
             if (int rc = encode(&tmB, a.W, 4, dims, strides, box)) return rc;
         } else {
             const cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.N, 1, 1};
             const cuuint64_t strides[3] = {(cuuint64_t)a.K * 2, (cuuint64_t)a.K * 2 * a.N, (cuuint64_t)a.K * 2 * a.N};
-            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)bn, 1, 1};
+            const cuuint32_t box[4] = {kPfBK, (cuuint32_t)box_rows, 1, 1};
             if (int rc = encode(&tmB, a.W, 4, dims, strides, box)) return rc;
         }
         it = cache->weights.emplace(key, tmB).first;
     }
-    return bn == 128 ? launch<128>(tmA, it->second, p, st) : launch<256>(tmA, it->second, p, st);
+    return pair ? launch<true>(tmA, it->second, p, st) : launch<false>(tmA, it->second, p, st);
 }
 
 }  // namespace sllm

@@ -29,7 +29,7 @@ from simplellminference_b200.engine import Engine
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("bn", [128, 256, 0])
+@pytest.mark.parametrize("bn", [128, 256, 0, 96, 224])
 @pytest.mark.parametrize("T,N,K_", [(128, 128, 64), (128, 256, 256), (512, 1024, 4096), (300, 1000, 1408), (77, 264, 520), (1, 128, 64),
                                     (640, 4096 + 32, 2048)])
 def test_gemm_tcgen05_matches_torch(T, N, K_, bn):

@@ -31,12 +31,14 @@ def main():
     ap.add_argument("--tokens", type=int, default=512)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--bn", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=-1, help="1/0 force/forbid the two-SM (cta_group::2) GEMM, -1 heuristic")
     a = ap.parse_args()
     ms = PRESETS[a.config]
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     if a.bn:
         _lib.load().sllm_tune(1, a.bn)
+    _lib.load().sllm_tune(2, a.pair)
     eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True).load_synthetic(1234)
     rng = np.random.default_rng(20260101)
     ids = rng.integers(1, ms.vocab, size=a.tokens, dtype=np.int32)
@@ -60,7 +62,7 @@ def main():
     tf = prefill_flops(ms, a.tokens) / (msec * 1e-3) / 1e12
     print(json.dumps({"config": a.config, "tokens": a.tokens, "ms": round(msec, 3), "all_ms": [round(t, 3) for t in times],
                       "prompt_tokens_per_s": round(a.tokens / (msec * 1e-3), 1), "tflops": round(tf, 1), "peak_tflops": peak,
-                      "tensor_pipe_frac": round(tf / peak, 4), "bn": a.bn, "next_token": int(eng.read_tokens(1)[0])}))
+                      "tensor_pipe_frac": round(tf / peak, 4), "bn": a.bn, "pair": a.pair, "next_token": int(eng.read_tokens(1)[0])}))
 
 
 if __name__ == "__main__":
