@@ -11,6 +11,7 @@
 #include "prefill.cuh"
 
 namespace sllm {
+extern int g_tune_pf_pdl;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
     const int n = valid ? 16 : 0;   // src-size 0: destination is zero-filled, nothing is read
@@ -53,6 +54,8 @@ __global__ void __launch_bounds__(kPaThreads) pf_attn_kernel(const uint16_t* __r
     const uint8_t* Kh = Kc + (size_t)kvh * S * HD * ESZ;
     const uint8_t* Vh = Vc + (size_t)kvh * S * HD * ESZ;
     auto sw = [](int row, int chunk) { return (row * CPR + (chunk ^ (row & 7))) * 16; };
+    pdl_wait();
+    pdl_launch_dependents();
 
     for (int i = tid; i < kPaBQ * CPR; i += kPaThreads) {
         const int row = i / CPR, c = i - row * CPR;
@@ -196,10 +199,10 @@ static int attn_launch(const uint16_t* q, const void* kc, const void* vc, uint16
     }
     const dim3 grid((T + kPaBQ - 1) / kPaBQ, heads);
     const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
-    pf_attn_kernel<HD, KVD><<<grid, kPaThreads, smem, st>>>(q, reinterpret_cast<const uint8_t*>(kc), reinterpret_cast<const uint8_t*>(vc), out, T, pos0, S,
-                                                            heads * HD, heads / kv_heads, scale_log2);
+    LaunchCfg lc(grid, dim3(kPaThreads), smem, st, g_tune_pf_pdl != 0);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, pf_attn_kernel<HD, KVD>, q, reinterpret_cast<const uint8_t*>(kc), reinterpret_cast<const uint8_t*>(vc), out, T, pos0, S,
+                                 heads * HD, heads / kv_heads, scale_log2));
     g_launches++;
-    SLLM_LAUNCH_CHECK();
     return SLLM_OK;
 }
 
@@ -241,6 +244,8 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_kernel(float* __restrict__ x, 
                                                         uint16_t* __restrict__ y, int d, float eps) {
     __shared__ float red[33];
     const int t = blockIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
     float4* xr = reinterpret_cast<float4*>(x + (size_t)t * d);
     const float4* ar = add ? reinterpret_cast<const float4*>(add + (size_t)t * d) : nullptr;
     float ss = 0.f;
@@ -265,9 +270,9 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_kernel(float* __restrict__ x, 
 
 int pf_rmsnorm(float* x, const float* add, const float* w, uint16_t* y, int T, int d, float eps, cudaStream_t st) {
     SLLM_REQUIRE(d % 4 == 0, SLLM_ENOTSUP, "pf_rmsnorm: d must be a multiple of 4");
-    pf_rmsnorm_kernel<<<T, 256, 0, st>>>(x, add, w, y, d, eps);
+    LaunchCfg lc(dim3(T), dim3(256), 0, st, g_tune_pf_pdl != 0);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, pf_rmsnorm_kernel, x, add, w, y, d, eps));
     g_launches++;
-    SLLM_LAUNCH_CHECK();
     return SLLM_OK;
 }
 

@@ -24,7 +24,7 @@
 
 namespace sllm {
 
-extern int g_tune_pf_bn, g_tune_pf_pair;
+extern int g_tune_pf_bn, g_tune_pf_pair, g_tune_pf_pdl;
 constexpr int kPfBM = 128, kPfBK = 64, kPfThreads = 192;
 constexpr uint32_t kPfABytes = kPfBM * kPfBK * 2;
 // PAIR = true: two CTAs of a cluster (the two SMs of a TPC) work on ONE 256 x BN tile with tcgen05.mma.cta_group::2 — each
@@ -318,6 +318,10 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int ntiles = p.m_tiles * p.n_tiles;
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (A, the residual
+    // stream) are visible after the wait. The next kernel may start ITS set-up as soon as every CTA here is past this point.
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
@@ -463,13 +467,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const PfDev& p
     cfg.blockDim = dim3(kPfThreads);
     cfg.dynamicSmemBytes = kPfSmem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_tune_pf_pdl ? 2 : 1;
     SLLM_CUDA(cudaLaunchKernelEx(&cfg, pf_gemm_kernel<PAIR>, tmA, tmB, p));
     g_launches++;
     return SLLM_OK;

@@ -10,6 +10,7 @@ static thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
 int g_tune_ctas_per_sm = 0;
 int g_tune_pf_bn = 0;   // prefill GEMM: force the N tile (128 / 256), 0 = heuristic
+int g_tune_pf_pdl = 1;     // prefill kernels: programmatic dependent launch (set-up overlaps the previous kernel's tail)
 int g_tune_pf_pair = -1;   // prefill GEMM: 1 / 0 = force / forbid the two-SM (cta_group::2) kernel, -1 = heuristic
 
 void set_error(const char* fmt, ...) {
@@ -58,6 +59,7 @@ int sllm_tune(int32_t key, int32_t value) {
         case 0: sllm::g_tune_ctas_per_sm = value; return SLLM_OK;
         case 1: sllm::g_tune_pf_bn = value; return SLLM_OK;
         case 2: sllm::g_tune_pf_pair = value; return SLLM_OK;
+        case 3: sllm::g_tune_pf_pdl = value; return SLLM_OK;
         default: sllm::set_error("unknown tunable %d", key); return SLLM_EINVAL;
     }
 }

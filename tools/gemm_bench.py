@@ -14,9 +14,11 @@ from simplellminference_b200 import _lib, kernels as K  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--tokens", type=int, default=512)
 ap.add_argument("--bn", type=int, default=0)
+ap.add_argument("--pdl", type=int, default=1)
 ap.add_argument("--pair", type=int, default=-1)
 a = ap.parse_args()
 _lib.load().sllm_tune(2, a.pair)
+_lib.load().sllm_tune(3, a.pdl)
 T = a.tokens
 shapes = [("qkv", 12288, 4096), ("wo", 4096, 4096), ("gate_up", 22016, 4096), ("down", 4096, 11008)]
 nw = 24   # rotate over several weight matrices so that W comes from HBM like in the real layer loop
