@@ -68,6 +68,11 @@ public:
     void set_weights(const float* blob, size_t n_floats);     // caller memory instead of model_path
     void set_forward_mode(ForwardMode mode) { mode_ = mode; }
     void set_storage(base::DataType weights, base::DataType kv_cache) { w_dtype_ = weights; kv_dtype_ = kv_cache; }
+    // predict(): run the prompt as ONE batched pass on the tensor cores (sllm_engine_prefill) instead of one forward per
+    // prompt token (model.cpp:157-166). Engine mode, bf16 weights, head_dim 64/128; silently keeps the token-by-token
+    // prompt where the engine cannot batch it. Results agree within the bf16-operand tolerance, not bit for bit.
+    void set_batched_prefill(bool on) { batched_prefill_ = on; }
+    bool batched_prefill_active() const;
 
     void init();
     void forward();   // one token at one position: reads input_token / position (CPU tensors), fills model_pred
@@ -94,7 +99,7 @@ protected:
     std::unique_ptr<LlamaLayer> Llama_layers_;
     ForwardMode mode_ = ForwardMode::kEngine;
     base::DataType w_dtype_ = base::DataType::kFp32, kv_dtype_ = base::DataType::kFp32;
-    bool config_set_ = false;
+    bool config_set_ = false, batched_prefill_ = false;
     sllm_engine* engine_ = nullptr;
     size_t n_weight_floats_ = 0;
 };

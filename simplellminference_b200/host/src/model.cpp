@@ -232,10 +232,23 @@ void LlamaModel::forward_op_by_op() {
     Ls.cls_layer->forward(B(ModelBufferType::rms_output), B(ModelBufferType::model_pred));
 }
 
+bool LlamaModel::batched_prefill_active() const {
+    return batched_prefill_ && engine_ != nullptr && sllm_engine_prefill_supported(engine_) == 1;
+}
+
 std::vector<int32_t> LlamaModel::predict(const std::vector<int32_t>& prompt_ids, int max_length) {
     if (prompt_ids.empty()) LOG("predict: empty prompt");
     if (max_length >= config_->max_length) LOG("predict: max_length must be below the configured context (KV cache size)");
     std::vector<int32_t> out;
+    if (mode_ == ForwardMode::kEngine && batched_prefill_active() && (int)prompt_ids.size() <= max_length) {
+        // prompt in one batched pass (fills the KV cache, leaves the first generated token), then device-resident decode
+        out.resize(max_length);
+        const int n = (int)prompt_ids.size();
+        if (sllm_engine_prefill(engine_, prompt_ids.data(), n, 0) != 0) LOG(sllm_last_error());
+        if (sllm_engine_enqueue_steps(engine_, max_length - n) != 0) LOG(sllm_last_error());
+        if (sllm_engine_read_tokens(engine_, out.data(), max_length) != 0) LOG(sllm_last_error());
+        return out;
+    }
     if (mode_ == ForwardMode::kEngine) {   // whole loop on the device, one copy of the token list at the end
         out.resize(max_length);
         if (sllm_engine_greedy(engine_, prompt_ids.data(), (int32_t)prompt_ids.size(), max_length + 1, out.data()) != 0) LOG(sllm_last_error());

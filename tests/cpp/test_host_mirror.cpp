@@ -222,6 +222,41 @@ static void test_model(model::ForwardMode mode, base::DataType wdt, const char* 
     orc_destroy(o2);
 }
 
+// predict() with the prompt as one batched tensor-core pass: prompt echo exact, the generated tokens equal to the
+// token-by-token predict() of the same model (gain-1 weights: the bf16 operand rounding stays far below the logit margins)
+static void test_batched_prefill() {
+    syn_shape s{2048, 64, 512, 128, 1408, 320, 3, 8, 2, 1e-5f, 10000.f};
+    std::vector<float> blob((size_t)syn_blob_floats(&s));
+    syn_fill_blob(&s, 21, SYN_BF16, 64, blob.data(), 4);
+    for (int seg = 2; seg < 9; ++seg) {   // projections scaled to gain 1 (exact in bf16)
+        int64_t off, cnt, row; float mean, cc;
+        syn_segment(&s, seg, &off, &cnt, &row, &mean, &cc);
+        for (int64_t i = 0; i < cnt; ++i) blob[(size_t)(off + i)] *= 0.25f;
+    }
+    model::LlamaModelConfig c;
+    c.vocab_size = s.vocab; c.head_dim = s.head_dim; c.hidden_size = s.hidden; c.kv_hidden_size = s.kv_hidden;
+    c.intermediate_size = s.inter; c.max_length = s.max_len; c.num_hidden_layers = s.layers; c.num_attention_heads = s.heads;
+    c.num_key_value_heads = s.kv_heads; c.rms_norm_eps = s.eps; c.rope_theta = s.theta;
+    std::vector<int32_t> prompt(150);
+    for (size_t i = 0; i < prompt.size(); ++i) prompt[i] = (int32_t)(1 + (i * 37 + 11) % (s.vocab - 1));
+    std::vector<int32_t> got[2];
+    for (int batched = 0; batched < 2; ++batched) {
+        model::LlamaModel m("", "", CUDA);
+        m.set_config(c);
+        m.set_weights(blob.data(), blob.size());
+        m.set_storage(base::DataType::kBf16, base::DataType::kBf16);
+        m.set_batched_prefill(batched != 0);
+        m.init();
+        CHECK(m.batched_prefill_active() == (batched != 0), "batched prefill active = %d", (int)m.batched_prefill_active());
+        got[batched] = m.predict(prompt, 170);
+    }
+    CHECK(got[0].size() == 170 && got[1].size() == 170, "predict sizes %zu %zu", got[0].size(), got[1].size());
+    bool echo = true;
+    for (size_t i = 0; i + 1 < prompt.size(); ++i) echo = echo && got[1][i] == prompt[i + 1];
+    CHECK(echo, "batched prefill: prompt echo differs");
+    CHECK(got[0] == got[1], "batched prefill: generated tokens differ from the token-by-token prompt");
+}
+
 int main() {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("no CUDA device\n"); return 2; }
@@ -231,6 +266,7 @@ int main() {
     test_model(model::ForwardMode::kOpByOp, base::DataType::kBf16, "op-by-op bf16 weights");
     test_model(model::ForwardMode::kEngine, base::DataType::kFp32, "engine fp32");
     test_model(model::ForwardMode::kEngine, base::DataType::kBf16, "engine bf16 weights");
+    test_batched_prefill();
     std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "PASS", g_checks, g_fail);
     return g_fail ? 1 : 0;
 }
