@@ -132,6 +132,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
 
     const int pos = p.st->pos;
     const int token = min(max(p.st->token, 0), p.V - 1);
+    // attention splits actually used at this position: ~128 cache rows per split (every split costs the wo prologue two
+    // polling round trips in the merge, so 32 splits of 16 rows — what a tensor-parallel rank with 4 KV heads would get —
+    // are far slower than 5 splits of 128). Same value in every CTA of every rank.
+    const int nsplit = min(p.nsplit, max(1, (pos + 1 + 127) / 128));
     const unsigned ebase = (unsigned)p.st->pad[1] * (unsigned)(p.L + 2) + 1u;   // epoch of layer l = ebase + l
     uint2* const my_area = p.area[p.rank];
 
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             const unsigned ein = (ph.kind == PH_QKV) ? e - 1u : e;
             for (int c4 = tid; c4 < p.d / 4; c4 += kMegaThreads) {
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int r0 = 0; r0 < p.tp; r0 += 2) {          // ranks in batches of 2 (register budget); rank order kept
+                for (int r0 = 0; r0 < p.tp; r0 += 2) {          // ranks in batches of 2 (register budget: wider batches spill in the hot loop); rank order kept
                     float4 pr[2];
                     ll_recv4xN<2>(my_area + off + (int64_t)r0 * p.d + 4 * c4, p.d, min(2, p.tp - r0), ein, pr);
 #pragma unroll
@@ -224,25 +228,25 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             for (int c4 = tid; c4 < cols / 4; c4 += kMegaThreads) {
                 const int col = c4 * 4;
                 const int head = col / p.hd, j = col - head * p.hd;
-                const uint2* base = my_area + p.off_att + (int64_t)head * p.nsplit * rec;
+                const uint2* base = my_area + p.off_att + (int64_t)head * nsplit * rec;
                 constexpr int kNS = 2;                     // splits handled per batch of in-flight loads (register budget)
                 float M = -INFINITY, Ls = 0.f;
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 // pass 1: running max over all splits (the {m, l, pad, pad} group is four words)
-                for (int s0 = 0; s0 < p.nsplit; s0 += kNS) {
+                for (int s0 = 0; s0 < nsplit; s0 += kNS) {
                     float4 ml[kNS];
-                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + p.hd, rec, min(kNS, p.nsplit - s0), e, ml);
+                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + p.hd, rec, min(kNS, nsplit - s0), e, ml);
 #pragma unroll
-                    for (int i = 0; i < kNS; ++i) if (s0 + i < p.nsplit) M = fmaxf(M, ml[i].x);
+                    for (int i = 0; i < kNS; ++i) if (s0 + i < nsplit) M = fmaxf(M, ml[i].x);
                 }
-                for (int s0 = 0; s0 < p.nsplit; s0 += kNS) {
+                for (int s0 = 0; s0 < nsplit; s0 += kNS) {
                     float4 ml[kNS], ov[kNS];
-                    const int nn = min(kNS, p.nsplit - s0);
+                    const int nn = min(kNS, nsplit - s0);
                     ll_recv4xN<kNS>(base + (int64_t)s0 * rec + p.hd, rec, nn, e, ml);
                     ll_recv4xN<kNS>(base + (int64_t)s0 * rec + j, rec, nn, e, ov);
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) {
-                        if (s0 + i < p.nsplit) {
+                        if (s0 + i < nsplit) {
                             const float w = (ml[i].x == -INFINITY) ? 0.f : expf(ml[i].x - M);
                             Ls = fmaf(ml[i].y, w, Ls);
                             o.x = fmaf(ov[i].x, w, o.x); o.y = fmaf(ov[i].y, w, o.y); o.z = fmaf(ov[i].z, w, o.z); o.w = fmaf(ov[i].w, w, o.w);
@@ -304,15 +308,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             }
         }
 
-        if (ph.kind == PH_QKV && cta < p.KVH_loc * p.nsplit) {
+        if (ph.kind == PH_QKV && cta < p.KVH_loc * nsplit) {
             // K/V rows of this CTA's first attention item (all but the newest row were stored by EARLIER launches):
             // start their TMA now so they land while phase A streams its weights. (xs is idle: A reads resid_s.)
             __syncthreads();
             if (warp == 0 && lane == 0) {
                 fence_async_smem();
                 const int row_bytes = p.hd * KESZ;
-                const int npos = pos + 1, per = (npos + p.nsplit - 1) / p.nsplit;
-                const int kvh = cta / p.nsplit, split = cta - kvh * p.nsplit;
+                const int npos = pos + 1, per = (npos + nsplit - 1) / nsplit;
+                const int kvh = cta / nsplit, split = cta - kvh * nsplit;
                 const int t0 = split * per, t1 = min(npos, t0 + per);
                 const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;
                 for (int tile = 0; tile < 2; ++tile) {
@@ -527,8 +531,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             const int row_bytes = p.hd * KESZ;
             const int cpr = row_bytes / 16;
             const int npos = pos + 1;
-            const int per = (npos + p.nsplit - 1) / p.nsplit;
-            const int nitems = p.KVH_loc * p.nsplit;
+            const int per = (npos + nsplit - 1) / nsplit;
+            const int nitems = p.KVH_loc * nsplit;
             const float scale = 1.0f / sqrtf((float)p.hd);
             constexpr int kStripes = 16;
             const int pv_chunk = tid % cpr, pv_stripe = tid / cpr;
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
 
 #pragma unroll 1
             for (int item = cta; item < nitems; item += ncta) {
-                const int kvh = item / p.nsplit, split = item - kvh * p.nsplit;
+                const int kvh = item / nsplit, split = item - kvh * nsplit;
                 const int t0 = split * per, t1 = min(npos, t0 + per);
                 const int ntiles = (t1 > t0) ? (t1 - t0 + kAttTile - 1) / kAttTile : 0;
                 // q of this KV head's query heads: words written by phase A's epilogues (any CTA)
@@ -676,10 +680,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                     float o = 0.f;
                     for (int s = 0; s < kStripes; ++s) o += o_s[(size_t)s * G * p.hd + i];
                     const int gi = i / p.hd, j = i - gi * p.hd;
-                    ll_send(my_area + p.off_att + ((int64_t)(kvh * G + gi) * p.nsplit + split) * rec + j, o, e);
+                    ll_send(my_area + p.off_att + ((int64_t)(kvh * G + gi) * nsplit + split) * rec + j, o, e);
                 }
                 if (tid < G) {
-                    uint2* r = my_area + p.off_att + ((int64_t)(kvh * G + tid) * p.nsplit + split) * rec + p.hd;
+                    uint2* r = my_area + p.off_att + ((int64_t)(kvh * G + tid) * nsplit + split) * rec + p.hd;
                     ll_send(r, ml_s[2 * tid], e);
                     ll_send(r + 1, ml_s[2 * tid + 1], e);
                     ll_send(r + 2, 0.f, e);   // pad words: the merge reads the record tail as one group of four
