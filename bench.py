@@ -341,9 +341,18 @@ def run_ours(args):
     mode = eng.mode
     if mode.startswith("megakernel"):
         ach = step_bytes / (ms_total * 1e-3 / K) / 1e9
+        traffic = None   # DRAM bytes of one launch from the committed ncu --set full capture (same kernel, config and position range)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_mega_traffic.json")) as f:
+                tj = json.load(f)
+            if world == 1 and args.config == "llama2-7b" and args.wdtype == "bf16" and args.kvdtype == "bf16" and mode == "megakernel":
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": "mega_step_kernel (persistent: all layers' qkv|attention|wo|gate_up|down + classifier/argmax)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": step_bytes,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "bytes_per_launch": step_bytes,
                 "us_per_launch": 1e3 * ms_total / K, "peak_source": peak_src,
+                "traffic_source": "profiles/r01_mega_r1d_ncu_raw.md: dram__bytes_read.sum + dram__bytes_write.sum of one launch at position 520" if traffic else None,
                 "how": f"{K} launches = the timed region itself, CUDA events on the launching stream; B(p) per SURVEY.md 8d"}
     elif not args.unfused:
         eng.set_state(tok, min(pos, ms.max_len - 1))

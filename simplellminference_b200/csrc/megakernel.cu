@@ -75,6 +75,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    if (p.trace && threadIdx.x == 0) {   // which SM this CTA runs on (event 0, slot 7)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[((size_t)blockIdx.x * kTraceEvents) * 8 + 7] = smid;
+    }
     const int pos = p.st->pos;
     const int token = min(max(p.st->token, 0), p.V - 1);
     const unsigned bar_base = (unsigned)p.st->pad[0];

@@ -34,3 +34,21 @@ for ev in range(nev):
 for kind, rows in agg.items():
     keys = [k for k in rows[0] if k != "begin"]
     print(kind.ljust(8), " ".join(f"{k}={np.mean([r[k] for r in rows[1:] or rows]):7.2f}" for k in keys))
+
+# per-CTA streaming time of the big phases, layer by layer: is the spread systematic (same CTAs slow every time)?
+smid = t[:, 0, 7]
+import json as _json
+per = {}
+for kind, off in (("qkv", 0), ("gate_up", 3), ("down", 4)):
+    m = np.stack([(t[:, 5 * l + off, 3] - t[:, 5 * l + off, 1]).astype(np.float64) / 1e3 for l in range(1, a.layers)], 1)   # [cta][layer]
+    per[kind] = m
+    mean = m.mean(1)
+    cc = np.corrcoef(m.T)
+    print(f"{kind}: per-CTA mean stream us min {mean.min():.2f} max {mean.max():.2f} std {mean.std():.2f}; layer-to-layer corr of per-CTA times: {cc[np.triu_indices_from(cc, 1)].mean():.2f}")
+allm = np.concatenate([per[k] / per[k].mean() for k in per], 1).mean(1)
+order = np.argsort(allm)
+print("slowest CTAs (cta, smid, relative time):", [(int(c), int(smid[c]), round(float(allm[c]), 3)) for c in order[-10:]])
+print("fastest CTAs:", [(int(c), int(smid[c]), round(float(allm[c]), 3)) for c in order[:10]])
+print("relative time by smid parity / half:", {"smid<74": round(float(allm[smid < 74].mean()), 4), "smid>=74": round(float(allm[smid >= 74].mean()), 4),
+      "even": round(float(allm[smid % 2 == 0].mean()), 4), "odd": round(float(allm[smid % 2 == 1].mean()), 4)})
+np.save("gpurun_out/mega_rel_time.npy", np.stack([smid.astype(np.float64), allm], 1)) if os.path.isdir("gpurun_out") else None
