@@ -189,3 +189,33 @@ def test_prefill_rejected_where_unsupported():
         eng.prefill([1, 2, 3])
     assert np.array_equal(eng.greedy([1, 2, 3], 5)[:2], [2, 3])   # the token-by-token path still serves the prompt
     eng.close()
+
+
+def test_prefill_longer_than_one_block(port):
+    """Prompts longer than the 1024-row block of the workspace run as several blocks (the later ones attend to the cached rows
+    of the earlier ones); n = 1 is a degenerate block. Compared with the oracle on the gain-1 blob."""
+    ms = ModelShape(1024, 64, 256, 128, 512, 1300, 2, 4, 2)
+    n = 1100
+    ids = _prompt(n, ms.vocab, 3)
+    blob = _blob(port, ms, 8, 1)
+    om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
+    first = om.forward(int(ids[0]), 0)
+    for p in range(1, n - 1):
+        om.step(int(ids[p]), p)
+    want_l = om.forward(int(ids[n - 1]), n - 1)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, mega=True).load_blob(blob)
+    eng.prefill(ids[:1])
+    torch.cuda.synchronize()
+    got1 = eng.buffer("model_pred").cpu().numpy()
+    assert float(np.abs(got1 - first).max()) <= 3e-2 * max(1.0, float(np.abs(first).max()))
+    eng.prefill(ids)
+    torch.cuda.synchronize()
+    got = eng.buffer("model_pred").cpu().numpy()
+    err = float(np.abs(got - want_l).max())
+    assert err <= 3e-2 * max(1.0, float(np.abs(want_l).max())), err
+    assert int(np.argmax(got)) == int(np.argmax(want_l))
+    with pytest.raises(Exception):
+        eng.prefill(ids, start_pos=ms.max_len - 10)      # would overrun the KV cache
+    with pytest.raises(Exception):
+        eng.prefill([ms.vocab])                           # token outside the vocabulary
+    eng.close()
