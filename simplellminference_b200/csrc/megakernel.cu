@@ -673,7 +673,7 @@ MegaPlan mega_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_l
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaSmem SL = mega_smem_layout(hd, g, kesz);
     if (SL.total > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
-    if ((size_t)16 * g * hd * 4 > (size_t)2 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }
+    if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
     if ((size_t)std::max(d, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 2 || kv_loc % 2) { pl.why = "odd dims"; return pl; }
     pl.grid = sm_count();

@@ -715,7 +715,7 @@ MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaLLSmem SL = mega_ll_smem_layout(d, hd, g, kesz);
     if (SL.total + 1024 > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
-    if ((size_t)16 * g * hd * 4 > (size_t)2 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }
+    if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
     if ((size_t)std::max(q_loc, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 4 || kv_loc % 2 || I_loc % 4 || d % 4) { pl.why = "dims not multiples of 4"; return pl; }
     // every CTA must own >= 1 tile row of every weight phase (see the safety argument at the top of this file)

@@ -140,3 +140,24 @@ def test_medium_shape_tokens(port, mega):
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
     assert err <= logit_tol(want_l), err
     eng.close()
+
+
+@pytest.mark.parametrize("kvd", [F32, BF16])
+@pytest.mark.parametrize("mega_ll", [False, True])
+def test_gqa8_hd64_megakernel(port, kvd, mega_ll):
+    """TinyLlama's head geometry (8 query heads per KV head, head_dim 64): the cross-stripe attention buffer spans both K/V
+    stages. Must run in megakernel mode (it used to fall back) and match the oracle."""
+    ms = ModelShape(2048, 64, 512, 64, 1408, 200, 3, 8, 1)
+    blob = port.fill_blob(oracle_shape(ms), 5, BF16)
+    want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=(kvd == BF16)).greedy([1, 5, 9], 190)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=kvd, mega=True, mega_ll=mega_ll).load_synthetic(5)
+    assert eng.mode == ("megakernel(ll)" if mega_ll else "megakernel"), eng.mode
+    got = eng.greedy([1, 5, 9], 190)
+    err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
+    if kvd == F32:
+        assert np.array_equal(got, want), int(np.flatnonzero(got != want)[0])
+        assert err <= logit_tol(want_l), err
+    else:   # bf16 cache: a value on a rounding boundary may flip and move a low-margin token late in a long run
+        same = int(np.flatnonzero(got != want)[0]) if not np.array_equal(got, want) else len(want)
+        assert same >= 60, same
+    eng.close()
