@@ -1068,8 +1068,8 @@ int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32
         case 105: *ptr = e->wdown.w; *n = (int64_t)e->L * e->wdown.rows * e->wdown.cols; *dtype = e->cfg.w_dtype; break;
         case 200: {   // megakernel timeline: allocate on first request, stamps are written from the next step on
             SLLM_REQUIRE(e->mega, SLLM_ESTATE, "trace needs megakernel mode");
-            const size_t nb = (size_t)e->mega_plan_.grid * 512 * 8 * 8;
-            if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; }
+            const size_t nb = (size_t)(e->mega_ll ? e->ll_plan.grid : e->mega_plan_.grid) * 512 * 8 * 8;
+            if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; e->ll_params.trace = e->trace; }
             *ptr = e->trace; *n = (int64_t)(nb / 4); *dtype = SLLM_F32; break;
         }
         case 110: *ptr = e->emb.sc; *n = e->emb.sc ? (int64_t)e->V * e->d / e->cfg.group : 0; break;

@@ -70,6 +70,7 @@ struct MegaLLParams {
     int32_t tp, rank;
     uint2* area[8];            // area[r] = rank r's word area (area[rank] is local memory, the others CUDA-IPC mappings)
     int64_t off_wop, off_dnp, off_qv, off_kvn, off_att, off_swi, off_arg;   // word offsets inside an area
+    unsigned long long* trace; // optional [grid][512][8] %globaltimer stamps (nullptr = off)
 };
 struct MegaLLPlan {
     bool ok = false;

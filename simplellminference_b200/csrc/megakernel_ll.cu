@@ -106,6 +106,20 @@ __device__ __forceinline__ void ll_recv4xN(const uint2* p, int64_t stride, int n
     }
 }
 
+// optional per-CTA timeline, same slots as megakernel.cu (tools/mega_trace.py --ll): event = phase in step order (5 per layer:
+// qkv, attention, wo, gate_up, down; then the classifier), slots 0 start, 1 activation vector ready, 3 streaming done,
+// 4 results sent
+constexpr int kLLTraceEvents = 512;
+__device__ __forceinline__ unsigned long long ll_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define LL_STAMP(ev, slot)                                                                                  \
+    do {                                                                                                    \
+        if (p.trace && threadIdx.x == 0 && (ev) < kLLTraceEvents) p.trace[((size_t)blockIdx.x * kLLTraceEvents + (ev)) * 8 + (slot)] = ll_gtime(); \
+    } while (0)
+
 template <int WD, int KVD, int G>
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLParams p) {
     constexpr int E = WInfo<WD>::E;
@@ -183,6 +197,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
         const int nsc = max(0, min(ph.SC, ph.nchunks - c0));
         const int cols = ph.nchunks * E;
         const bool normed = (ph.kind == PH_QKV || ph.kind == PH_GATEUP || ph.kind == PH_CLS);
+        const int ev = wp + l + (ph.kind != PH_QKV && ph.kind != PH_CLS ? 1 : 0);
+        LL_STAMP(ev, 0);
 
         // ---- 1. build the activation vector (spinning on the {value, epoch} words it is made of) -------------
         float ss = 0.f;
@@ -225,34 +241,49 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
         } else if (ph.kind == PH_WO) {                                       // merge the attention splits
             xsrc = xs;
             const int rec = p.hd + kAttRecPad;
+            // step 1: one thread per (head, split) polls that record's {m, l} pair ONCE and turns it into a merge weight in shared
+            // memory (the partial-sum table is idle here); the columns of a head then share it — before, every thread polled all
+            // splits' {m, l} twice, twelve L2 round trips in a row per layer (trace: 12.5 us of wo prologue, 6.7 us now).
+            float* mw = part;                                  // [H_loc][nsplit]: merge weight exp(m - M), L_total
+            const int nrec = p.H_loc * nsplit;
+            for (int i = tid; i < nrec; i += kMegaThreads) {
+                const float2 ml = ll_recv2(my_area + p.off_att + (int64_t)i * rec + p.hd, e);
+                mw[2 * i] = ml.x;
+                mw[2 * i + 1] = ml.y;
+            }
+            __syncthreads();
+            for (int h = tid; h < p.H_loc; h += kMegaThreads) {
+                float M = -INFINITY, Ls = 0.f;
+                for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, mw[2 * (h * nsplit + sp)]);
+                for (int sp = 0; sp < nsplit; ++sp) {
+                    const float m = mw[2 * (h * nsplit + sp)];
+                    const float w = (m == -INFINITY) ? 0.f : expf(m - M);
+                    Ls = fmaf(mw[2 * (h * nsplit + sp) + 1], w, Ls);
+                    mw[2 * (h * nsplit + sp)] = w;
+                }
+                for (int sp = 0; sp < nsplit; ++sp) mw[2 * (h * nsplit + sp) + 1] = Ls;
+            }
+            __syncthreads();
+            // step 2: weighted sum of the splits' outputs, two splits (four 16-byte loads) in flight per polling round trip
+            // (four in flight, inline or out of line, pushes the kernel over its 128-register cap into the streaming loop: slower)
             for (int c4 = tid; c4 < cols / 4; c4 += kMegaThreads) {
                 const int col = c4 * 4;
                 const int head = col / p.hd, j = col - head * p.hd;
                 const uint2* base = my_area + p.off_att + (int64_t)head * nsplit * rec;
-                constexpr int kNS = 2;                     // splits handled per batch of in-flight loads (register budget)
-                float M = -INFINITY, Ls = 0.f;
+                constexpr int kNS = 2;
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                // pass 1: running max over all splits (the {m, l, pad, pad} group is four words)
                 for (int s0 = 0; s0 < nsplit; s0 += kNS) {
-                    float4 ml[kNS];
-                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + p.hd, rec, min(kNS, nsplit - s0), e, ml);
-#pragma unroll
-                    for (int i = 0; i < kNS; ++i) if (s0 + i < nsplit) M = fmaxf(M, ml[i].x);
-                }
-                for (int s0 = 0; s0 < nsplit; s0 += kNS) {
-                    float4 ml[kNS], ov[kNS];
-                    const int nn = min(kNS, nsplit - s0);
-                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + p.hd, rec, nn, e, ml);
-                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + j, rec, nn, e, ov);
+                    float4 ov[kNS];
+                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + j, rec, min(kNS, nsplit - s0), e, ov);
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) {
                         if (s0 + i < nsplit) {
-                            const float w = (ml[i].x == -INFINITY) ? 0.f : expf(ml[i].x - M);
-                            Ls = fmaf(ml[i].y, w, Ls);
+                            const float w = mw[2 * (head * nsplit + s0 + i)];
                             o.x = fmaf(ov[i].x, w, o.x); o.y = fmaf(ov[i].y, w, o.y); o.z = fmaf(ov[i].z, w, o.z); o.w = fmaf(ov[i].w, w, o.w);
                         }
                     }
                 }
+                const float Ls = mw[2 * head * nsplit + 1];
                 reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
             }
         } else {                                                              // down: sigmoid(gate)*up of this layer
@@ -333,6 +364,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             }
         }
 
+        LL_STAMP(ev, 1);
         // ---- 2. stream this CTA's tile rows through the rings, round by round ------------------------------
         int g0, g1;
         cta_tiles(ph, cta, ncta, g0, g1);
@@ -398,6 +430,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 }
             }
             __syncthreads();
+            if (rbase + kRoundUnits >= n) LL_STAMP(ev, 3);
             // ---- 3. finish the round's units: sum over K slices, fused epilogue, results leave as words ----------
             const int nround = min(kRoundUnits, n - rbase);
 #pragma unroll 1
@@ -517,7 +550,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             }
             break;
         }
+        LL_STAMP(ev, 4);
         if (ph.kind != PH_QKV) continue;
+        LL_STAMP(ev + 1, 0);
 
         // =============================== attention phase of layer l ======================================
         {
@@ -585,11 +620,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                     if (pos >= ts && pos < ts + rows && warp == 1) {
                         for (int c = lane; c < cpr; c += 32) {
                             float kf[KVEC], vf[KVEC];
+                            {   // KVEC consecutive words each of K and V: one polling round trip per matrix
+                                const uint2* kp = my_area + p.off_kvn + (int64_t)kvh * p.hd + c * KVEC;
+                                const uint2* vp = kp + p.kv_loc;
+                                float4 t4[KVEC / 4];
+                                ll_recv4xN<KVEC / 4>(kp, 4, KVEC / 4, e, t4);
 #pragma unroll
-                            for (int ee = 0; ee < KVEC; ee += 2) {
-                                const float2 a = ll_recv2(my_area + p.off_kvn + (int64_t)kvh * p.hd + c * KVEC + ee, e);
-                                const float2 b = ll_recv2(my_area + p.off_kvn + p.kv_loc + (int64_t)kvh * p.hd + c * KVEC + ee, e);
-                                kf[ee] = a.x; kf[ee + 1] = a.y; vf[ee] = b.x; vf[ee + 1] = b.y;
+                                for (int q4 = 0; q4 < KVEC / 4; ++q4) { kf[4 * q4] = t4[q4].x; kf[4 * q4 + 1] = t4[q4].y; kf[4 * q4 + 2] = t4[q4].z; kf[4 * q4 + 3] = t4[q4].w; }
+                                ll_recv4xN<KVEC / 4>(vp, 4, KVEC / 4, e, t4);
+#pragma unroll
+                                for (int q4 = 0; q4 < KVEC / 4; ++q4) { vf[4 * q4] = t4[q4].x; vf[4 * q4 + 1] = t4[q4].y; vf[4 * q4 + 2] = t4[q4].z; vf[4 * q4 + 3] = t4[q4].w; }
                             }
                             uint4 kw, vw;
                             if (KVD == SLLM_F32) {
@@ -693,6 +733,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             fence_async_smem();
             __syncthreads();   // o_s / xs region is reused by the next prologue
         }
+        LL_STAMP(ev + 1, 4);
     }
 }
 

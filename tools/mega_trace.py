@@ -4,16 +4,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from simplellminference_b200.config import PRESETS, BF16
 from simplellminference_b200.engine import Engine
-ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4); ap.add_argument("--pos", type=int, default=512)
+ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--ll", action="store_true")
 a = ap.parse_args()
 ms = dataclasses.replace(PRESETS["llama2-7b"], layers=a.layers)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True).load_synthetic(1)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True, mega_ll=a.ll).load_synthetic(1)
 eng.set_state(1, a.pos); eng.enqueue_steps(3); torch.cuda.synchronize()
 tr = eng.buffer(200); torch.cuda.synchronize()
 eng.enqueue_steps(1); torch.cuda.synchronize()
 t = tr.view(torch.int64).cpu().numpy().reshape(-1, 512, 8)
 nev = 5 * a.layers + 1
+if a.ll:   # no barriers in the word-based kernel: 'barrier' = time from results sent to the start of this CTA's next phase
+    for ev in range(nev - 1):
+        t[:, ev, 5] = t[:, ev + 1, 0]
 names = ["qkv", "att", "wo", "gate_up", "down"]
 t0 = t[:, 0, 0].min()
 print(f"grid={t.shape[0]} step total = {(t[:, nev-1, :5].max() - t0)/1e3:.1f} us")
