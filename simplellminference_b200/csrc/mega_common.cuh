@@ -13,19 +13,6 @@ constexpr int kCplMax = 4;        // max 16-byte chunks per lane per row slice (
 constexpr int kRoundUnits = 128;  // units per partial-table round
 constexpr int kAttTile = 64;
 constexpr unsigned kSpinLimit = 1u << 26;
-#ifndef SLLM_L2_AHEAD
-#define SLLM_L2_AHEAD 0
-#endif
-constexpr int kL2AheadBytes = SLLM_L2_AHEAD;  // per CTA: how much of the next phase is pulled into L2 during a phase gap
-#ifndef SLLM_L2_START
-#define SLLM_L2_START 0
-#endif
-#ifndef SLLM_L2_ATT
-#define SLLM_L2_ATT 0
-#endif
-// per CTA: bytes of a weight phase pulled into L2 right AFTER the grid barrier that precedes it (HBM is idle while every CTA
-// builds its activation vector), and bytes of the wo phase pulled in when the (latency-bound) attention phase starts
-constexpr int kL2StartBytes = SLLM_L2_START, kL2AttBytes = SLLM_L2_ATT;
 constexpr int kAttRecPad = 4;     // partial record = hd floats of O, then m, l (+2 pad: keeps float4 alignment)
 
 
@@ -82,10 +69,6 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
-}
-// HBM -> L2 only (no shared memory needed): extends the effective prefetch depth far beyond the smem rings
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

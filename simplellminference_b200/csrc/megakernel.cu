@@ -131,22 +131,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
         const bool normed = (ph.kind == PH_QKV || ph.kind == PH_GATEUP || ph.kind == PH_CLS);
         const int ev = wp + l + (ph.kind != PH_QKV && ph.kind != PH_CLS ? 1 : 0) + (ph.kind == PH_CLS ? 0 : 0);   // event slot: weight phases and attention phases in order
         MEGA_STAMP(ev, 0);
-        // what the rings do not hold yet of phase `which`, up to `bytes`, HBM -> L2 in 16 KB pieces (all threads)
-        auto l2_ahead = [&](int which, int bytes) {
-            const PhaseDesc nx = p.phases[which];
-            int h0, h1;
-            cta_tiles(nx, cta, ncta, h0, h1);
-            const size_t row_bytes = (size_t)nx.KS * nx.tile_bytes;
-            const size_t skip = (size_t)kSlots * (kMegaWarps / nx.KS) * row_bytes;
-            const size_t total = (size_t)(h1 - h0) * row_bytes;
-            const size_t want = total > skip ? min(total - skip, (size_t)bytes) : 0;
-            const uint8_t* base = nx.W + (size_t)h0 * row_bytes + skip;
-            const size_t piece = 16384;
-            for (size_t off = (size_t)tid * piece; off < want; off += (size_t)kMegaThreads * piece)
-                l2_prefetch(base + off, (uint32_t)min(piece, want - off));
-        };
-        if (kL2StartBytes > 0 && wp > 0 && ph.kind != PH_WO) l2_ahead(wp, kL2StartBytes);
-
         // norm weights of this lane's columns: constant data, requested before anything that has to wait
         float nwr[kCplMax][E];
         if (normed) {
@@ -340,22 +324,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                 }
             }
             if (rbase + kRoundUnits >= n) MEGA_STAMP(ev, 2);   // this thread-0 warp finished streaming
-            if (kL2AheadBytes > 0 && rbase + kRoundUnits >= n && wp + 1 < nwp) {
-                // This CTA has streamed its share of phase wp. While it finishes the epilogue and waits in the grid
-                // barrier HBM would idle once the rings are full: pull the next kL2AheadBytes of ITS share of the NEXT
-                // phase (one contiguous range in the tiled layout) into L2 now, in large pieces.
-                const PhaseDesc nx = p.phases[wp + 1];
-                int h0, h1;
-                cta_tiles(nx, cta, ncta, h0, h1);
-                const size_t row_bytes = (size_t)nx.KS * nx.tile_bytes;                    // one tile row
-                const size_t skip = (size_t)kSlots * (kMegaWarps / nx.KS) * row_bytes;      // what the rings already hold
-                const size_t total = (size_t)(h1 - h0) * row_bytes;
-                const size_t want = total > skip ? min(total - skip, (size_t)kL2AheadBytes) : 0;
-                const uint8_t* base = nx.W + (size_t)h0 * row_bytes + skip;
-                const size_t piece = 16384;
-                for (size_t off = (size_t)tid * piece; off < want; off += (size_t)kMegaThreads * piece)
-                    l2_prefetch(base + off, (uint32_t)min(piece, want - off));
-            }
             __syncthreads();
             if (rbase + kRoundUnits >= n) MEGA_STAMP(ev, 3);   // whole CTA finished streaming
             // ---- 3. finish the round's units: sum over K slices, fused epilogue -------------------------------
@@ -458,7 +426,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
         MEGA_STAMP(ev, 5);   // barrier passed
         if (ph.kind != PH_QKV) continue;
         MEGA_STAMP(ev + 1, 0);
-        if (kL2AttBytes > 0) l2_ahead(wp + 1, kL2AttBytes);
 
         // =============================== attention phase of layer l ======================================
         {
