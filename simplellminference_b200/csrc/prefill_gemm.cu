@@ -24,7 +24,7 @@
 
 namespace sllm {
 
-extern int g_tune_pf_bn, g_tune_pf_pair, g_tune_pf_pdl;
+extern int g_tune_pf_bn, g_tune_pf_pair, g_tune_pf_pdl, g_tune_pf_ksplit;
 constexpr int kPfBM = 128, kPfBK = 64, kPfThreads = 192;
 constexpr uint32_t kPfABytes = kPfBM * kPfBK * 2;
 // PAIR = true: two CTAs of a cluster (the two SMs of a TPC) work on ONE 256 x BN tile with tcgen05.mma.cta_group::2 — each
@@ -40,6 +40,8 @@ constexpr size_t kPfSmem = 1024 /*alignment slack*/ + kPfRingBytes + 512 /*barri
 
 struct PfDev {           // kernel-side view of PfGemmArgs
     int32_t T, N, m_tiles, n_tiles, BN;
+    int32_t ksplit;       // > 1 (residual epilogue only): a tile's k-blocks are cut into ksplit work units whose partial sums are ADDED to
+                          // the residual stream with red.global.add — fills the machine when a GEMM has fewer tiles than SM pairs
     int32_t nkb, kb_per_seg, seg_elems, R, tiled;
     int32_t epilogue;
     float* out; int32_t ld_out, n_valid;
@@ -167,6 +169,20 @@ __device__ __forceinline__ void epi_store(const PfDev& p, int t, int n0, const u
     } else {
         for (int i = 0; i < 32; ++i)
             if (n0 + i < p.n_valid) dst[i] = (add ? dst[i] : 0.f) + __uint_as_float(v[i]);
+    }
+}
+
+// split-K residual epilogue: out[t][n0..n0+31] += v, one vector reduction per 16 bytes (no return value, resolved in L2)
+__device__ __forceinline__ void epi_red_add(const PfDev& p, int t, int n0, const uint32_t* v) {
+    float* dst = p.out + (size_t)t * p.ld_out + n0;
+    if (n0 + 32 <= p.n_valid && (p.ld_out & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                         "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3])) : "memory");
+    } else {
+        for (int i = 0; i < 32; ++i)
+            if (n0 + i < p.n_valid) atomicAdd(dst + i, __uint_as_float(v[i]));
     }
 }
 
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
     if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int ntiles = p.m_tiles * p.n_tiles;
+    const int nunits = p.m_tiles * p.n_tiles * p.ksplit;
     // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (A, the residual
     // stream) are visible after the wait. The next kernel may start ITS set-up as soon as every CTA here is past this point.
     pdl_wait();
@@ -327,11 +343,13 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
         if (lane == 0) {   // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = worker; tile < ntiles; tile += nworkers) {
+            for (int unit = worker; unit < nunits; unit += nworkers) {
+                const int tile = unit / p.ksplit, part = unit - tile * p.ksplit;
+                const int kb0 = (p.nkb * part) / p.ksplit, kb1 = (p.nkb * (part + 1)) / p.ksplit;
                 const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;   // consecutive workers share the weight tile (L2)
                 const int row0 = m_tile * BM + (int)rank * kPfBM;                  // this CTA's 128 rows of A
                 const int n0 = n_tile * BN + (int)rank * b_rows;                   // this CTA's rows of W
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mb_wait(empty + stage, phase ^ 1);
                     const int ks = kb / p.kb_per_seg, kk = kb - ks * p.kb_per_seg;
                     uint8_t* a_dst = sA + (size_t)stage * kPfABytes;
@@ -358,19 +376,21 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
             const uint32_t idesc = umma_idesc_bf16(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = worker; tile < ntiles; tile += nworkers) {
+            for (int unit = worker; unit < nunits; unit += nworkers) {
+                const int part = unit % p.ksplit;
+                const int kb0 = (p.nkb * part) / p.ksplit, kb1 = (p.nkb * (part + 1)) / p.ksplit;
                 mb_wait(tempty + acc, acc_phase ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mb_wait(full + stage, phase);
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(sA + (size_t)stage * kPfABytes);
                     const uint64_t bd = umma_desc_sw128(sB + (size_t)stage * b_bytes);
 #pragma unroll
                     for (int k = 0; k < kPfBK / 16; ++k) {   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
-                        if (PAIR) tc_mma_bf16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        else tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if (PAIR) tc_mma_bf16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+                        else tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
                     }
                     if (PAIR) tc_commit_pair(empty + stage); else tc_commit(empty + stage);   // stage reusable once these MMAs have read it
                     if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -385,7 +405,8 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         const uint32_t tempty_leader[2] = {PAIR ? mapa_u32(tempty, 0) : 0u, PAIR ? mapa_u32(tempty + 1, 0) : 0u};
-        for (int tile = worker; tile < ntiles; tile += nworkers) {
+        for (int unit = worker; unit < nunits; unit += nworkers) {
+            const int tile = unit / p.ksplit;
             const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
             const int t = m_tile * BM + (int)rank * kPfBM + row;
             mb_wait(tfull + acc, acc_phase);
@@ -398,6 +419,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
                 if (t < p.T && n0 < p.N) {
                     if (p.epilogue == PF_EPI_QKV) epi_qkv(p, t, n0, v);
                     else if (p.epilogue == PF_EPI_GATEUP) epi_gateup(p, t, n0, v);
+                    else if (p.ksplit > 1) epi_red_add(p, t, n0, v);
                     else epi_store(p, t, n0, v, p.epilogue == PF_EPI_RESID);
                 }
             }
@@ -461,7 +483,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const PfDev& p
         SLLM_CUDA(cudaFuncSetAttribute(pf_gemm_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem));
         configured = true;
     }
-    const int workers = std::min(PAIR ? sm_count() / 2 : sm_count(), p.m_tiles * p.n_tiles);
+    const int workers = std::min(PAIR ? sm_count() / 2 : sm_count(), p.m_tiles * p.n_tiles * p.ksplit);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
     cfg.blockDim = dim3(kPfThreads);
@@ -501,18 +523,28 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
         p.kb_per_seg = (a.K + kPfBK - 1) / kPfBK;
         p.nkb = p.kb_per_seg;
     }
-    // N extent of a tile: any multiple of 32 up to 256. A tile costs ~BN tensor-core time (plus a fixed per-tile part, here 32
-    // columns' worth: pipeline fill + epilogue tail); the step takes ceil(tiles / workers) waves of it. Pick the cheapest.
+    // N extent of a tile (a multiple of 32 up to 256) and, for the residual epilogue, a split of K: a work unit costs about
+    // k-blocks x operand bytes per k-block (the kernel is bound by what an SM can ingest) plus the epilogue of its tile, and the
+    // GEMM takes ceil(units / workers) waves of it. Pick the cheapest combination.
     int bn = a.bn ? a.bn : g_tune_pf_bn;
+    int ksplit = 1;
     if (bn < 32 || bn > 256 || bn % 32) {
         const int workers = pair ? sm_count() / 2 : sm_count();
+        const int max_split = (a.epilogue == PF_EPI_RESID && g_tune_pf_ksplit != 0) ? (g_tune_pf_ksplit > 0 ? g_tune_pf_ksplit : 4) : 1;
         double best = 1e30;
         for (int b = 256; b >= 64; b -= 32) {
-            const long tiles = (long)p.m_tiles * ((a.N + b - 1) / b);
-            const double c = (double)((tiles + workers - 1) / workers) * (b + 32);
-            if (c < best - 1e-9) { best = c; bn = b; }
+            for (int sp = 1; sp <= max_split; ++sp) {
+                if (sp > 1 && p.nkb / sp < 8) break;   // keep at least 8 k-blocks per work unit
+                const long units = (long)p.m_tiles * ((a.N + b - 1) / b) * sp;
+                const double unit_cost = (double)((p.nkb + sp - 1) / sp) * (kPfBM + (pair ? b / 2 : b)) + 10.0 * b;
+                const double c = (double)((units + workers - 1) / workers) * unit_cost;
+                if (c < best - 1e-9) { best = c; bn = b; ksplit = sp; }
+            }
         }
+    } else if (a.epilogue == PF_EPI_RESID && g_tune_pf_ksplit > 0 && p.nkb / g_tune_pf_ksplit >= 1) {
+        ksplit = g_tune_pf_ksplit;
     }
+    p.ksplit = ksplit;
     p.BN = bn;
     p.n_tiles = (a.N + bn - 1) / bn;
     p.out = a.out; p.ld_out = a.ld_out; p.n_valid = a.n_valid;

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--bn", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--ksplit", type=int, default=-1)
     ap.add_argument("--pair", type=int, default=-1, help="1/0 force/forbid the two-SM (cta_group::2) GEMM, -1 heuristic")
     a = ap.parse_args()
     ms = PRESETS[a.config]
@@ -41,6 +42,7 @@ def main():
         _lib.load().sllm_tune(1, a.bn)
     _lib.load().sllm_tune(2, a.pair)
     _lib.load().sllm_tune(3, a.pdl)
+    _lib.load().sllm_tune(4, a.ksplit)
     eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True).load_synthetic(1234)
     rng = np.random.default_rng(20260101)
     ids = rng.integers(1, ms.vocab, size=a.tokens, dtype=np.int32)
