@@ -579,6 +579,7 @@ static int mega_stage_end(sllm_engine* e) {
         const size_t tiled = mega_matrix_bytes((int)m->rows, (int)m->cols, m->kind, e->cfg.w_dtype);
         for (int64_t l = 0; l < m->layers && rc == SLLM_OK; ++l)
             rc = mega_repack(reinterpret_cast<uint8_t*>(m->rm) + wbytes(e->cfg.w_dtype, l * m->rows * m->cols),
+                             m->sc ? m->sc + l * m->rows * m->cols / e->cfg.group : nullptr,
                              reinterpret_cast<uint8_t*>(m->w) + (size_t)l * tiled, (int)m->rows, (int)m->cols, m->kind, e->cfg.w_dtype, e->hd,
                              e->q_loc, e->kv_loc, e->I_loc, e->stream);
     }
@@ -693,7 +694,7 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
             e->mega_ll = e->mega = e->ll_plan.ok;
         }
         if (!e->mega && tp == 1) {
-            e->mega_plan_ = mega_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->H_loc, e->KVH_loc, e->S);
+            e->mega_plan_ = mega_plan(cfg->w_dtype, e->cfg.group, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->H_loc, e->KVH_loc, e->S);
             e->mega = e->mega_plan_.ok;
         }
         if (e->mega) e->p2p_mode = false;   // the megakernel carries its own in-kernel all-reduce

@@ -142,6 +142,11 @@ __device__ __forceinline__ float reg_dot(const uint4 w, const float* x, float ac
     if (WD == SLLM_F32) {
         acc = fmaf(__uint_as_float(w.x), x[0], acc); acc = fmaf(__uint_as_float(w.y), x[1], acc);
         acc = fmaf(__uint_as_float(w.z), x[2], acc); acc = fmaf(__uint_as_float(w.w), x[3], acc);
+    } else if (WD == SLLM_INT8) {   // unscaled: the caller multiplies by the chunk's group scale
+        acc = word_dot_s8(w.x, make_float4(x[0], x[1], x[2], x[3]), acc);
+        acc = word_dot_s8(w.y, make_float4(x[4], x[5], x[6], x[7]), acc);
+        acc = word_dot_s8(w.z, make_float4(x[8], x[9], x[10], x[11]), acc);
+        acc = word_dot_s8(w.w, make_float4(x[12], x[13], x[14], x[15]), acc);
     } else {
         acc = fmaf(bf16_lo(w.x), x[0], acc); acc = fmaf(bf16_hi(w.x), x[1], acc);
         acc = fmaf(bf16_lo(w.y), x[2], acc); acc = fmaf(bf16_hi(w.y), x[3], acc);

@@ -55,6 +55,7 @@ struct ProdState {
 template <int WD, int KVD, int G>
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaParams p) {
     constexpr int E = WInfo<WD>::E;                 // weights per 16-byte chunk
+    constexpr int CPL = (WD == SLLM_INT8) ? 2 : kCplMax;   // max chunks per lane per row slice (x of a lane: CPL * E = 32 registers)
     constexpr int KESZ = MKv<KVD>::ESZ, KVEC = MKv<KVD>::VEC;
     extern __shared__ __align__(128) uint8_t mega_smem[];
     uint8_t* const smem = mega_smem;
@@ -132,11 +133,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
         const int ev = wp + l + (ph.kind != PH_QKV && ph.kind != PH_CLS ? 1 : 0) + (ph.kind == PH_CLS ? 0 : 0);   // event slot: weight phases and attention phases in order
         MEGA_STAMP(ev, 0);
         // norm weights of this lane's columns: constant data, requested before anything that has to wait
-        float nwr[kCplMax][E];
+        float nwr[CPL][E];
         if (normed) {
             const float* nw = p.norms + (size_t)(ph.kind == PH_QKV ? 2 * l : ph.kind == PH_GATEUP ? 2 * l + 1 : 2 * p.L) * p.d;
 #pragma unroll
-            for (int i = 0; i < kCplMax; ++i) {
+            for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i;
 #pragma unroll
                 for (int e4 = 0; e4 < E; e4 += 4) {
@@ -155,11 +156,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             for (int c = tid; c < ph.nchunks; c += kMegaThreads) {
                 const int eks = c / em.SC, ecc = c - eks * em.SC;
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(trow + (size_t)eks * em.tile_bytes + (size_t)ecc * 16));
-                float f[8];
+                float f[E];
                 if (WD == SLLM_F32) {
                     f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y); f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
-                } else {
+                } else if (WD == SLLM_BF16) {
                     kv_unpack<SLLM_BF16>(raw, f);
+                } else {   // int8: dequantised value = q * group scale (the scales sit behind the tile's weights)
+                    const uint8_t* tile = p.emb + ((size_t)(token / em.R) * em.KS + eks) * em.tile_bytes;
+                    const float sc = __ldg(reinterpret_cast<const float*>(tile + (size_t)em.R * em.SC * 16 + (size_t)(token % em.R) * em.srow) + (ecc >> 2));
+                    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t wf = w4[k] ^ 0x80808080u;
+                        f[4 * k] = s8f<0>(wf) * sc; f[4 * k + 1] = s8f<1>(wf) * sc; f[4 * k + 2] = s8f<2>(wf) * sc; f[4 * k + 3] = s8f<3>(wf) * sc;
+                    }
                 }
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
@@ -208,9 +218,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             __syncthreads();
         }
         // ---- this lane's columns -> registers (chunk c = c0 + lane + 32 i  <->  columns c*E .. c*E+E)
-        float xr[kCplMax][E];
+        float xr[CPL][E];
 #pragma unroll
-        for (int i = 0; i < kCplMax; ++i) {
+        for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
 #pragma unroll
             for (int e = 0; e < E; ++e) xr[i][e] = 0.f;
@@ -276,9 +286,27 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                     mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
                     const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (upp == 2) {
+                    if (WD == SLLM_INT8) {
+                        // 16 int8 weights per chunk, exact int8 -> fp32 by byte permute (gemv_core.cuh s8f); the group scale of
+                        // the chunk (one fp32 per 4 chunks, stored behind the tile's weights) multiplies the chunk's partial sum
+                        const uint8_t* sc_base = sp - lane * 16 + (size_t)ph.R * sbytes;
 #pragma unroll
-                        for (int i = 0; i < kCplMax; ++i) {
+                        for (int i = 0; i < CPL; ++i) {
+                            const int c = lane + 32 * i;
+                            if (i < cpl && c < nsc) {
+                                const uint8_t* q = sp + i * 512;
+                                const float* scp = reinterpret_cast<const float*>(sc_base) + (c >> 2);
+                                a0 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], 0.f), scp[0], a0);
+                                a1 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + sbytes), xr[i], 0.f), scp[ph.srow >> 2], a1);
+                                if (upp == 2) {
+                                    a2 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 2 * sbytes), xr[i], 0.f), scp[2 * (ph.srow >> 2)], a2);
+                                    a3 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 3 * sbytes), xr[i], 0.f), scp[3 * (ph.srow >> 2)], a3);
+                                }
+                            }
+                        }
+                    } else if (upp == 2) {
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
                             if (i < cpl && lane + 32 * i < nsc) {
                                 const uint8_t* q = sp + i * 512;
                                 a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
@@ -289,7 +317,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < kCplMax; ++i) {
+                        for (int i = 0; i < CPL; ++i) {
                             if (i < cpl && lane + 32 * i < nsc) {
                                 const uint8_t* q = sp + i * 512;
                                 a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
@@ -591,15 +619,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
 // ------------------------------------------------------------------------------------------- host ----
 TileGeom mega_tile_geom(int rows_phys, int cols, int w_dtype) {
     TileGeom g;
-    const int E = w_dtype == SLLM_F32 ? 4 : 8;
+    const int E = w_dtype == SLLM_F32 ? 4 : w_dtype == SLLM_BF16 ? 8 : 16;
     g.nchunks = cols / E;
     int KS = 1;
     while (KS < 16 && (g.nchunks + KS - 1) / KS * 16 > 1024) KS *= 2;
     g.KS = KS;
     g.SC = (g.nchunks + KS - 1) / KS;
-    g.R = (g.SC * 16 * 4 <= kSlotBytes) ? 4 : 2;
+    g.srow = 0;
+    if (w_dtype == SLLM_INT8) {   // a quantisation group = 64 weights = 4 chunks must not straddle K slices; SC/4 scales per row
+        g.SC = (g.SC + 3) / 4 * 4;
+        g.srow = (g.SC + 15) / 16 * 16;
+    }
+    g.R = ((g.SC * 16 + g.srow) * 4 <= kSlotBytes) ? 4 : 2;
     g.ntr = (rows_phys + g.R - 1) / g.R;
-    g.tile_bytes = g.R * g.SC * 16;
+    g.tile_bytes = g.R * (g.SC * 16 + g.srow);
     g.bytes = (size_t)g.ntr * g.KS * g.tile_bytes;
     return g;
 }
@@ -621,18 +654,21 @@ static void fill_desc(PhaseDesc& ds, const void* W, int rows, int cols, int kind
     ds.R = g.R;
     ds.ntr = g.ntr;
     ds.tile_bytes = g.tile_bytes;
+    ds.srow = g.srow;
 }
 
 // can the megakernel run this shape? (everything else keeps using the per-kernel fused path)
-MegaPlan mega_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len) {
+MegaPlan mega_plan(int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len) {
     MegaPlan pl;
-    if (w_dtype == SLLM_INT8) { pl.why = "int8 weights"; return pl; }
-    const int E = w_dtype == SLLM_F32 ? 4 : 8;
+    if (w_dtype == SLLM_INT8 && group != 64) { pl.why = "int8 group size other than 64"; return pl; }
+    const int E = w_dtype == SLLM_F32 ? 4 : w_dtype == SLLM_BF16 ? 8 : 16;
     for (int cols : {d, q_loc, I_loc}) {
-        const int nch = cols / E;
-        const int SC = (nch + 15) / 16;
-        if (cols % E) { pl.why = "row length not a multiple of 16 bytes"; return pl; }
-        if (SC * 16 * 2 > kSlotBytes || SC > 32 * kCplMax) { pl.why = "rows longer than 32 KB"; return pl; }
+        if (cols % E || (w_dtype == SLLM_INT8 && cols % 64)) { pl.why = "row length not a multiple of 16 bytes / of the int8 group"; return pl; }
+        const TileGeom tg = mega_tile_geom(2, cols, w_dtype);
+        if (tg.KS * tg.SC < tg.nchunks || (tg.SC * 16 + tg.srow) * 2 > kSlotBytes || tg.SC > 32 * (w_dtype == SLLM_INT8 ? 2 : kCplMax)) {
+            pl.why = "rows longer than 32 KB";
+            return pl;
+        }
     }
     const int g = H_loc / KVH_loc;
     if (g > 8 || hd % 16 || hd > 256) { pl.why = "head shape"; return pl; }
@@ -697,8 +733,58 @@ __global__ void repack_kernel(const uint4* __restrict__ src, uint4* __restrict__
     }
 }
 
-int mega_repack(const void* src, void* dst, int rows, int cols, int kind, int w_dtype, int hd, int q_loc, int kv_loc, int I_loc, cudaStream_t st) {
+// int8: a tile = R rows of SC 16-byte chunks, then R rows of srow bytes of group scales (scale j of a row = group ks*SC/4 + j)
+__global__ void repack_int8_kernel(const uint4* __restrict__ src, const float* __restrict__ scales, uint4* __restrict__ dst, int rows, int nchunks,
+                                   int kind, int KS, int SC, int R, int srow, int ntr, int hd, int q_loc, int kv_loc, int I_loc) {
+    const int wu = R * SC, su = R * (srow / 16), tu = wu + su;   // 16-byte units per tile: weights, scales
+    const int64_t total = (int64_t)ntr * KS * tu;
+    const int ngroups = nchunks / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int unit = (int)(i % tu);
+        const int ks = (int)((i / tu) % KS);
+        const int g = (int)(i / ((int64_t)tu * KS));
+        const bool is_scale = unit >= wu;
+        const int rr = is_scale ? (unit - wu) / (srow / 16) : unit / SC;
+        const int cc = is_scale ? (unit - wu) % (srow / 16) : unit % SC;
+        const int pr = g * R + rr;
+        const int u = pr >> 1, m = pr & 1;
+        int r0, r1;
+        if (kind == PH_QKV) {
+            const int half = hd >> 1, rope_units = (q_loc + kv_loc) >> 1;
+            if (u < rope_units) { const int head = u / half; r0 = head * hd + (u - head * half); r1 = r0 + half; }
+            else { r0 = q_loc + kv_loc + 2 * (u - rope_units); r1 = r0 + 1; }
+        } else if (kind == PH_GATEUP) { r0 = u; r1 = I_loc + u; }
+        else { r0 = 2 * u; r1 = r0 + 1; }
+        const int row = m ? r1 : r0;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (!is_scale) {
+            const int c = ks * SC + cc;
+            if (row < rows && c < nchunks) v = src[(int64_t)row * nchunks + c];
+        } else if (row < rows) {
+            float f[4];
+            for (int k = 0; k < 4; ++k) {
+                const int gi = ks * (SC / 4) + cc * 4 + k;
+                f[k] = (cc * 4 + k < SC / 4 && gi < ngroups) ? scales[(int64_t)row * ngroups + gi] : 0.f;
+            }
+            v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+        }
+        dst[i] = v;
+    }
+}
+
+int mega_repack(const void* src, const float* scales, void* dst, int rows, int cols, int kind, int w_dtype, int hd, int q_loc, int kv_loc, int I_loc,
+                cudaStream_t st) {
     const TileGeom g = mega_tile_geom(phys_rows(rows, kind), cols, w_dtype);
+    if (w_dtype == SLLM_INT8) {
+        SLLM_REQUIRE(scales, SLLM_EINVAL, "mega_repack: int8 weights without scales");
+        const int64_t total = (int64_t)g.ntr * g.KS * (g.tile_bytes / 16);
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+        repack_int8_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), scales, reinterpret_cast<uint4*>(dst), rows, g.nchunks, kind,
+                                                   g.KS, g.SC, g.R, g.srow, g.ntr, hd, q_loc, kv_loc, I_loc);
+        g_launches++;
+        SLLM_LAUNCH_CHECK();
+        return SLLM_OK;
+    }
     const int64_t total = (int64_t)g.ntr * g.KS * g.R * g.SC;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
     repack_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), rows, g.nchunks, kind, g.KS, g.SC,
@@ -736,6 +822,10 @@ int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t 
         if (p.w_dtype == SLLM_F32) {                                                                      \
             return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_F32, SLLM_F32, GG>(p, grid, smem, st)      \
                                           : mega_launch_t<SLLM_F32, SLLM_BF16, GG>(p, grid, smem, st);    \
+        }                                                                                                 \
+        if (p.w_dtype == SLLM_INT8) {                                                                     \
+            return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_INT8, SLLM_F32, GG>(p, grid, smem, st)     \
+                                          : mega_launch_t<SLLM_INT8, SLLM_BF16, GG>(p, grid, smem, st);   \
         }                                                                                                 \
         return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_BF16, SLLM_F32, GG>(p, grid, smem, st)         \
                                       : mega_launch_t<SLLM_BF16, SLLM_BF16, GG>(p, grid, smem, st);

@@ -21,11 +21,12 @@ struct PhaseDesc {       // one weight phase, built on the host
     int32_t SC;          // chunks per slice
     int32_t R;           // physical rows per tile (4 or 2)
     int32_t ntr;         // tile rows = ceil(2*nunits / R)
-    int32_t tile_bytes;  // R * SC * 16
+    int32_t tile_bytes;  // R * (SC * 16 + srow)
+    int32_t srow;        // int8 only: bytes of one row's group scales inside a tile (SC/4 fp32 scales padded to 16 bytes), else 0
 };
 
 // geometry of a [rows][cols] matrix in the tiled layout
-struct TileGeom { int nchunks, KS, SC, R, ntr, tile_bytes; size_t bytes; };
+struct TileGeom { int nchunks, KS, SC, R, ntr, tile_bytes, srow; size_t bytes; };
 TileGeom mega_tile_geom(int rows_phys, int cols, int w_dtype);
 // bytes of one [rows][cols] matrix of phase kind `kind` in the tiled layout
 size_t mega_matrix_bytes(int rows, int cols, int kind, int w_dtype);
@@ -93,12 +94,13 @@ struct MegaPlan {
     const char* why = "";
 };
 
-MegaPlan mega_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len);
+MegaPlan mega_plan(int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len);
 void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, const void* wo, const void* wug, const void* wdown,
                       const void* cls, int d, int q_loc, int kv_loc, int I_loc, int V_loc);
 // row-major [rows][cols] (storage dtype) -> tiled layout in unit order. kind: PH_* (row pairing rule).
-int mega_repack(const void* src_rowmajor, void* dst_tiled, int rows, int cols, int kind, int w_dtype, int hd, int q_loc, int kv_loc,
-                int I_loc, cudaStream_t st);
+// scales_rowmajor: int8 only, fp32 [rows][cols/64] (the tiled layout carries each tile's scales behind its weights)
+int mega_repack(const void* src_rowmajor, const float* scales_rowmajor, void* dst_tiled, int rows, int cols, int kind, int w_dtype, int hd,
+                int q_loc, int kv_loc, int I_loc, cudaStream_t st);
 enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4 };
 int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st);
 

@@ -43,8 +43,9 @@ def test_golden_models(golden_models, name, mode):
     kw = dict(mega=dict(mega=True), mega_ll=dict(mega=True, mega_ll=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
     if mode.startswith("mega"):
-        want_mode = "fused+graph" if wd == INT8 else ("megakernel" if mode == "mega" else "megakernel(ll)")
-        assert eng.mode == want_mode, eng.mode   # int8 falls back, loudly visible
+        # int8 group-64 tiles are streamed by the grid-barrier megakernel only: asking for the word-based one falls back to it, visibly
+        want_mode = "megakernel" if (mode == "mega" or wd == INT8) else "megakernel(ll)"
+        assert eng.mode == want_mode, eng.mode
     toks = eng.greedy(prompt, n_total)
     want = golden_models[name + "/tokens"]
     assert np.array_equal(toks, want), (np.flatnonzero(toks != want)[:5], toks[:8], want[:8])
@@ -161,3 +162,20 @@ def test_gqa8_hd64_megakernel(port, kvd, mega_ll):
         same = int(np.flatnonzero(got != want)[0]) if not np.array_equal(got, want) else len(want)
         assert same >= 60, same
     eng.close()
+
+
+def test_int8_megakernel_shapes(port):
+    """int8 group-64 weights in the persistent megakernel on shapes that exercise the tile geometry: K slices whose chunk count
+    had to be rounded up to a whole quantisation group (inter = 1408 -> 88 chunks over 2 slices), 2- and 4-row tiles, GQA."""
+    for ms, seed in ((ModelShape(2048, 64, 512, 128, 1408, 96, 3, 8, 2), 3), (ModelShape(1024, 64, 1024, 256, 2816, 80, 2, 16, 4), 4)):
+        blob = port.fill_blob(oracle_shape(ms), seed, INT8, 64)
+        want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1).greedy([1, 2, 3, 4], 70)
+        eng = Engine(ms, w_dtype=INT8, kv_dtype=F32, group=64, mega=True).load_synthetic(seed)
+        assert eng.mode == "megakernel", eng.mode
+        got = eng.greedy([1, 2, 3, 4], 70)
+        assert np.array_equal(got, want), (int(np.flatnonzero(got != want)[0]), got[:8], want[:8])
+        err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
+        assert err <= logit_tol(want_l), err
+        ref = Engine(ms, w_dtype=INT8, kv_dtype=F32, group=64, mega=False).load_synthetic(seed)   # per-kernel int8 path: same tokens
+        assert np.array_equal(ref.greedy([1, 2, 3, 4], 70), want)
+        eng.close(); ref.close()
