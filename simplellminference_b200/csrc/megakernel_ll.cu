@@ -36,12 +36,14 @@ __host__ __device__ inline MegaLLSmem mega_ll_smem_layout(int d, int hd, int g, 
     L.bars = off; off += 512;
     L.red = off; off += 256;
     L.part = off; off += (size_t)kRoundUnits * 2 * kMegaWarps * 4;
+    // the attention phase's q / probabilities / bookkeeping live IN the partial-sum table (16 KB), which only the weight phases
+    // use: with the replicated residual stream (d floats) there is no room for both next to the rings and the K/V stages
+    L.att_q = L.part;
+    L.att_p = L.att_q + (size_t)g * hd * 4;
+    L.att_misc = L.att_p + (size_t)g * kAttTile * 4;
     off = (off + 127) & ~(size_t)127;
     L.ring = off; off += (size_t)kMegaWarps * kSlots * kSlotBytes;
     L.resid = off; off += (size_t)d * 4;
-    L.att_q = off; off += (size_t)g * hd * 4;
-    L.att_p = off; off += (size_t)g * kAttTile * 4;
-    L.att_misc = off; off += 256;
     off = (off + 127) & ~(size_t)127;
     L.kv_stride = hd * kv_esz;
     L.att_k = off; off += (size_t)2 * kAttTile * L.kv_stride;
@@ -756,6 +758,7 @@ MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaLLSmem SL = mega_ll_smem_layout(d, hd, g, kesz);
     if (SL.total + 1024 > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
+    if ((size_t)g * hd * 4 + (size_t)g * kAttTile * 4 + 256 > (size_t)kRoundUnits * 2 * kMegaWarps * 4) { pl.why = "attention scratch (q/p)"; return pl; }
     if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
     if ((size_t)std::max(q_loc, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 4 || kv_loc % 2 || I_loc % 4 || d % 4) { pl.why = "dims not multiples of 4"; return pl; }

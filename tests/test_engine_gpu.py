@@ -179,3 +179,52 @@ def test_int8_megakernel_shapes(port):
         ref = Engine(ms, w_dtype=INT8, kv_dtype=F32, group=64, mega=False).load_synthetic(seed)   # per-kernel int8 path: same tokens
         assert np.array_equal(ref.greedy([1, 2, 3, 4], 70), want)
         eng.close(); ref.close()
+
+
+@pytest.mark.parametrize("wd,mega", [(BF16, True), (INT8, True), (BF16, False)])
+def test_full_width_llama2_7b_two_layers(port, wd, mega):
+    """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers: the tile geometry the bench runs on
+    (K = 11008 -> 16 K slices of 86 chunks, 2-row tiles; int8: 88 chunks) checked against the oracle, which the small shapes cannot
+    do. bf16 KV cache (fp32 K/V tiles of 128-wide heads do not fit the megakernel), so the oracle rounds its cache rows too."""
+    import dataclasses
+    ms = dataclasses.replace(PRESETS["llama2-7b"], layers=2, max_len=64)
+    blob = port.fill_blob(oracle_shape(ms), 9, wd, 64, threads=os.cpu_count() or 1)
+    om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
+    want, want_l = om.greedy([1, 2, 3], 14)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=mega).load_synthetic(9)
+    assert eng.mode == ("megakernel" if mega else "fused+graph"), eng.mode
+    got = eng.greedy([1, 2, 3], 14)
+    assert np.array_equal(got, want), (got, want)
+    err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
+    assert err <= 5e-3 * max(1.0, float(np.abs(want_l).max())), err
+    if wd == BF16 and mega:   # the same prompt as ONE batched tensor-core pass: K = 11008 with its ragged k-block tail per K slice
+        ids = np.concatenate([[1, 2, 3], want[:9]]).astype(np.int32)
+        om2 = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
+        for p in range(ids.size - 1):
+            om2.step(int(ids[p]), p)
+        pl = om2.forward(int(ids[-1]), ids.size - 1)
+        eng.prefill(ids)
+        torch.cuda.synchronize()
+        perr = float(np.abs(eng.buffer("model_pred").cpu().numpy() - pl).max())
+        assert perr <= 6e-2 * max(1.0, float(np.abs(pl).max())), perr     # bf16 operands, 2 layers of the gain-4 model
+        k1 = eng.kv_row("k", 1, 5).float().cpu().numpy()
+        wk1 = om2.read(2, (1 * ms.max_len + 5) * ms.kv_hidden, ms.kv_hidden)
+        assert float(np.abs(k1 - wk1).max()) <= 3e-2 * float(np.abs(wk1).max())
+    eng.close()
+
+
+@pytest.mark.parametrize("mega_ll", [False, True])
+def test_full_width_llama3_8b_one_layer(port, mega_ll):
+    """Llama-3-8B widths (GQA 4 query heads per KV head, inter 14336 -> 112-chunk K slices, 128 256-row tied classifier) with one
+    layer, both megakernels, against the oracle (bf16 KV on both sides)."""
+    import dataclasses
+    ms = dataclasses.replace(PRESETS["llama3-8b"], layers=1, max_len=48)
+    blob = port.fill_blob(oracle_shape(ms), 13, BF16, 64, threads=os.cpu_count() or 1)
+    want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True).greedy([1, 2, 3, 4, 5], 14)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, mega=True, mega_ll=mega_ll).load_synthetic(13)
+    assert eng.mode == ("megakernel(ll)" if mega_ll else "megakernel"), eng.mode
+    got = eng.greedy([1, 2, 3, 4, 5], 14)
+    assert np.array_equal(got, want), (got, want)
+    err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
+    assert err <= 5e-3 * max(1.0, float(np.abs(want_l).max())), err
+    eng.close()
