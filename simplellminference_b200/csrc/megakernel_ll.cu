@@ -267,26 +267,51 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             }
             __syncthreads();
             // step 2: weighted sum of the splits' outputs, two splits (four 16-byte loads) in flight per polling round trip
-            // (four in flight, inline or out of line, pushes the kernel over its 128-register cap into the streaming loop: slower)
-            for (int c4 = tid; c4 < cols / 4; c4 += kMegaThreads) {
+            // (four in flight, inline or out of line, pushes the kernel over its 128-register cap into the streaming loop: slower).
+            // When the rank has fewer float4 column groups than threads (tensor parallel: q_loc / 4 < 512), P threads share a
+            // group and each takes a contiguous block of the splits — 32 splits at 8K context are then 4 round trips, not 16 —
+            // and the P partial sums are added in block order from shared memory (fixed order: every CTA and rank agrees bit for bit).
+            const int ngr = cols / 4;
+            const int P = (2 * nrec > 1024) ? 1 : max(1, min(min(8, kMegaThreads / ngr), nsplit));   // (merge weights must end before the scratch)
+            const int blk = (nsplit + P - 1) / P;
+            float4* scratch = reinterpret_cast<float4*>(part + 1024);       // behind the merge weights (<= 4 KB), <= 8 KB
+            for (int idx = tid; idx < ngr * P; idx += kMegaThreads) {
+                const int c4 = idx % ngr, pt = idx / ngr;
                 const int col = c4 * 4;
                 const int head = col / p.hd, j = col - head * p.hd;
                 const uint2* base = my_area + p.off_att + (int64_t)head * nsplit * rec;
                 constexpr int kNS = 2;
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int s0 = 0; s0 < nsplit; s0 += kNS) {
+                const int s_end = min(nsplit, (pt + 1) * blk);
+                for (int s0 = pt * blk; s0 < s_end; s0 += kNS) {
                     float4 ov[kNS];
-                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + j, rec, min(kNS, nsplit - s0), e, ov);
+                    ll_recv4xN<kNS>(base + (int64_t)s0 * rec + j, rec, min(kNS, s_end - s0), e, ov);
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) {
-                        if (s0 + i < nsplit) {
+                        if (s0 + i < s_end) {
                             const float w = mw[2 * (head * nsplit + s0 + i)];
                             o.x = fmaf(ov[i].x, w, o.x); o.y = fmaf(ov[i].y, w, o.y); o.z = fmaf(ov[i].z, w, o.z); o.w = fmaf(ov[i].w, w, o.w);
                         }
                     }
                 }
-                const float Ls = mw[2 * head * nsplit + 1];
-                reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+                if (P == 1) {
+                    const float Ls = mw[2 * head * nsplit + 1];
+                    reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+                } else {
+                    scratch[pt * ngr + c4] = o;
+                }
+            }
+            if (P > 1) {
+                __syncthreads();
+                for (int c4 = tid; c4 < ngr; c4 += kMegaThreads) {
+                    float4 o = scratch[c4];
+                    for (int pt = 1; pt < P; ++pt) {
+                        const float4 q = scratch[pt * ngr + c4];
+                        o = make_float4(o.x + q.x, o.y + q.y, o.z + q.z, o.w + q.w);
+                    }
+                    const float Ls = mw[2 * ((c4 * 4) / p.hd) * nsplit + 1];
+                    reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+                }
             }
         } else {                                                              // down: sigmoid(gate)*up of this layer
             xsrc = xs;
