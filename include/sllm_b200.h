@@ -46,7 +46,9 @@ typedef void* sllm_stream_t;
 
 const char* sllm_last_error(void);
 int sllm_abi_version(void);
-/* development knobs (not part of the drop-in surface): key 0 = GEMV CTAs per SM (0 = built-in choice) */
+/* development knobs (not part of the drop-in surface): key 0 = GEMV CTAs per SM (0 = built-in choice); prefill GEMM: key 1 = force
+ * the N extent of a tile (multiple of 32, 0 = cost model), key 2 = two-SM tiles (1 / 0 force / forbid, -1 = by T), key 3 = programmatic
+ * dependent launch (1 default), key 4 = K split of the residual-epilogue GEMMs (0 never, n up to n ranges, -1 cost model) */
 int sllm_tune(int32_t key, int32_t value);
 /* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
 int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);
@@ -213,6 +215,11 @@ int sllm_engine_prefill_supported(const sllm_engine* e);
  * C[T][N] (fp32) = A[T][K] (bf16) . W[N][K]^T (bf16, row-major) on tcgen05; bn = 0 (auto), 128 or 256 = N tile. */
 int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, int32_t T, int32_t N, int32_t K, int32_t bn,
                            sllm_stream_t stream);
+/* How sllm_prefill_gemm_bf16 / the engine would run a [T][K] x [N][K]^T GEMM (host arithmetic only, no launch): two_sm = 1 when SM
+ * pairs share 256-row tiles (tcgen05 cta_group::2), bn = N extent of a tile, ksplit = K ranges per tile (> 1 only with the
+ * residual epilogue, whose partial sums are added with red.global.add), work_units = tiles x ksplit. */
+int sllm_prefill_gemm_plan(int32_t T, int32_t N, int32_t K, int32_t residual_epilogue, int32_t* two_sm, int32_t* bn,
+                           int32_t* ksplit, int32_t* work_units);
 /* causal attention of T queries (bf16 [T][heads*head_dim]) at positions pos0.. over a HEAD-MAJOR cache
  * [kv_heads][max_len][head_dim] (kv_dtype f32 or bf16), rows 0..pos0+T-1 valid; out bf16 like q. */
 int sllm_prefill_attention(const void* q, const void* key_cache, const void* value_cache, int32_t kv_dtype, void* out,

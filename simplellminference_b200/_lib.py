@@ -71,6 +71,7 @@ SIGNATURES = {
     "sllm_engine_prefill": (C.c_int, [_P, _P, _I, _I]),
     "sllm_engine_prefill_supported": (C.c_int, [_P]),
     "sllm_prefill_gemm_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "sllm_prefill_gemm_plan": (C.c_int, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "sllm_prefill_attention": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "sllm_engine_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_engine_step_bytes": (_L, [_P, _I]),

@@ -503,50 +503,64 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const PfDev& p
     return SLLM_OK;
 }
 
-int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
-    SLLM_REQUIRE(cache && a.A && a.W && a.T > 0 && a.N > 0 && a.K > 0, SLLM_EINVAL, "pf_gemm: bad argument");
-    SLLM_REQUIRE(a.K % 8 == 0, SLLM_ENOTSUP, "pf_gemm: K=%d must be a multiple of 8", a.K);
-    PfDev p{};
-    p.T = a.T; p.N = a.N; p.tiled = a.tiled; p.epilogue = a.epilogue;
+// Host-side plan of one GEMM: cluster shape, N extent of a tile, K split, k-blocks. Pure arithmetic (no device access beyond the
+// cached SM count), exposed as sllm_prefill_gemm_plan for tests.
+struct PfPlan { int pair, bn, ksplit, m_tiles, n_tiles, nkb, kb_per_seg, seg_elems, R; TileGeom g; };
+static PfPlan pf_plan(int T, int N, int K, int tiled, int epilogue, int bn_forced) {
+    PfPlan pl{};
     // more than one 128-row block of tokens: two SMs share a 256-row tile (tcgen05 cta_group::2)
-    const bool pair = g_tune_pf_pair >= 0 ? (g_tune_pf_pair != 0) : (a.T > kPfBM);
-    const int BM = pair ? 2 * kPfBM : kPfBM;
-    p.m_tiles = (a.T + BM - 1) / BM;
-    TileGeom g{};
-    if (a.tiled) {
-        g = mega_tile_geom(a.N, a.K, SLLM_BF16);
-        p.seg_elems = g.SC * 8; p.R = g.R;
-        p.kb_per_seg = (p.seg_elems + kPfBK - 1) / kPfBK;
-        p.nkb = g.KS * p.kb_per_seg;
+    pl.pair = g_tune_pf_pair >= 0 ? (g_tune_pf_pair != 0) : (T > kPfBM);
+    const int BM = pl.pair ? 2 * kPfBM : kPfBM;
+    pl.m_tiles = (T + BM - 1) / BM;
+    if (tiled) {
+        pl.g = mega_tile_geom(N, K, SLLM_BF16);
+        pl.seg_elems = pl.g.SC * 8; pl.R = pl.g.R;
+        pl.kb_per_seg = (pl.seg_elems + kPfBK - 1) / kPfBK;
+        pl.nkb = pl.g.KS * pl.kb_per_seg;
     } else {
-        p.seg_elems = a.K; p.R = 1;
-        p.kb_per_seg = (a.K + kPfBK - 1) / kPfBK;
-        p.nkb = p.kb_per_seg;
+        pl.seg_elems = K; pl.R = 1;
+        pl.kb_per_seg = (K + kPfBK - 1) / kPfBK;
+        pl.nkb = pl.kb_per_seg;
     }
     // N extent of a tile (a multiple of 32 up to 256) and, for the residual epilogue, a split of K: a work unit costs about
     // k-blocks x operand bytes per k-block (the kernel is bound by what an SM can ingest) plus the epilogue of its tile, and the
     // GEMM takes ceil(units / workers) waves of it. Pick the cheapest combination.
-    int bn = a.bn ? a.bn : g_tune_pf_bn;
+    int bn = bn_forced ? bn_forced : g_tune_pf_bn;
     int ksplit = 1;
     if (bn < 32 || bn > 256 || bn % 32) {
-        const int workers = pair ? sm_count() / 2 : sm_count();
-        const int max_split = (a.epilogue == PF_EPI_RESID && g_tune_pf_ksplit != 0) ? (g_tune_pf_ksplit > 0 ? g_tune_pf_ksplit : 4) : 1;
+        const int workers = pl.pair ? sm_count() / 2 : sm_count();
+        const int max_split = (epilogue == PF_EPI_RESID && g_tune_pf_ksplit != 0) ? (g_tune_pf_ksplit > 0 ? g_tune_pf_ksplit : 4) : 1;
         double best = 1e30;
         for (int b = 256; b >= 64; b -= 32) {
             for (int sp = 1; sp <= max_split; ++sp) {
-                if (sp > 1 && p.nkb / sp < 8) break;   // keep at least 8 k-blocks per work unit
-                const long units = (long)p.m_tiles * ((a.N + b - 1) / b) * sp;
-                const double unit_cost = (double)((p.nkb + sp - 1) / sp) * (kPfBM + (pair ? b / 2 : b)) + 10.0 * b;
+                if (sp > 1 && pl.nkb / sp < 8) break;   // keep at least 8 k-blocks per work unit
+                const long units = (long)pl.m_tiles * ((N + b - 1) / b) * sp;
+                const double unit_cost = (double)((pl.nkb + sp - 1) / sp) * (kPfBM + (pl.pair ? b / 2 : b)) + 10.0 * b;
                 const double c = (double)((units + workers - 1) / workers) * unit_cost;
                 if (c < best - 1e-9) { best = c; bn = b; ksplit = sp; }
             }
         }
-    } else if (a.epilogue == PF_EPI_RESID && g_tune_pf_ksplit > 0 && p.nkb / g_tune_pf_ksplit >= 1) {
+    } else if (epilogue == PF_EPI_RESID && g_tune_pf_ksplit > 0 && pl.nkb / g_tune_pf_ksplit >= 1) {
         ksplit = g_tune_pf_ksplit;
     }
+    pl.bn = bn; pl.ksplit = ksplit;
+    pl.n_tiles = (N + bn - 1) / bn;
+    return pl;
+}
+
+int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
+    SLLM_REQUIRE(cache && a.A && a.W && a.T > 0 && a.N > 0 && a.K > 0, SLLM_EINVAL, "pf_gemm: bad argument");
+    SLLM_REQUIRE(a.K % 8 == 0, SLLM_ENOTSUP, "pf_gemm: K=%d must be a multiple of 8", a.K);
+    const PfPlan pl = pf_plan(a.T, a.N, a.K, a.tiled, a.epilogue, a.bn);
+    const bool pair = pl.pair != 0;
+    const int bn = pl.bn, ksplit = pl.ksplit;
+    const TileGeom g = pl.g;
+    PfDev p{};
+    p.T = a.T; p.N = a.N; p.tiled = a.tiled; p.epilogue = a.epilogue;
+    p.m_tiles = pl.m_tiles; p.seg_elems = pl.seg_elems; p.R = pl.R; p.kb_per_seg = pl.kb_per_seg; p.nkb = pl.nkb;
     p.ksplit = ksplit;
     p.BN = bn;
-    p.n_tiles = (a.N + bn - 1) / bn;
+    p.n_tiles = pl.n_tiles;
     p.out = a.out; p.ld_out = a.ld_out; p.n_valid = a.n_valid;
     p.q_out = a.q_out; p.kc = a.k_cache; p.vc = a.v_cache; p.kv_dtype = a.kv_dtype; p.q_loc = a.q_loc; p.kv_loc = a.kv_loc; p.hd = a.hd; p.S = a.S;
     p.pos0 = a.pos0; p.sin_t = a.sin_t; p.cos_t = a.cos_t; p.s_out = a.s_out; p.I_loc = a.I_loc;
@@ -589,4 +603,16 @@ extern "C" int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, in
     PfGemmArgs a{};
     a.A = A; a.W = W; a.T = T; a.N = N; a.K = K; a.tiled = 0; a.epilogue = PF_EPI_STORE; a.out = C; a.ld_out = N; a.n_valid = N; a.bn = bn;
     return pf_gemm(cache, a, as_stream(stream));
+}
+
+extern "C" int sllm_prefill_gemm_plan(int32_t T, int32_t N, int32_t K, int32_t residual_epilogue, int32_t* two_sm, int32_t* bn, int32_t* ksplit,
+                                      int32_t* work_units) {
+    using namespace sllm;
+    SLLM_REQUIRE(T > 0 && N > 0 && K > 0 && K % 8 == 0, SLLM_EINVAL, "bad GEMM shape");
+    const PfPlan pl = pf_plan(T, N, K, /*tiled=*/0, residual_epilogue ? PF_EPI_RESID : PF_EPI_STORE, 0);
+    if (two_sm) *two_sm = pl.pair;
+    if (bn) *bn = pl.bn;
+    if (ksplit) *ksplit = pl.ksplit;
+    if (work_units) *work_units = pl.m_tiles * pl.n_tiles * pl.ksplit;
+    return SLLM_OK;
 }
