@@ -248,8 +248,24 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_kernel(float* __restrict__ x, 
     pdl_launch_dependents();
     float4* xr = reinterpret_cast<float4*>(x + (size_t)t * d);
     const float4* ar = add ? reinterpret_cast<const float4*>(add + (size_t)t * d) : nullptr;
+    constexpr int kKeep = 8;   // float4 per thread kept in registers between the two passes (rows up to 8192 floats are read once)
+    float4 keep[kKeep];
     float ss = 0.f;
-    for (int i = threadIdx.x; i < d / 4; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < d / 4) {
+            float4 v = xr[i];
+            if (ar) {
+                const float4 a = ar[i];
+                v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+                xr[i] = v;
+            }
+            keep[k] = v;
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+    }
+    for (int i = threadIdx.x + kKeep * 256; i < d / 4; i += 256) {
         float4 v = xr[i];
         if (ar) {
             const float4 a = ar[i];
@@ -260,12 +276,17 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_kernel(float* __restrict__ x, 
     }
     ss = block_sum(ss, red);
     const float inv = 1.0f / sqrtf(ss / (float)d + eps);   // rms_kernel.cpp:17-19
-    for (int i = threadIdx.x; i < d / 4; i += blockDim.x) {
-        const float4 v = xr[i];
-        const float4 g = reinterpret_cast<const float4*>(w)[i];
+    auto emit = [&](int i, const float4 v) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w) + i);
         *reinterpret_cast<uint2*>(y + (size_t)t * d + 4 * i) =
             make_uint2(bf16x2((v.x * inv) * g.x, (v.y * inv) * g.y), bf16x2((v.z * inv) * g.z, (v.w * inv) * g.w));
+    };
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < d / 4) emit(i, keep[k]);
     }
+    for (int i = threadIdx.x + kKeep * 256; i < d / 4; i += 256) emit(i, xr[i]);
 }
 
 int pf_rmsnorm(float* x, const float* add, const float* w, uint16_t* y, int T, int d, float eps, cudaStream_t st) {
