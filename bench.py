@@ -140,7 +140,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------ reference arm --
 def cpu_reference_sample(ms, pos, steps, warmup, want_fast=True):
     """Times the reference's own CPU forward (oracle/_ref = the unmodified sources compiled by oracle/Makefile;
-    falls back to the C port only if that library was never built) on a BOUNDED sample of the workload:
+    falls back to the C port only if that library was never built) on a BOUNDED sample of the workload (~10 s of CPU work):
     the full-shape model cut to L1 and L2 layers (+ the full classifier), one forward at position `pos` per
     step; the 32-layer token time is extrapolated linearly in the layer count (layers are identical in cost).
     The reference is single-threaded by construction (no threads/OpenMP anywhere in it): cores = 1."""
@@ -152,7 +152,7 @@ def cpu_reference_sample(ms, pos, steps, warmup, want_fast=True):
         fast = want_fast and loader.cpu_supports_v3() and os.path.exists(loader.REF_FAST_SO)
         ref = loader.Ref(fast=fast)
         kind, flags = "reference", ref.flags
-    L1, L2 = 1, 2
+    L1, L2 = 1, 3   # two cuts two layers apart: the per-layer time is a difference of medians, a wider base makes it steadier
     times = {}
     cwd = os.getcwd()
     os.chdir("/tmp")  # LlamaModel::forward() opens layer_outputs_cpu.txt in the cwd on every call (model.cpp:42)
@@ -388,7 +388,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_sample(ms, P, 3, 1)
+            cpu = cpu_reference_sample(ms, P, 5, 1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the baseline is informational; never lose the GPU numbers over it
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)}
