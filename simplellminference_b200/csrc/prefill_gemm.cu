@@ -3,17 +3,22 @@
 //   C[T][N] = A[T][K] . W[N][K]^T      A = bf16 activations, W = bf16 weights, C = fp32 accumulators in TMEM
 //
 // One persistent CTA per SM, 192 threads, three roles (no role ever blocks another with __syncthreads):
-//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor of a 128 x 64 A box and a BN x 64 W box per k-block into a
-//                      ring of 128B-swizzled stages, completion counted on the stage's "full" mbarrier;
-//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per stage, both operands
-//                      through shared-memory descriptors; tcgen05.commit frees the stage / publishes the accumulator;
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor of a 128 x 64 A box and this CTA's W box per k-block into a ring of
+//                      128B-swizzled stages, completion counted on the stage's "full" mbarrier;
+//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma.kind::f16 (K = 16 each) per stage, both operands through shared-memory
+//                      descriptors; tcgen05.commit frees the stage / publishes the accumulator;
 //   warps 2-5          epilogue: tcgen05.ld 32 columns at a time (one accumulator row per thread), fused epilogue
 //                      (RoPE + KV-cache write, sigmoid(gate)*up, residual add), while the issuer already fills the
-//                      second accumulator (TMEM holds two: 2 x BN columns).
+//                      second accumulator (TMEM holds two of up to 256 columns).
+// Two cluster shapes: one SM per 128 x BN tile (cta_group::1, prompts of <= 128 rows and the T = 1 classifier), or the two SMs of
+// a TPC on one 256 x BN tile (cta_group::2: each CTA stages its own 128 rows of A and BN/2 rows of W, the leader issues the MMAs,
+// its commits are multicast to both CTAs). BN is a run-time multiple of 32; the residual-epilogue GEMMs may split K (pf_plan).
 // W is read straight from the megakernel's TILED decode layout (megakernel.cuh) through a 4-D tensor map
 // {k inside a K slice, row inside a tile, K slice, tile row}: prefill and decode share one copy of the weights.
 // Rows of the tiled layout are in unit order, so the two values an epilogue needs together (RoPE partners,
 // (up, gate)) sit in ADJACENT accumulator columns of the same thread.
+// What bounds it (profiles/r01_prefill_ncu_raw.md): the bytes an SM can ingest (~65 GB/s per SM through TMA),
+// not the tensor pipe — hence the two-SM tile; L2 prefetch, TMA multicast across pairs and stream-K were measured and dropped.
 #include <cuda.h>
 
 #include <map>
