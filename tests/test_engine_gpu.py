@@ -228,3 +228,36 @@ def test_full_width_llama3_8b_one_layer(port, mega_ll):
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
     assert err <= 5e-3 * max(1.0, float(np.abs(want_l).max())), err
     eng.close()
+
+
+def test_predict_driver(port):
+    """simplellminference_b200.predict.predict_ids (the loop of LlamaModel::predict, model.cpp:148-185) around a real engine:
+    identical to the oracle's greedy stream token by token; with the batched prefill the prompt echo is exact and the stream is the
+    oracle's on the gain-1 model; EOS stops generation (additive — the reference never stops)."""
+    from simplellminference_b200.predict import predict_ids
+    ms = PRESETS["tiny_gqa"]
+    blob = port.fill_blob(oracle_shape(ms), 1234)
+    want, _ = port.model(oracle_shape(ms), blob).greedy([1, 7, 300], 41)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32, mega=True).load_blob(blob)
+    got = predict_ids(eng, [1, 7, 300], 40, chunk=7)
+    assert np.array_equal(got, want)
+    eos = int(want[20])
+    first = int(np.flatnonzero(want == eos)[0])
+    stopped = predict_ids(eng, [1, 7, 300], 40, eos_id=eos, chunk=7)
+    assert np.array_equal(stopped, want[:first + 1])
+    eng.close()
+
+    ms2 = ModelShape(2048, 64, 512, 128, 1408, 320, 2, 8, 2)
+    sh2 = oracle_shape(ms2)
+    blob2 = port.fill_blob(sh2, 21, BF16)
+    for seg in range(2, 9):
+        off, cnt = port.segment(sh2, seg)[:2]
+        blob2[off:off + cnt] *= 0.25
+    prompt = np.random.default_rng(2).integers(1, ms2.vocab, size=100, dtype=np.int32)
+    want2, _ = port.model(sh2, blob2, threads=os.cpu_count() or 1, kv_bf16=True).greedy(prompt, 121)
+    eng2 = Engine(ms2, w_dtype=BF16, kv_dtype=BF16, mega=True).load_blob(blob2)
+    assert eng2.prefill_supported
+    got2 = predict_ids(eng2, prompt, 120)
+    assert np.array_equal(got2[:99], prompt[1:])
+    assert np.array_equal(got2, want2), int(np.flatnonzero(got2 != want2)[0])
+    eng2.close()
