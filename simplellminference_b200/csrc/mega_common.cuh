@@ -13,6 +13,9 @@ constexpr int kCplMax = 4;        // max 16-byte chunks per lane per row slice (
 constexpr int kRoundUnits = 128;  // units per partial-table round
 constexpr int kAttTile = 64;
 constexpr unsigned kSpinLimit = 1u << 26;
+#ifndef SLLM_BARRIER_POLL_COUNTER
+#define SLLM_BARRIER_POLL_COUNTER 1   // measured on B200 (llama2-7b bf16): 350.4 tok/s vs 338.1 with the separate release flag
+#endif
 constexpr int kAttRecPad = 4;     // partial record = hd floats of O, then m, l (+2 pad: keeps float4 alignment)
 
 
@@ -72,13 +75,25 @@ __device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t byt
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// grid-wide barrier (cooperative launch guarantees co-residency). counter[0] = arrivals (monotonic), counter[32] =
-// released epoch on its own 128-byte line: the last arriver publishes the epoch, everybody else polls that line
-// only, so the polling never collides with the arriving atomics. Wrap-safe compares. No trailing fence: every
-// cross-CTA read in this kernel is an L2 access (ld.global.cg or TMA), never an L1-cached load.
+// grid-wide barrier (cooperative launch guarantees co-residency). counter[0] = arrivals (monotonic across launches; wrap-safe
+// compares). Default: thread 0 of every CTA arrives with ONE atom.add.release and then polls the counter itself with ld.acquire
+// until the target — the last arriver needs no extra hop to publish anything (measured: 2.85 ms/token instead of 2.96 with the
+// older scheme, kept under SLLM_BARRIER_POLL_COUNTER=0: fence + atomicAdd, the last arriver stores the epoch to counter[32] on
+// its own 128-byte line, the others poll that line). No trailing fence: every cross-CTA read in this kernel is an L2 access
+// (ld.global.cg or TMA), never an L1-cached load.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
+#if SLLM_BARRIER_POLL_COUNTER
+        unsigned v;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+        v += 1u;
+        unsigned spins = 0;
+        while ((int)(v - target) < 0) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spins > kSpinLimit) __trap();
+        }
+#else
         __threadfence();
         const unsigned prev = atomicAdd(counter, 1u);
         if (prev + 1u == target) {
@@ -92,6 +107,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
                 if (++spins > kSpinLimit) __trap();
             }
         }
+#endif
     }
     __syncthreads();
 }
