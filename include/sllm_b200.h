@@ -112,6 +112,14 @@ int sllm_argmax_f32(const float* logits, int32_t n, int32_t* idx_dev, sllm_strea
 /* KV-row store used by the op-by-op path when the cache is bf16: cache_row[i] = bf16(src[i]) */
 int sllm_store_kv_row(const float* src, void* cache_row, int32_t kv_dtype, int32_t n, sllm_stream_t stream);
 
+/* Sampling beyond arg-max (additive: the reference only has argmaxLayer; LayerType::kLayerSoftmax is declared but unused,
+ * include/op/layer.h:17). One draw from softmax(logits / temperature) restricted to the top_k largest logits (0 = all; ties at
+ * the k-th value are kept) and then to the smallest set of largest logits whose mass reaches top_p (0 or 1 = all). The draw is a
+ * pure function of (logits, parameters, seed, step): u = hash(seed, step), first index whose running kept mass exceeds u * mass.
+ * temperature <= 0 = arg-max (first maximum). idx_dev: device int32. */
+int sllm_sample_f32(const float* logits, int32_t n, float temperature, int32_t top_k, float top_p, uint64_t seed,
+                    uint64_t step, int32_t* idx_dev, sllm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Synthetic weights (device side of oracle/synth_weights.h: same integer hash, bit-identical values).
  * Fills `count` elements [first, first+count) of blob segment `segment` (0 E, 1 norms, 2 wq, 3 wk, 4 wv,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "sllm_swiglu_f32": (C.c_int, [_P, _P, _P, _I, _P]),
     "sllm_argmax_f32": (C.c_int, [_P, _I, _P, _P]),
     "sllm_store_kv_row": (C.c_int, [_P, _P, _I, _I, _P]),
+    "sllm_sample_f32": (C.c_int, [_P, _I, _F, _I, _F, C.c_uint64, C.c_uint64, _P, _P]),
     "sllm_synth_fill": (C.c_int, [C.POINTER(Shape), C.c_uint64, _I, _L, _L, _L, _L, _L, _P, _I, _P, _I, _P]),
     "sllm_convert_weights": (C.c_int, [_P, _P, _I, _P, _I, _L, _L, _P]),
     "sllm_engine_create": (C.c_int, [C.POINTER(EngineConfig), _P, C.POINTER(_P)]),

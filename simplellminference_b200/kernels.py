@@ -102,6 +102,14 @@ def argmax(logits):
     return idx
 
 
+def sample(logits, temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0, seed: int = 0, step: int = 0):
+    """One draw from softmax(logits / temperature) under top-k / top-p (sllm_sample_f32): CUDA int32 tensor with the index."""
+    idx = torch.empty(1, dtype=torch.int32, device=logits.device)
+    _lib.check(_lib.load().sllm_sample_f32(_p(_f32(logits)), logits.numel(), float(temperature), int(top_k), float(top_p), int(seed), int(step),
+                                           _p(idx), _stream()))
+    return idx
+
+
 def convert_weights(w_f32, w_dtype, group=64):
     """fp32 [rows][cols] -> storage dtype (+ scales for int8)."""
     rows, cols = w_f32.shape

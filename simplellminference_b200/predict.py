@@ -41,6 +41,32 @@ class SPELayer:
         return int(self.processor_.GetPieceSize())
 
 
+def sample_ids(engine, prompt_ids, max_length: int, temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0, seed: int = 0,
+               eos_id: Optional[int] = None) -> np.ndarray:
+    """Like predict_ids, but every generated token is DRAWN on the device (kernels.sample on the logits the engine leaves in
+    model_pred) instead of arg-max. Host-driven: one forward(token, pos) + one sample + a 4-byte read per token. Single GPU (under
+    tensor parallelism each rank only holds its slice of the logits). Reproducible: the draw at position p uses (seed, step = p)."""
+    from . import kernels
+    if engine.tp_size != 1:
+        raise ValueError("sample_ids: sampling needs the full logits vector (tp_size == 1)")
+    prompt_ids = np.ascontiguousarray(prompt_ids, dtype=np.int32)
+    n = int(prompt_ids.size)
+    if n < 1 or n > max_length or max_length >= engine.shape.max_len:
+        raise ValueError("sample_ids: need 1 <= len(prompt) <= max_length < max_len")
+    out = [int(t) for t in prompt_ids[1:]]
+    for pos in range(n - 1):                                  # prompt: logits unused (model.cpp:159-165)
+        engine.forward(int(prompt_ids[pos]), pos, want_logits=False)
+    tok = int(prompt_ids[-1])
+    logits = engine.buffer("model_pred")
+    for pos in range(n - 1, max_length):
+        engine.forward(tok, pos, want_logits=False)
+        tok = int(kernels.sample(logits, temperature, top_k, top_p, seed=seed, step=pos).item())
+        out.append(tok)
+        if eos_id is not None and tok == eos_id:
+            break
+    return np.asarray(out, dtype=np.int32)
+
+
 def predict_ids(engine, prompt_ids, max_length: int, eos_id: Optional[int] = None, chunk: int = 16, batched_prefill: bool = True,
                 on_tokens: Optional[Callable[[np.ndarray], None]] = None) -> np.ndarray:
     """Greedy loop of LlamaModel::predict on token ids. Returns the tokens that follow prompt[0] (prompt echo, then generated
