@@ -234,6 +234,54 @@ int sllm_prefill_attention(const void* q, const void* key_cache, const void* val
                            int32_t T, int32_t pos0, int32_t max_len, int32_t head_dim, int32_t heads, int32_t kv_heads,
                            sllm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Batched multi-sequence decode over a paged KV cache (additive: the reference decodes one sequence at a time,
+ * include/model/model.h:15-18 input_token{1} / position{1}, source/model/model.cpp:148-185). Up to 64 sequences,
+ * each at its own position, advance one token per step and share ONE pass over the weights (the HBM traffic of a
+ * decode step); every sequence follows the semantics of sllm_engine_greedy (prompt tokens fed verbatim, then the
+ * first-max arg-max fed back, no EOS stop). Activations stay fp32: the decode parity contract holds per sequence.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Page bookkeeping of the paged cache — host arithmetic only (no device, no CUDA call): a stack of free pages and, per
+ * sequence, the list of pages that hold its positions [i*page_len, (i+1)*page_len). sllm_batch uses one internally; it
+ * is exported so that a scheduler can plan admissions with the same rules. */
+typedef struct sllm_kvpages sllm_kvpages;
+sllm_kvpages* sllm_kvpages_create(int32_t n_pages, int32_t page_len, int32_t max_seqs, int32_t max_pages_per_seq);
+void sllm_kvpages_destroy(sllm_kvpages* kp);
+/* grow `seq` so that positions [0, n_positions) are covered; all or nothing. Returns the number of pages newly taken
+ * (>= 0), SLLM_ENOMEM when the free pages do not suffice (nothing changes), SLLM_EINVAL beyond max_pages_per_seq. */
+int32_t sllm_kvpages_reserve(sllm_kvpages* kp, int32_t seq, int32_t n_positions);
+int sllm_kvpages_release(sllm_kvpages* kp, int32_t seq);   /* all pages of seq return to the free stack */
+int32_t sllm_kvpages_free_count(const sllm_kvpages* kp);
+int32_t sllm_kvpages_held(const sllm_kvpages* kp, int32_t seq);
+const int32_t* sllm_kvpages_table(const sllm_kvpages* kp); /* [max_seqs][max_pages_per_seq] page ids, -1 = none */
+
+typedef struct sllm_batch sllm_batch;
+/* A batch borrows the weights, RoPE tables and stream of `e`, which must outlive it: one GPU, weights loaded, created
+ * WITHOUT SLLM_ENGINE_MEGAKERNEL (the batched kernels read row-major matrices). It owns the paged cache: two pools of
+ * n_pages pages of page_len positions, [pages][layers][kv_heads][page_len][head_dim] in kv_dtype, plus per-slot
+ * activations. A sequence may grow to the engine's max_len (the RoPE tables' extent). */
+int sllm_batch_create(sllm_engine* e, int32_t max_seqs, int32_t page_len, int32_t n_pages, int32_t kv_dtype, sllm_batch** out);
+void sllm_batch_destroy(sllm_batch* b);
+/* admit a sequence into the lowest free slot at position 0 (pages are taken when it steps); slot_out = its handle */
+int sllm_batch_add(sllm_batch* b, const int32_t* prompt_host, int32_t n_prompt, int32_t* slot_out);
+/* retire a sequence: its slot and pages are free for the next sllm_batch_add at once (stream order protects them) */
+int sllm_batch_remove(sllm_batch* b, int32_t slot);
+/* n_steps tokens for EVERY live sequence, asynchronous. Takes the pages the steps will write first, for all sequences
+ * or none: SLLM_ENOMEM (nothing enqueued) when the pool is short, SLLM_EINVAL when a sequence would pass max_len. */
+int sllm_batch_step(sllm_batch* b, int32_t n_steps);
+/* the tokens that followed positions 0.. of the slot's sequence (prompt tokens included, as sllm_engine_greedy
+ * reports them), at most max_tokens; *n_out = how many. Synchronises the stream. */
+int sllm_batch_read(sllm_batch* b, int32_t slot, int32_t* tokens_out_host, int32_t max_tokens, int32_t* n_out);
+/* logits (vocab floats) of the slot's latest step. Synchronises the stream. */
+int sllm_batch_logits(sllm_batch* b, int32_t slot, float* logits_host);
+int32_t sllm_batch_free_pages(const sllm_batch* b);
+int32_t sllm_batch_position(const sllm_batch* b, int32_t slot);   /* position of the slot's next step; -1 = free slot */
+/* algorithmic HBM bytes of the NEXT step: every weight once, plus per live sequence its embedding row, the K/V rows
+ * 0..pos it reads and the row it writes (SURVEY.md 8d B(p) with the weight term shared) */
+int64_t sllm_batch_step_bytes(const sllm_batch* b);
+int64_t sllm_batch_total_launches(const sllm_batch* b);
+
 /* Introspection for parity tests and the roofline: named buffers follow the reference's ModelBufferType
  * numbering (include/model/model.h:14-34); returns a device pointer and its element count/dtype. */
 int sllm_engine_buffer(sllm_engine* e, int32_t buffer_id, void** dev_ptr, int64_t* n_elems, int32_t* dtype);

@@ -6,6 +6,7 @@ Layers (bottom-up):
   _lib.py      ctypes loader (fails loudly when the CUDA library is missing: there is no CPU fallback)
   kernels.py   one Python wrapper per op launcher (torch tensors are only the carriers of device pointers)
   engine.py    the decode engine (arena + KV cache + CUDA-graph decode step, tensor parallel)
+  batch.py     batched multi-sequence decode over a paged KV cache (sllm_batch_* / sllm_kvpages_*)
   config.py    the model-shape presets named by BASELINE.json
 """
 from .config import ModelShape, PRESETS, F32, BF16, INT8  # noqa: F401

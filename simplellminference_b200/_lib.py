@@ -30,6 +30,7 @@ class EngineConfig(C.Structure):
 
 
 ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE, ENGINE_MEGAKERNEL, ENGINE_MEGA_LL = 1, 2, 4, 8, 16, 32
+EINVAL, ENOTSUP, ENOMEM, ESTATE, ECOMM = -1, -2, -3, -4, -5   # SLLM_E* of include/sllm_b200.h
 
 _P = C.c_void_p
 _I = C.c_int32
@@ -74,6 +75,24 @@ SIGNATURES = {
     "sllm_prefill_gemm_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "sllm_prefill_gemm_plan": (C.c_int, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "sllm_prefill_attention": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "sllm_kvpages_create": (_P, [_I, _I, _I, _I]),
+    "sllm_kvpages_destroy": (None, [_P]),
+    "sllm_kvpages_reserve": (_I, [_P, _I, _I]),
+    "sllm_kvpages_release": (C.c_int, [_P, _I]),
+    "sllm_kvpages_free_count": (_I, [_P]),
+    "sllm_kvpages_held": (_I, [_P, _I]),
+    "sllm_kvpages_table": (C.POINTER(_I), [_P]),
+    "sllm_batch_create": (C.c_int, [_P, _I, _I, _I, _I, C.POINTER(_P)]),
+    "sllm_batch_destroy": (None, [_P]),
+    "sllm_batch_add": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
+    "sllm_batch_remove": (C.c_int, [_P, _I]),
+    "sllm_batch_step": (C.c_int, [_P, _I]),
+    "sllm_batch_read": (C.c_int, [_P, _I, _P, _I, C.POINTER(_I)]),
+    "sllm_batch_logits": (C.c_int, [_P, _I, _P]),
+    "sllm_batch_free_pages": (_I, [_P]),
+    "sllm_batch_position": (_I, [_P, _I]),
+    "sllm_batch_step_bytes": (_L, [_P]),
+    "sllm_batch_total_launches": (_L, [_P]),
     "sllm_engine_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_engine_step_bytes": (_L, [_P, _I]),
     "sllm_engine_enqueue_kernel": (C.c_int, [_P, _I, _I]),

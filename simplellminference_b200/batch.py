@@ -1,0 +1,119 @@
+"""Batched multi-sequence decode over a paged KV cache: Python face of sllm_batch_* / sllm_kvpages_*
+(include/sllm_b200.h). Additive to the reference, which decodes one sequence at a time (include/model/model.h:15-18,
+source/model/model.cpp:148-185); every sequence of a batch follows the semantics of ``Engine.greedy``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .config import BF16
+from .engine import Engine
+
+
+class KvPages:
+    """Host bookkeeping of the paged cache (free stack + per-sequence page lists); no device involved."""
+
+    def __init__(self, n_pages: int, page_len: int, max_seqs: int, max_pages_per_seq: int):
+        self.lib = _lib.load()
+        self.h = self.lib.sllm_kvpages_create(n_pages, page_len, max_seqs, max_pages_per_seq)
+        if not self.h:
+            raise _lib.SllmError(_lib.EINVAL, self.lib.sllm_last_error().decode(errors="replace"))
+        self.max_seqs, self.max_pages = max_seqs, max_pages_per_seq
+
+    def reserve(self, seq: int, n_positions: int) -> int:
+        """Cover positions [0, n_positions) of ``seq``; returns the number of pages newly taken. All or nothing."""
+        rc = self.lib.sllm_kvpages_reserve(self.h, seq, n_positions)
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
+    def release(self, seq: int) -> None:
+        _lib.check(self.lib.sllm_kvpages_release(self.h, seq))
+
+    @property
+    def free(self) -> int:
+        return int(self.lib.sllm_kvpages_free_count(self.h))
+
+    def held(self, seq: int) -> int:
+        return int(self.lib.sllm_kvpages_held(self.h, seq))
+
+    def table(self) -> np.ndarray:
+        ptr = self.lib.sllm_kvpages_table(self.h)
+        return np.ctypeslib.as_array(ptr, shape=(self.max_seqs, self.max_pages)).copy()
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.sllm_kvpages_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchDecoder:
+    """Up to ``max_seqs`` sequences stepping together over the weights of ``engine`` (one GPU, not a megakernel engine)."""
+
+    def __init__(self, engine: Engine, max_seqs: int, page_len: int = 64, n_pages: int | None = None, kv_dtype: int = BF16):
+        self.lib = _lib.load()
+        self.engine = engine   # keeps the weights alive
+        if n_pages is None:    # enough for every slot to reach the engine's max_len
+            n_pages = max_seqs * ((engine.shape.max_len + page_len - 1) // page_len)
+        h = C.c_void_p()
+        _lib.check(self.lib.sllm_batch_create(engine.h, max_seqs, page_len, n_pages, kv_dtype, C.byref(h)))
+        self.h = h
+        self.max_seqs, self.page_len, self.n_pages, self.kv_dtype = max_seqs, page_len, n_pages, kv_dtype
+
+    def add(self, prompt) -> int:
+        prompt = np.ascontiguousarray(prompt, dtype=np.int32)
+        slot = C.c_int32(-1)
+        _lib.check(self.lib.sllm_batch_add(self.h, prompt.ctypes.data, prompt.size, C.byref(slot)))
+        return slot.value
+
+    def remove(self, slot: int) -> None:
+        _lib.check(self.lib.sllm_batch_remove(self.h, slot))
+
+    def step(self, n_steps: int = 1) -> None:
+        _lib.check(self.lib.sllm_batch_step(self.h, n_steps))
+
+    def tokens(self, slot: int) -> np.ndarray:
+        """The tokens that followed positions 0.. of the slot's sequence (what ``Engine.greedy`` returns)."""
+        n = self.position(slot)
+        out = np.empty(max(n, 1), np.int32)
+        got = C.c_int32(0)
+        _lib.check(self.lib.sllm_batch_read(self.h, slot, out.ctypes.data, max(n, 0), C.byref(got)))
+        return out[:got.value]
+
+    def logits(self, slot: int) -> np.ndarray:
+        out = np.empty(self.engine.shape.vocab, np.float32)
+        _lib.check(self.lib.sllm_batch_logits(self.h, slot, out.ctypes.data))
+        return out
+
+    def position(self, slot: int) -> int:
+        return int(self.lib.sllm_batch_position(self.h, slot))
+
+    @property
+    def free_pages(self) -> int:
+        return int(self.lib.sllm_batch_free_pages(self.h))
+
+    def step_bytes(self) -> int:
+        return int(self.lib.sllm_batch_step_bytes(self.h))
+
+    @property
+    def total_launches(self) -> int:
+        return int(self.lib.sllm_batch_total_launches(self.h))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.sllm_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,483 @@
+// csrc/batch.cu — sllm_batch_* / sllm_kvpages_*: batched multi-sequence greedy decode over a paged KV cache
+// (SURVEY.md §8f rank 3). Additive: the reference decodes ONE sequence (include/model/model.h:15-18 input_token{1},
+// position{1}; source/model/model.cpp:148-185); here up to 64 sequences, each at its own position, advance one token
+// per step and share a single pass over the weights.
+//
+// A batch borrows the weights, RoPE tables and stream of an engine that stores its matrices row-major (any engine
+// created without SLLM_ENGINE_MEGAKERNEL, one GPU). Per step and layer (same five-kernel split as decode_fused.cuh):
+//   A  RMSNorm -> QKV GEMV for all slots -> RoPE -> q buffer + the K/V rows of each slot's position in ITS page
+//   B  split-KV flash decoding per (slot, KV head) through the slot's block table (mha.cu, PAGED instantiation)
+//   C  Wo GEMV + residual      D  RMSNorm -> up/gate GEMV -> sigmoid(gate)*up      E  Wdown GEMV + residual
+// then RMSNorm -> tied classifier for all slots, and one CTA per slot for first-max arg-max + token/position feedback
+// (prompt tokens are fed verbatim first, exactly as LlamaModel::predict does, model.cpp:157-166). Everything a step
+// needs (tokens, positions, block tables) lives in device memory, so n steps are n launch sequences with no host
+// round trip; the host only hands out pages ahead of the steps it enqueues.
+//
+// Pages: sllm_kvpages is plain host bookkeeping (free stack + per-sequence page lists), exported on its own so that it
+// is testable without a GPU. The device pools are [pages][layers][kv_heads][page_len][head_dim] (paged_kv.cuh).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "batch_gemv.cuh"
+#include "engine_view.cuh"
+
+using namespace sllm;
+
+// ---------------------------------------------------------------------------------------- page bookkeeping ---
+struct sllm_kvpages {
+    int n_pages = 0, page_len = 0, max_seqs = 0, max_pages = 0;
+    std::vector<int32_t> free_;    // stack of free page ids; page 0 is handed out first
+    std::vector<int32_t> table;    // [max_seqs][max_pages], -1 = none
+    std::vector<int32_t> held;     // pages held by each sequence
+
+    int pages_for(int n_positions) const { return (n_positions + page_len - 1) / page_len; }
+    // pages a sequence would have to take to cover positions [0, n_positions); < 0: it cannot (beyond max_pages)
+    int extra_needed(int seq, int n_positions) const {
+        const int need = pages_for(n_positions);
+        if (need > max_pages) return -1;
+        return std::max(0, need - held[seq]);
+    }
+    void take(int seq, int extra) {
+        for (int i = 0; i < extra; ++i) {
+            table[(size_t)seq * max_pages + held[seq]++] = free_.back();
+            free_.pop_back();
+        }
+    }
+    void release(int seq) {
+        for (int i = held[seq] - 1; i >= 0; --i) {   // so that the pages come back in the order they were handed out
+            free_.push_back(table[(size_t)seq * max_pages + i]);
+            table[(size_t)seq * max_pages + i] = -1;
+        }
+        held[seq] = 0;
+    }
+};
+
+extern "C" {
+
+sllm_kvpages* sllm_kvpages_create(int32_t n_pages, int32_t page_len, int32_t max_seqs, int32_t max_pages_per_seq) {
+    if (n_pages < 1 || page_len < 1 || max_seqs < 1 || max_pages_per_seq < 1) {
+        set_error("kvpages: n_pages=%d page_len=%d max_seqs=%d max_pages_per_seq=%d must all be positive", n_pages, page_len, max_seqs, max_pages_per_seq);
+        return nullptr;
+    }
+    auto* kp = new sllm_kvpages();
+    kp->n_pages = n_pages; kp->page_len = page_len; kp->max_seqs = max_seqs; kp->max_pages = max_pages_per_seq;
+    kp->free_.resize(n_pages);
+    for (int i = 0; i < n_pages; ++i) kp->free_[i] = n_pages - 1 - i;
+    kp->table.assign((size_t)max_seqs * max_pages_per_seq, -1);
+    kp->held.assign(max_seqs, 0);
+    return kp;
+}
+
+void sllm_kvpages_destroy(sllm_kvpages* kp) { delete kp; }
+
+int32_t sllm_kvpages_reserve(sllm_kvpages* kp, int32_t seq, int32_t n_positions) {
+    SLLM_REQUIRE(kp && seq >= 0 && seq < kp->max_seqs && n_positions >= 0, SLLM_EINVAL, "kvpages_reserve: bad argument (seq %d, positions %d)", seq, n_positions);
+    const int extra = kp->extra_needed(seq, n_positions);
+    SLLM_REQUIRE(extra >= 0, SLLM_EINVAL, "kvpages_reserve: %d positions need more than %d pages of %d", n_positions, kp->max_pages, kp->page_len);
+    SLLM_REQUIRE(extra <= (int)kp->free_.size(), SLLM_ENOMEM, "out of KV pages: sequence %d needs %d more, %d free", seq, extra, (int)kp->free_.size());
+    kp->take(seq, extra);
+    return extra;
+}
+
+int sllm_kvpages_release(sllm_kvpages* kp, int32_t seq) {
+    SLLM_REQUIRE(kp && seq >= 0 && seq < kp->max_seqs, SLLM_EINVAL, "kvpages_release: bad sequence %d", seq);
+    kp->release(seq);
+    return SLLM_OK;
+}
+
+int32_t sllm_kvpages_free_count(const sllm_kvpages* kp) { return kp ? (int32_t)kp->free_.size() : 0; }
+int32_t sllm_kvpages_held(const sllm_kvpages* kp, int32_t seq) { return (kp && seq >= 0 && seq < kp->max_seqs) ? kp->held[seq] : 0; }
+const int32_t* sllm_kvpages_table(const sllm_kvpages* kp) { return kp ? kp->table.data() : nullptr; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the batch ---
+constexpr int kBatchMaxSeqs = 64;
+
+struct sllm_batch {
+    EngineView ev{};
+    cudaStream_t stream = nullptr;
+    int max_seqs = 0, kv_dtype = SLLM_BF16, esz_kv = 2;
+    int d = 0, hd = 0, L = 0, S = 0, V = 0, H = 0, KVH = 0, I = 0, q_dim = 0, kv_dim = 0;
+    sllm_kvpages* pages = nullptr;
+    // device arena (one cudaMalloc)
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    void *k_pool = nullptr, *v_pool = nullptr;
+    float *x = nullptr, *h = nullptr, *q = nullptr, *att = nullptr, *swi = nullptr, *logits = nullptr;
+    int32_t *token = nullptr, *pos = nullptr, *n_prompt = nullptr, *next = nullptr, *block_table = nullptr, *prompt = nullptr, *history = nullptr;
+    void* mha_ws = nullptr;
+    // host mirror
+    std::vector<int> host_pos;     // position of the slot's next step; -1 = slot free
+    int64_t total_launches = 0;
+};
+
+template <class T>
+static T* bcarve(sllm_batch* b, size_t bytes) {
+    const size_t off = (b->arena_used + 255) / 256 * 256;
+    b->arena_used = off + bytes;
+    return b->arena ? reinterpret_cast<T*>(b->arena + off) : nullptr;
+}
+
+static void batch_layout(sllm_batch* b) {   // first pass (arena == nullptr) only measures
+    b->arena_used = 0;
+    const size_t ms = b->max_seqs;
+    const size_t pool = (size_t)b->pages->n_pages * b->L * b->KVH * b->pages->page_len * b->hd * b->esz_kv;
+    b->k_pool = bcarve<void>(b, pool);
+    b->v_pool = bcarve<void>(b, pool);
+    b->x = bcarve<float>(b, 4 * ms * b->d);
+    b->h = bcarve<float>(b, 4 * ms * b->d);
+    b->q = bcarve<float>(b, 4 * ms * b->q_dim);
+    b->att = bcarve<float>(b, 4 * ms * b->q_dim);
+    b->swi = bcarve<float>(b, 4 * ms * b->I);
+    b->logits = bcarve<float>(b, 4 * ms * b->V);
+    b->token = bcarve<int32_t>(b, 4 * ms);
+    b->n_prompt = bcarve<int32_t>(b, 4 * ms);
+    b->next = bcarve<int32_t>(b, 4 * ms);
+    b->prompt = bcarve<int32_t>(b, 4 * ms * b->S);
+    b->history = bcarve<int32_t>(b, 4 * ms * b->S);
+    b->mha_ws = bcarve<void>(b, mha_paged_workspace_bytes(b->max_seqs, b->H, b->KVH, b->hd));
+    // the two arrays that start at -1 (no position, no page) come last: one memset of 0xFF covers both
+    b->pos = bcarve<int32_t>(b, 4 * ms);
+    b->block_table = bcarve<int32_t>(b, 4 * ms * b->pages->max_pages);
+}
+
+static size_t wbytes(int dtype, int64_t n) { return dtype == SLLM_F32 ? 4 * (size_t)n : dtype == SLLM_BF16 ? 2 * (size_t)n : (size_t)n; }
+
+// ------------------------------------------------------------------------------------------ small kernels ---
+__global__ void batch_embed_kernel(const int32_t* __restrict__ token, const int32_t* __restrict__ pos, const void* __restrict__ table,
+                                   int w_dtype, const float* __restrict__ scales, int group, float* __restrict__ x, int vocab, int d) {
+    const int slot = blockIdx.y;
+    const bool live = pos[slot] >= 0;
+    const int tok = min(max(token[slot], 0), vocab - 1);
+    const int64_t base = (int64_t)tok * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+        float v = 0.f;   // a slot that is not in use carries zeros through the step
+        if (live) {
+            if (w_dtype == SLLM_F32) v = reinterpret_cast<const float*>(table)[base + i];
+            else if (w_dtype == SLLM_BF16) v = __uint_as_float((uint32_t) reinterpret_cast<const uint16_t*>(table)[base + i] << 16);
+            else v = (float)reinterpret_cast<const int8_t*>(table)[base + i] * scales[(base + i) / group];
+        }
+        x[(size_t)slot * d + i] = v;
+    }
+}
+
+__device__ __forceinline__ void first_max(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }   // first maximum, argmax.cpp:11
+}
+
+// One CTA per slot: arg-max of the slot's logits, then the predict loop's feedback (model.cpp:157-185): prompt tokens
+// are fed verbatim while pos + 1 < n_prompt, afterwards the arg-max; history[p] = the token that followed position p.
+constexpr int kArgmaxThreads = 1024;
+__global__ void __launch_bounds__(kArgmaxThreads)
+batch_argmax_feedback_kernel(const float* __restrict__ logits, int V, int32_t* __restrict__ token, int32_t* __restrict__ pos,
+                             const int32_t* __restrict__ n_prompt, int32_t* __restrict__ next, const int32_t* __restrict__ prompt,
+                             int32_t* __restrict__ history, int S) {
+    __shared__ float sv[kArgmaxThreads / 32];
+    __shared__ int si[kArgmaxThreads / 32];
+    const int slot = blockIdx.x;
+    const int p = pos[slot];
+    if (p < 0) return;   // uniform over the CTA
+    const float* lg = logits + (size_t)slot * V;
+    float v = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += kArgmaxThreads) first_max(v, idx, lg[i], i);
+    for (int o = 16; o > 0; o >>= 1) first_max(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = v; si[warp] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kArgmaxThreads / 32; ++w) first_max(v, idx, sv[w], si[w]);
+        if (idx == 0x7fffffff) idx = 0;
+        const int nxt = (p + 1 < n_prompt[slot]) ? prompt[(size_t)slot * S + p + 1] : idx;
+        next[slot] = idx;
+        history[(size_t)slot * S + p] = nxt;
+        token[slot] = nxt;
+        pos[slot] = p + 1;
+    }
+}
+
+__global__ void batch_set_slot_kernel(int32_t* token, int32_t* pos, int32_t* n_prompt, int slot, int tok, int p, int np) {
+    token[slot] = tok;
+    pos[slot] = p;
+    n_prompt[slot] = np;
+}
+
+// ------------------------------------------------------------------------------------------ GEMV launches ---
+template <int WD, int NB, class Policy>
+static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units) {
+    const size_t smem = bgemv_smem_bytes(p.cols_, p.nb_);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SLLM_REQUIRE(smem <= (size_t)smem_optin_bytes(), SLLM_ENOTSUP, "%d activation vectors of %d floats do not fit shared memory", p.nb_, p.cols_);
+        SLLM_CUDA(cudaFuncSetAttribute(bgemv_kernel<WD, NB, Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int per_sm = (smem + 1024) * 2 <= (size_t)smem_optin_bytes() ? 2 : 1;   // CTAs of this size that fit one SM
+    LaunchCfg lc(dim3(gemv_grid(units, per_sm)), dim3(kGemvThreads), smem, b->stream, false);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, bgemv_kernel<WD, NB, Policy>, p));
+    g_launches++;
+    b->total_launches++;
+    return SLLM_OK;
+}
+
+template <int WD, class Policy>
+static int launch_bgemv(sllm_batch* b, Policy& p, int units) {
+    if (p.nb_ <= 1) return launch_bgemv_nb<WD, 1>(b, p, units);
+    if (p.nb_ <= 2) return launch_bgemv_nb<WD, 2>(b, p, units);
+    if (p.nb_ <= 4) return launch_bgemv_nb<WD, 4>(b, p, units);
+    return launch_bgemv_nb<WD, kBatchMaxNb>(b, p, units);
+}
+
+// activation vectors of `cols` floats one launch can stage
+static int fit_nb(int cols) {
+    int nb = kBatchMaxNb;
+    while (nb > 1 && bgemv_smem_bytes(cols, nb) > (size_t)smem_optin_bytes()) --nb;
+    return nb;
+}
+
+static const void* layer_w(const sllm_batch* b, const void* w, int64_t rows, int64_t cols, int l) {
+    return reinterpret_cast<const uint8_t*>(w) + wbytes(b->ev.w_dtype, (int64_t)l * rows * cols);
+}
+static const float* layer_sc(const sllm_batch* b, const float* sc, int64_t rows, int64_t cols, int l) {
+    return sc ? sc + (int64_t)l * rows * cols / b->ev.group : nullptr;
+}
+
+// one token for every live slot among the first `hi`
+template <int WD>
+static int enqueue_batch_step(sllm_batch* b, int hi) {
+    const EngineView& ev = b->ev;
+    const int d = b->d, L = b->L, I = b->I, V = b->V, q_dim = b->q_dim, kv_dim = b->kv_dim;
+    PagedKv pk{};
+    pk.block_table = b->block_table; pk.pos = b->pos; pk.max_pages = b->pages->max_pages; pk.page_len = b->pages->page_len;
+    pk.layers = L; pk.q_stride = q_dim; pk.heads = b->H;
+    const int nsplit = mha_paged_nsplit(b->KVH, hi, b->S);
+    const int g_d = fit_nb(d), g_q = fit_nb(q_dim), g_i = fit_nb(I);
+
+    {
+        dim3 grid(std::max(1, std::min((d + 255) / 256, 64)), hi);
+        batch_embed_kernel<<<grid, 256, 0, b->stream>>>(b->token, b->pos, ev.emb, ev.w_dtype, ev.emb_sc, ev.group, b->x, V, d);
+        SLLM_LAUNCH_CHECK();
+        g_launches++;
+        b->total_launches++;
+    }
+    for (int l = 0; l < L; ++l) {
+        for (int b0 = 0; b0 < hi; b0 += g_d) {   // A
+            BQkvPolicy<WD> A{};
+            A.W_ = layer_w(b, ev.wqkv, q_dim + 2 * kv_dim, d, l); A.sc_ = layer_sc(b, ev.wqkv_sc, q_dim + 2 * kv_dim, d, l);
+            A.grp_ = ev.group; A.cols_ = d; A.nb_ = std::min(g_d, hi - b0); A.b0 = b0;
+            A.x = b->x; A.norm_w = ev.norms + (int64_t)(2 * l) * d; A.eps = ev.shape.eps; A.sin_t = ev.sin_t; A.cos_t = ev.cos_t;
+            A.q_out = b->q; A.k_pool = b->k_pool; A.v_pool = b->v_pool; A.pk = pk; A.layer = l; A.kv_dtype = b->kv_dtype;
+            A.q_dim = q_dim; A.kv_dim = kv_dim; A.hd = b->hd;
+            if (int rc = launch_bgemv<WD>(b, A, (q_dim + 2 * kv_dim) / 2)) return rc;
+        }
+        if (int rc = mha_paged_dispatch(b->q, b->k_pool, b->v_pool, b->kv_dtype, b->att, b->mha_ws, l, pk, hi, b->max_seqs, nsplit, b->hd,
+                                        b->KVH, b->stream)) return rc;   // B
+        b->total_launches++;
+        for (int b0 = 0; b0 < hi; b0 += g_q) {   // C: h = x + Wo.att
+            BResidualPolicy<WD> C{};
+            C.W_ = layer_w(b, ev.wo, d, q_dim, l); C.sc_ = layer_sc(b, ev.wo_sc, d, q_dim, l);
+            C.grp_ = ev.group; C.cols_ = q_dim; C.nb_ = std::min(g_q, hi - b0); C.b0 = b0;
+            C.x = b->att; C.resid = b->x; C.y = b->h; C.nrows = d;
+            if (int rc = launch_bgemv<WD>(b, C, (d + 1) / 2)) return rc;
+        }
+        for (int b0 = 0; b0 < hi; b0 += g_d) {   // D
+            BGateUpPolicy<WD> D{};
+            D.W_ = layer_w(b, ev.wug, 2 * (int64_t)I, d, l); D.sc_ = layer_sc(b, ev.wug_sc, 2 * (int64_t)I, d, l);
+            D.grp_ = ev.group; D.cols_ = d; D.nb_ = std::min(g_d, hi - b0); D.b0 = b0;
+            D.h = b->h; D.norm_w = ev.norms + (int64_t)(2 * l + 1) * d; D.eps = ev.shape.eps; D.s_out = b->swi; D.inter = I;
+            if (int rc = launch_bgemv<WD>(b, D, I)) return rc;
+        }
+        for (int b0 = 0; b0 < hi; b0 += g_i) {   // E: x = Wdown.s + h
+            BResidualPolicy<WD> E{};
+            E.W_ = layer_w(b, ev.wdown, d, I, l); E.sc_ = layer_sc(b, ev.wdown_sc, d, I, l);
+            E.grp_ = ev.group; E.cols_ = I; E.nb_ = std::min(g_i, hi - b0); E.b0 = b0;
+            E.x = b->swi; E.resid = b->h; E.y = b->x; E.nrows = d;
+            if (int rc = launch_bgemv<WD>(b, E, (d + 1) / 2)) return rc;
+        }
+    }
+    for (int b0 = 0; b0 < hi; b0 += g_d) {   // F
+        BClsPolicy<WD> F{};
+        F.W_ = ev.emb; F.sc_ = ev.emb_sc; F.grp_ = ev.group; F.cols_ = d; F.nb_ = std::min(g_d, hi - b0); F.b0 = b0;
+        F.x = b->x; F.norm_w = ev.norms + (int64_t)(2 * L) * d; F.eps = ev.shape.eps; F.logits = b->logits; F.nrows = V;
+        if (int rc = launch_bgemv<WD>(b, F, (V + 1) / 2)) return rc;
+    }
+    batch_argmax_feedback_kernel<<<hi, kArgmaxThreads, 0, b->stream>>>(b->logits, V, b->token, b->pos, b->n_prompt, b->next, b->prompt,
+                                                                      b->history, b->S);
+    SLLM_LAUNCH_CHECK();
+    g_launches++;
+    b->total_launches++;
+    return SLLM_OK;
+}
+
+static int live_hi(const sllm_batch* b) {
+    int hi = 0;
+    for (int s = 0; s < b->max_seqs; ++s)
+        if (b->host_pos[s] >= 0) hi = s + 1;
+    return hi;
+}
+
+extern "C" {
+
+int sllm_batch_create(sllm_engine* e, int32_t max_seqs, int32_t page_len, int32_t n_pages, int32_t kv_dtype, sllm_batch** out) {
+    SLLM_REQUIRE(e && out, SLLM_EINVAL, "batch_create: null argument");
+    SLLM_REQUIRE(max_seqs >= 1 && max_seqs <= kBatchMaxSeqs, SLLM_EINVAL, "batch_create: max_seqs=%d outside [1, %d]", max_seqs, kBatchMaxSeqs);
+    SLLM_REQUIRE(page_len >= 1 && n_pages >= 1, SLLM_EINVAL, "batch_create: page_len=%d, n_pages=%d must be positive", page_len, n_pages);
+    SLLM_REQUIRE(kv_dtype == SLLM_F32 || kv_dtype == SLLM_BF16, SLLM_EINVAL, "batch_create: bad kv dtype %d", kv_dtype);
+    EngineView ev{};
+    if (int rc = engine_view(e, &ev)) return rc;
+    SLLM_REQUIRE(ev.weights_loaded, SLLM_ESTATE, "batch_create: the engine's weights are not loaded");
+    SLLM_REQUIRE(ev.tp == 1, SLLM_ENOTSUP, "batched decode is single-GPU (tensor-parallel size %d)", ev.tp);
+    SLLM_REQUIRE(!ev.mega, SLLM_ENOTSUP, "batched decode reads row-major weights: create the engine without SLLM_ENGINE_MEGAKERNEL (its matrices are tiled)");
+    auto* b = new sllm_batch();
+    b->ev = ev;
+    b->stream = ev.stream;
+    b->max_seqs = max_seqs;
+    b->kv_dtype = kv_dtype;
+    b->esz_kv = kv_dtype == SLLM_F32 ? 4 : 2;
+    const sllm_shape& s = ev.shape;
+    b->d = s.hidden; b->hd = s.head_dim; b->L = s.layers; b->S = s.max_len; b->V = s.vocab; b->H = s.heads; b->KVH = s.kv_heads; b->I = s.inter;
+    b->q_dim = s.heads * s.head_dim; b->kv_dim = s.kv_heads * s.head_dim;
+    b->pages = sllm_kvpages_create(n_pages, page_len, max_seqs, (s.max_len + page_len - 1) / page_len);
+    if (!b->pages) { delete b; return SLLM_EINVAL; }
+    b->host_pos.assign(max_seqs, -1);
+    batch_layout(b);   // measure
+    b->arena_bytes = (b->arena_used + ((size_t)1 << 20) - 1) >> 20 << 20;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (b->arena_bytes > free_b) {
+        set_error("batch needs %zu MiB of HBM (%d pages of %d positions), %zu MiB free", b->arena_bytes >> 20, n_pages, page_len, free_b >> 20);
+        sllm_batch_destroy(b);
+        return SLLM_ENOMEM;
+    }
+    if (cudaMalloc(&b->arena, b->arena_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc(%zu MiB) failed", b->arena_bytes >> 20);
+        sllm_batch_destroy(b);
+        return SLLM_ENOMEM;
+    }
+    batch_layout(b);   // assign
+    uint8_t* minus1 = reinterpret_cast<uint8_t*>(b->pos);
+    cudaError_t ce = cudaMemsetAsync(b->arena, 0, minus1 - b->arena, b->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(minus1, 0xFF, b->arena + b->arena_used - minus1, b->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    if (ce != cudaSuccess) { cuda_fail(ce, "batch init", __FILE__, __LINE__); sllm_batch_destroy(b); return (int)ce; }
+    *out = b;
+    return SLLM_OK;
+}
+
+void sllm_batch_destroy(sllm_batch* b) {
+    if (!b) return;
+    if (b->arena) {
+        cudaStreamSynchronize(b->stream);
+        cudaFree(b->arena);
+    }
+    sllm_kvpages_destroy(b->pages);
+    delete b;
+}
+
+int sllm_batch_add(sllm_batch* b, const int32_t* prompt_host, int32_t n_prompt, int32_t* slot_out) {
+    SLLM_REQUIRE(b && prompt_host && slot_out, SLLM_EINVAL, "batch_add: null argument");
+    SLLM_REQUIRE(n_prompt >= 1 && n_prompt <= b->S, SLLM_EINVAL, "batch_add: prompt length %d outside [1, %d]", n_prompt, b->S);
+    for (int i = 0; i < n_prompt; ++i)
+        SLLM_REQUIRE(prompt_host[i] >= 0 && prompt_host[i] < b->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", prompt_host[i], b->V);
+    int slot = -1;
+    for (int s = 0; s < b->max_seqs && slot < 0; ++s)
+        if (b->host_pos[s] < 0) slot = s;
+    SLLM_REQUIRE(slot >= 0, SLLM_ESTATE, "batch_add: all %d slots are in use", b->max_seqs);
+    // pageable source: the runtime stages it before returning, so the caller's buffer is free afterwards
+    SLLM_CUDA(cudaMemcpyAsync(b->prompt + (size_t)slot * b->S, prompt_host, sizeof(int32_t) * (size_t)n_prompt, cudaMemcpyHostToDevice, b->stream));
+    batch_set_slot_kernel<<<1, 1, 0, b->stream>>>(b->token, b->pos, b->n_prompt, slot, prompt_host[0], 0, n_prompt);
+    SLLM_LAUNCH_CHECK();
+    g_launches++;
+    b->total_launches++;
+    b->host_pos[slot] = 0;
+    *slot_out = slot;
+    return SLLM_OK;
+}
+
+int sllm_batch_remove(sllm_batch* b, int32_t slot) {
+    SLLM_REQUIRE(b && slot >= 0 && slot < b->max_seqs && b->host_pos[slot] >= 0, SLLM_EINVAL, "batch_remove: slot %d is not in use", slot);
+    batch_set_slot_kernel<<<1, 1, 0, b->stream>>>(b->token, b->pos, b->n_prompt, slot, 0, -1, 0);
+    SLLM_LAUNCH_CHECK();
+    g_launches++;
+    b->total_launches++;
+    // the pages may be handed to another sequence right away: everything that touches them is ordered on the stream
+    b->pages->release(slot);
+    b->host_pos[slot] = -1;
+    return SLLM_OK;
+}
+
+int sllm_batch_step(sllm_batch* b, int32_t n_steps) {
+    SLLM_REQUIRE(b && n_steps >= 0, SLLM_EINVAL, "batch_step: bad argument");
+    const int hi = live_hi(b);
+    if (hi == 0 || n_steps == 0) return SLLM_OK;
+    // pages for every position the n steps will write, for all slots or for none
+    int extra_total = 0;
+    for (int s = 0; s < hi; ++s) {
+        if (b->host_pos[s] < 0) continue;
+        SLLM_REQUIRE(b->host_pos[s] + n_steps <= b->S, SLLM_EINVAL, "batch_step: slot %d at position %d cannot take %d more steps (max_len %d): remove it first",
+                     s, b->host_pos[s], n_steps, b->S);
+        extra_total += b->pages->extra_needed(s, b->host_pos[s] + n_steps);
+    }
+    SLLM_REQUIRE(extra_total <= sllm_kvpages_free_count(b->pages), SLLM_ENOMEM, "out of KV pages: %d steps need %d more pages, %d free", n_steps,
+                 extra_total, sllm_kvpages_free_count(b->pages));
+    for (int s = 0; s < hi; ++s) {
+        if (b->host_pos[s] < 0) continue;
+        const int extra = b->pages->extra_needed(s, b->host_pos[s] + n_steps);
+        if (extra == 0) continue;
+        b->pages->take(s, extra);
+        const size_t row = (size_t)s * b->pages->max_pages;
+        SLLM_CUDA(cudaMemcpyAsync(b->block_table + row, b->pages->table.data() + row, sizeof(int32_t) * (size_t)b->pages->max_pages,
+                                  cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before the call returns
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        int rc;
+        switch (b->ev.w_dtype) {
+            case SLLM_F32: rc = enqueue_batch_step<SLLM_F32>(b, hi); break;
+            case SLLM_BF16: rc = enqueue_batch_step<SLLM_BF16>(b, hi); break;
+            default: rc = enqueue_batch_step<SLLM_INT8>(b, hi); break;
+        }
+        if (rc) return rc;
+        for (int s = 0; s < hi; ++s)
+            if (b->host_pos[s] >= 0) b->host_pos[s] += 1;
+    }
+    return SLLM_OK;
+}
+
+int sllm_batch_read(sllm_batch* b, int32_t slot, int32_t* tokens_out_host, int32_t max_tokens, int32_t* n_out) {
+    SLLM_REQUIRE(b && tokens_out_host && slot >= 0 && slot < b->max_seqs && b->host_pos[slot] >= 0 && max_tokens >= 0, SLLM_EINVAL,
+                 "batch_read: bad argument (slot %d)", slot);
+    const int n = std::min((int)max_tokens, b->host_pos[slot]);
+    if (n > 0)
+        SLLM_CUDA(cudaMemcpyAsync(tokens_out_host, b->history + (size_t)slot * b->S, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    SLLM_CUDA(cudaStreamSynchronize(b->stream));
+    if (n_out) *n_out = n;
+    return SLLM_OK;
+}
+
+int sllm_batch_logits(sllm_batch* b, int32_t slot, float* logits_host) {
+    SLLM_REQUIRE(b && logits_host && slot >= 0 && slot < b->max_seqs && b->host_pos[slot] > 0, SLLM_EINVAL, "batch_logits: slot %d has not stepped", slot);
+    SLLM_CUDA(cudaMemcpyAsync(logits_host, b->logits + (size_t)slot * b->V, sizeof(float) * (size_t)b->V, cudaMemcpyDeviceToHost, b->stream));
+    SLLM_CUDA(cudaStreamSynchronize(b->stream));
+    return SLLM_OK;
+}
+
+int32_t sllm_batch_free_pages(const sllm_batch* b) { return b ? sllm_kvpages_free_count(b->pages) : 0; }
+int32_t sllm_batch_position(const sllm_batch* b, int32_t slot) { return (b && slot >= 0 && slot < b->max_seqs) ? b->host_pos[slot] : -1; }
+int64_t sllm_batch_total_launches(const sllm_batch* b) { return b ? b->total_launches : 0; }
+
+int64_t sllm_batch_step_bytes(const sllm_batch* b) {
+    if (!b) return 0;
+    const double bw = b->ev.w_dtype == SLLM_F32 ? 4.0 : b->ev.w_dtype == SLLM_BF16 ? 2.0 : 1.0 + 4.0 / b->ev.group;
+    const double d = b->d, kv = b->kv_dim, I = b->I, L = b->L, V = b->V;
+    double bytes = bw * (V * d + L * (2 * d * d + 2 * kv * d + 3 * I * d)) + 4.0 * (2 * L + 1) * d;   // every weight once per STEP
+    for (int s = 0; s < b->max_seqs; ++s) {
+        if (b->host_pos[s] < 0) continue;
+        bytes += bw * d + (double)b->esz_kv * 2 * L * kv * (b->host_pos[s] + 1) + (double)b->esz_kv * 2 * L * kv;   // per sequence
+    }
+    return (int64_t)bytes;
+}
+
+}  // extern "C"

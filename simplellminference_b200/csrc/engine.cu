@@ -16,6 +16,7 @@
 #include <cstring>
 #include <vector>
 
+#include "engine_view.cuh"
 #include "megakernel.cuh"
 #include "prefill.cuh"
 
@@ -641,6 +642,27 @@ static int finish_weights(sllm_engine* e) {
 }
 
 // -------------------------------------------------------------------------------------------- C ABI ----
+namespace sllm {
+int engine_view(const sllm_engine* e, EngineView* v) {
+    SLLM_REQUIRE(e && v, SLLM_EINVAL, "engine_view: null argument");
+    v->shape = e->cfg.shape;
+    v->w_dtype = e->cfg.w_dtype;
+    v->group = e->cfg.group;
+    v->tp = e->tp;
+    v->mega = e->mega ? 1 : 0;
+    v->weights_loaded = e->weights_loaded ? 1 : 0;
+    v->stream = e->stream;
+    v->emb = e->emb.w; v->emb_sc = e->emb.sc;
+    v->norms = e->norms;
+    v->wqkv = e->wqkv.w; v->wqkv_sc = e->wqkv.sc;
+    v->wo = e->wo.w; v->wo_sc = e->wo.sc;
+    v->wug = e->wug.w; v->wug_sc = e->wug.sc;
+    v->wdown = e->wdown.w; v->wdown_sc = e->wdown.sc;
+    v->sin_t = e->sin_t; v->cos_t = e->cos_t;
+    return SLLM_OK;
+}
+}  // namespace sllm
+
 extern "C" {
 
 int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm_engine** out) {

@@ -12,12 +12,18 @@
 // are merged by whichever CTA of the KV head finishes last (atomic ticket), so there is no second kernel and
 // no host-visible scratch besides `workspace`.
 //
+// The same body serves the batched multi-sequence decode over a PAGED cache (batch.cu): grid.z = sequence slot, every
+// slot has its own position, and a cache row is found through the slot's block table (pool layout
+// [pages][layers][kv_heads][page_len][hd]: the rows of one (page, layer, head) are contiguous). PAGED is a compile-time
+// switch; the dense instantiation is the kernel above, unchanged.
+//
 // Numerics: fp32 scores and accumulators, accurate expf, score = (q.k) * (1/sqrt(hd)) applied after the sum
 // like the reference (matmul_kernel.cpp:26 via mha_kernel.cpp:59). Only the summation order differs from the
 // oracle's serial loops.
 #include <cmath>
 
 #include "common.cuh"
+#include "paged_kv.cuh"
 
 namespace sllm {
 
@@ -105,11 +111,12 @@ __device__ __forceinline__ void unpack16(const uint4 v, float* f) {
 }
 
 // G = query heads per KV head (compile-time so the accumulators live in registers)
-template <int KVD, int G>
-__global__ void __launch_bounds__(kMhaThreads)
-mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, const uint8_t* __restrict__ vc,
-                  float* __restrict__ out, float* __restrict__ partials, int* __restrict__ counters, int layer,
-                  const int32_t* __restrict__ pos_dev, int pos_val, int max_len, int hd, int kv_heads, int nsplit) {
+template <int KVD, int G, bool PAGED>
+__device__ __forceinline__ void
+mha_decode_body(const float* __restrict__ q, const uint8_t* __restrict__ kc, const uint8_t* __restrict__ vc,
+                float* __restrict__ out, float* __restrict__ partials, int* __restrict__ counters, int layer,
+                const int32_t* __restrict__ pos_dev, int pos_val, int max_len, int hd, int kv_heads, int nsplit,
+                const PagedKv& pk) {
     constexpr int ESZ = KvInfo<KVD>::ESZ, VEC = KvInfo<KVD>::VEC;
     extern __shared__ __align__(128) uint8_t smem[];
     const MhaSmem L = mha_smem_layout(hd, G, ESZ);
@@ -133,7 +140,20 @@ mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // q and the newest cache row come from the previous kernel; pos from the previous step
-    const int pos = pos_dev ? *pos_dev : pos_val;
+    int pos;
+    const int32_t* bt = nullptr;
+    if constexpr (PAGED) {
+        const int slot = blockIdx.z;
+        pos = pk.pos[slot];
+        if (pos < 0) return;   // slot not in use (uniform over the CTA; nothing is pending on the mbarriers yet)
+        bt = pk.block_table + (size_t)slot * pk.max_pages;
+        q += (size_t)slot * pk.q_stride;
+        out += (size_t)slot * pk.q_stride;
+        partials += (size_t)slot * pk.heads * nsplit * (hd + 2);
+        counters += (size_t)slot * kv_heads;
+    } else {
+        pos = pos_dev ? *pos_dev : pos_val;
+    }
     const int n = pos + 1;
     const int per = (n + nsplit - 1) / nsplit;
     const int t0 = split * per;
@@ -152,7 +172,13 @@ mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, c
         if (lane == 0) mbar_expect_tx(&bars[stage], (uint32_t)(2 * rows * row_bytes));
         __syncwarp();
         for (int r = lane; r < rows; r += 32) {
-            const size_t g_off = head_off + (size_t)(ts + r) * kv * ESZ;
+            size_t g_off;
+            if constexpr (PAGED) {
+                const int t = ts + r, pi = t / pk.page_len;
+                g_off = paged_row_index(bt[pi], pk.layers, layer, kv_heads, kvh, pk.page_len, t - pi * pk.page_len, hd) * ESZ;
+            } else {
+                g_off = head_off + (size_t)(ts + r) * kv * ESZ;
+            }
             bulk_g2s(k_s + ((size_t)stage * kMhaTile + r) * L.stride, kc + g_off, row_bytes, &bars[stage]);
             bulk_g2s(v_s + ((size_t)stage * kMhaTile + r) * L.stride, vc + g_off, row_bytes, &bars[stage]);
         }
@@ -308,6 +334,22 @@ mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, c
 }
 
 template <int KVD, int G>
+__global__ void __launch_bounds__(kMhaThreads)
+mha_decode_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, const uint8_t* __restrict__ vc,
+                  float* __restrict__ out, float* __restrict__ partials, int* __restrict__ counters, int layer,
+                  const int32_t* __restrict__ pos_dev, int pos_val, int max_len, int hd, int kv_heads, int nsplit) {
+    mha_decode_body<KVD, G, false>(q, kc, vc, out, partials, counters, layer, pos_dev, pos_val, max_len, hd, kv_heads, nsplit, PagedKv{});
+}
+
+template <int KVD, int G>
+__global__ void __launch_bounds__(kMhaThreads)
+mha_paged_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kc, const uint8_t* __restrict__ vc,
+                 float* __restrict__ out, float* __restrict__ partials, int* __restrict__ counters, int layer, int hd,
+                 int kv_heads, int nsplit, PagedKv pk) {
+    mha_decode_body<KVD, G, true>(q, kc, vc, out, partials, counters, layer, nullptr, 0, 0, hd, kv_heads, nsplit, pk);
+}
+
+template <int KVD, int G>
 static int launch_mha(const float* q, const void* kc, const void* vc, float* out, void* ws, int layer, const int32_t* pos_dev,
                       int pos, int max_len, int hd, int kv_heads, cudaStream_t st, bool pdl) {
     const int nsplit = mha_nsplit(kv_heads, max_len);
@@ -351,6 +393,71 @@ int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_d
         SLLM_MHA_CASE(7)
         SLLM_MHA_CASE(8)
         default: SLLM_REQUIRE(false, SLLM_ENOTSUP, "mha: heads/kv_heads=%d > 8 query heads per KV head", g);
+    }
+#undef SLLM_MHA_CASE
+}
+
+// ---- paged, batched launch (batch.cu) -------------------------------------------------------------------
+// Fixed number of KV splits per slot: ~2 CTAs per SM over all slots, never more than one tile per split at max_ctx.
+int mha_paged_nsplit(int kv_heads, int slots, int max_ctx) {
+    const int ctas = kv_heads * (slots < 1 ? 1 : slots);
+    int n = (2 * sm_count() + ctas - 1) / ctas;
+    const int by_len = (max_ctx + kMhaTile - 1) / kMhaTile;
+    if (n > by_len) n = by_len;
+    if (n > kMhaMaxSplit) n = kMhaMaxSplit;
+    return n < 1 ? 1 : n;
+}
+
+static size_t paged_counter_bytes(int slots, int kv_heads) { return ((size_t)slots * kv_heads * sizeof(int) + 255) / 256 * 256; }
+
+size_t mha_paged_workspace_bytes(int slots, int heads, int kv_heads, int head_dim) {
+    return paged_counter_bytes(slots, kv_heads) + (size_t)slots * heads * kMhaMaxSplit * (head_dim + 2) * sizeof(float);
+}
+
+template <int KVD, int G>
+static int launch_mha_paged(const float* q, const void* kp, const void* vp, float* out, void* ws, int layer, const PagedKv& pk,
+                            int slots, int max_slots, int nsplit, int hd, int kv_heads, cudaStream_t st) {
+    const MhaSmem L = mha_smem_layout(hd, G, KvInfo<KVD>::ESZ);
+    SLLM_REQUIRE(L.total <= (size_t)smem_optin_bytes(), SLLM_ENOTSUP, "paged mha: tile does not fit shared memory (hd=%d)", hd);
+    static size_t configured = 0;
+    if (L.total > 48 * 1024 && L.total > configured) {
+        SLLM_CUDA(cudaFuncSetAttribute(mha_paged_kernel<KVD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        configured = L.total;
+    }
+    int* counters = reinterpret_cast<int*>(ws);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + paged_counter_bytes(max_slots, kv_heads));
+    LaunchCfg lc(dim3(kv_heads, nsplit, slots), dim3(kMhaThreads), L.total, st, false);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, mha_paged_kernel<KVD, G>, q, reinterpret_cast<const uint8_t*>(kp),
+                                 reinterpret_cast<const uint8_t*>(vp), out, partials, counters, layer, hd, kv_heads, nsplit, pk));
+    g_launches++;
+    return SLLM_OK;
+}
+
+// q / out: [slots][pk.q_stride]; pools [pages][layers][kv_heads][page_len][hd] in kv_dtype; ws: mha_paged_workspace_bytes(max_slots, ..),
+// zeroed once (the kernel leaves it zeroed); the first `slots` slots are served (unused ones carry pos < 0).
+int mha_paged_dispatch(const float* q, const void* k_pool, const void* v_pool, int kv_dtype, float* out, void* ws, int layer,
+                       const PagedKv& pk, int slots, int max_slots, int nsplit, int hd, int kv_heads, cudaStream_t st) {
+    SLLM_REQUIRE(q && k_pool && v_pool && out && ws && pk.block_table && pk.pos, SLLM_EINVAL, "paged mha: null pointer");
+    SLLM_REQUIRE(slots >= 1 && slots <= max_slots && slots <= 65535, SLLM_EINVAL, "paged mha: %d slots (max %d)", slots, max_slots);
+    SLLM_REQUIRE(pk.heads > 0 && kv_heads > 0 && pk.heads % kv_heads == 0, SLLM_EINVAL, "paged mha: heads=%d not a multiple of kv_heads=%d", pk.heads, kv_heads);
+    SLLM_REQUIRE(hd >= 16 && hd <= 256 && hd % 16 == 0, SLLM_ENOTSUP, "paged mha: head_dim=%d must be a multiple of 16 in [16,256]", hd);
+    SLLM_REQUIRE(kv_dtype == SLLM_F32 || kv_dtype == SLLM_BF16, SLLM_EINVAL, "paged mha: kv dtype %d", kv_dtype);
+    SLLM_REQUIRE(nsplit >= 1 && nsplit <= kMhaMaxSplit && pk.page_len >= 1 && pk.max_pages >= 1, SLLM_EINVAL, "paged mha: bad split/page geometry");
+    const int g = pk.heads / kv_heads;
+#define SLLM_MHA_CASE(GG)                                                                                                             \
+    case GG:                                                                                                                          \
+        return kv_dtype == SLLM_F32 ? launch_mha_paged<SLLM_F32, GG>(q, k_pool, v_pool, out, ws, layer, pk, slots, max_slots, nsplit, hd, kv_heads, st) \
+                                    : launch_mha_paged<SLLM_BF16, GG>(q, k_pool, v_pool, out, ws, layer, pk, slots, max_slots, nsplit, hd, kv_heads, st);
+    switch (g) {
+        SLLM_MHA_CASE(1)
+        SLLM_MHA_CASE(2)
+        SLLM_MHA_CASE(3)
+        SLLM_MHA_CASE(4)
+        SLLM_MHA_CASE(5)
+        SLLM_MHA_CASE(6)
+        SLLM_MHA_CASE(7)
+        SLLM_MHA_CASE(8)
+        default: SLLM_REQUIRE(false, SLLM_ENOTSUP, "paged mha: heads/kv_heads=%d > 8 query heads per KV head", g);
     }
 #undef SLLM_MHA_CASE
 }
