@@ -275,6 +275,10 @@ int sllm_batch_step(sllm_batch* b, int32_t n_steps);
 int sllm_batch_read(sllm_batch* b, int32_t slot, int32_t* tokens_out_host, int32_t max_tokens, int32_t* n_out);
 /* logits (vocab floats) of the slot's latest step. Synchronises the stream. */
 int sllm_batch_logits(sllm_batch* b, int32_t slot, float* logits_host);
+/* Introspection for parity tests: per-slot buffers under the reference's ModelBufferType numbers (include/model/model.h:14-34),
+ * each [max_seqs][...] fp32: 4 emb_output (the residual stream) [d], 6 query [q], 8 mha_output [q], 10 ffn_input [d], 14 swi_output
+ * [I], 16 model_pred [vocab]; 2 / 3 = the key / value page pools in kv_dtype. Synchronises the stream. */
+int sllm_batch_buffer(sllm_batch* b, int32_t buffer_id, void** dev_ptr, int64_t* n_elems, int32_t* dtype);
 int32_t sllm_batch_free_pages(const sllm_batch* b);
 int32_t sllm_batch_position(const sllm_batch* b, int32_t slot);   /* position of the slot's next step; -1 = free slot */
 /* algorithmic HBM bytes of the NEXT step: every weight once, plus per live sequence its embedding row, the K/V rows

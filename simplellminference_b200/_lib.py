@@ -89,6 +89,7 @@ SIGNATURES = {
     "sllm_batch_step": (C.c_int, [_P, _I]),
     "sllm_batch_read": (C.c_int, [_P, _I, _P, _I, C.POINTER(_I)]),
     "sllm_batch_logits": (C.c_int, [_P, _I, _P]),
+    "sllm_batch_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_batch_free_pages": (_I, [_P]),
     "sllm_batch_position": (_I, [_P, _I]),
     "sllm_batch_step_bytes": (_L, [_P]),

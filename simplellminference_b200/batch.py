@@ -93,6 +93,22 @@ class BatchDecoder:
         _lib.check(self.lib.sllm_batch_logits(self.h, slot, out.ctypes.data))
         return out
 
+    def buffer(self, name_or_id):
+        """Device view (no copy) of a per-slot buffer as a torch tensor [max_seqs, width] (reference ModelBufferType names);
+        the page pools ("key_cache" / "value_cache") come back as [pages, layers, kv_heads, page_len, head_dim]."""
+        import torch
+        from .engine import BUF, _CudaView, _TORCH_DT
+        bid = BUF[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        ptr, n, dt = C.c_void_p(), C.c_int64(), C.c_int32()
+        _lib.check(self.lib.sllm_batch_buffer(self.h, bid, C.byref(ptr), C.byref(n), C.byref(dt)))
+        tdt = _TORCH_DT[dt.value]
+        t = torch.as_tensor(_CudaView(ptr.value, n.value, tdt), device="cuda")
+        t = t.view(torch.bfloat16) if tdt == torch.bfloat16 else t
+        if bid in (2, 3):
+            s = self.engine.shape
+            return t.view(self.n_pages, s.layers, s.kv_heads, self.page_len, s.head_dim)
+        return t.view(self.max_seqs, -1)
+
     def position(self, slot: int) -> int:
         return int(self.lib.sllm_batch_position(self.h, slot))
 

@@ -464,6 +464,25 @@ int sllm_batch_logits(sllm_batch* b, int32_t slot, float* logits_host) {
     return SLLM_OK;
 }
 
+int sllm_batch_buffer(sllm_batch* b, int32_t id, void** dev_ptr, int64_t* n_elems, int32_t* dtype) {
+    SLLM_REQUIRE(b && dev_ptr && n_elems && dtype, SLLM_EINVAL, "batch_buffer: null argument");
+    const int64_t ms = b->max_seqs;
+    *dtype = SLLM_F32;
+    switch (id) {
+        case 2: *dev_ptr = b->k_pool; *dtype = b->kv_dtype; *n_elems = (int64_t)b->pages->n_pages * b->L * b->KVH * b->pages->page_len * b->hd; break;
+        case 3: *dev_ptr = b->v_pool; *dtype = b->kv_dtype; *n_elems = (int64_t)b->pages->n_pages * b->L * b->KVH * b->pages->page_len * b->hd; break;
+        case 4: *dev_ptr = b->x; *n_elems = ms * b->d; break;
+        case 6: *dev_ptr = b->q; *n_elems = ms * b->q_dim; break;
+        case 8: *dev_ptr = b->att; *n_elems = ms * b->q_dim; break;
+        case 10: *dev_ptr = b->h; *n_elems = ms * b->d; break;
+        case 14: *dev_ptr = b->swi; *n_elems = ms * b->I; break;
+        case 16: *dev_ptr = b->logits; *n_elems = ms * b->V; break;
+        default: SLLM_REQUIRE(false, SLLM_EINVAL, "batch_buffer: unknown buffer id %d", id);
+    }
+    SLLM_CUDA(cudaStreamSynchronize(b->stream));
+    return SLLM_OK;
+}
+
 int32_t sllm_batch_free_pages(const sllm_batch* b) { return b ? sllm_kvpages_free_count(b->pages) : 0; }
 int32_t sllm_batch_position(const sllm_batch* b, int32_t slot) { return (b && slot >= 0 && slot < b->max_seqs) ? b->host_pos[slot] : -1; }
 int64_t sllm_batch_total_launches(const sllm_batch* b) { return b ? b->total_launches : 0; }

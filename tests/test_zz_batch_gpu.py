@@ -1,0 +1,183 @@
+"""GPU parity tests of the batched multi-sequence decode over a paged KV cache (sllm_batch_*).
+
+The reference decodes one sequence at a time, so the oracle of a batch is the oracle run once per sequence: every
+sequence of a batch — whatever its neighbours, its slot, its pages and the moment it was admitted — must produce the
+token stream the CPU oracle produces for that sequence alone (IDENTICAL tokens), with final logits inside the decode
+tolerance of tests/test_engine_gpu.py (3e-4 * max(1, max|logit|) for fp32 cache rows, 5e-3 with a bf16 cache).
+
+(The file sorts last on purpose: it is the newest subsystem; a failure here must not hide the rest of the suite.)"""
+import numpy as np
+import pytest
+
+from conftest import oracle_shape
+from simplellminference_b200 import _lib
+from simplellminference_b200.batch import BatchDecoder
+from simplellminference_b200.config import F32, BF16, INT8, PRESETS, ModelShape
+from simplellminference_b200.engine import Engine
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def logit_tol(want, kv_dtype):
+    return (3e-4 if kv_dtype == F32 else 5e-3) * max(1.0, float(np.abs(want).max()))
+
+
+def run_ragged(port, ms, wd, kvd, seed, prompts, joins, n_steps, page_len, max_seqs, n_pages=None):
+    """Sequence i is admitted before step joins[i] and then steps with the others until step n_steps. Returns the engine's
+    batch so that callers can look further; asserts tokens and final logits against the oracle of each sequence alone."""
+    shape = oracle_shape(ms)
+    blob = port.fill_blob(shape, seed, wd, 64)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd).load_synthetic(seed)
+    bd = BatchDecoder(eng, max_seqs=max_seqs, page_len=page_len, n_pages=n_pages, kv_dtype=kvd)
+    slots = {}
+    for step in range(n_steps):
+        for i, j in enumerate(joins):
+            if j == step:
+                slots[i] = bd.add(prompts[i])
+        bd.step(1)
+    for i, prompt in enumerate(prompts):
+        n = n_steps - joins[i]                       # steps this sequence took = tokens after its prompt[0]
+        want, want_l = port.model(shape, blob, kv_bf16=(kvd == BF16)).greedy(prompt, n + 1)
+        got = bd.tokens(slots[i])
+        assert bd.position(slots[i]) == n
+        assert np.array_equal(got, want), (i, np.flatnonzero(got != want)[:5], got[:8], want[:8])
+        err = float(np.abs(bd.logits(slots[i]) - want_l).max())
+        assert err <= logit_tol(want_l, kvd), (i, err)
+    return eng, bd, slots
+
+
+@pytest.mark.parametrize("wd,kvd", [(F32, F32), (BF16, F32), (INT8, F32), (BF16, BF16)])
+def test_ragged_batch_matches_oracle_per_sequence(port, wd, kvd):
+    """Five sequences of different prompt lengths admitted at different steps (GQA shape, pages of 4 positions)."""
+    ms = PRESETS["tiny_gqa"]
+    prompts = [[1, 7, 300], [5], [9, 2, 44, 17, 3, 8], [100, 200], [3]]
+    eng, bd, _ = run_ragged(port, ms, wd, kvd, 1234, prompts, joins=[0, 0, 3, 10, 25], n_steps=40, page_len=4, max_seqs=6)
+    bd.close(); eng.close()
+
+
+def test_head_dim_48_and_page_of_one_position(port):
+    """MHA shape with head_dim 48 (not a power of two), fp32 everywhere, the smallest possible page."""
+    ms = PRESETS["tiny_mha_hd48"]
+    eng, bd, _ = run_ragged(port, ms, F32, F32, 42, [[5], [7, 8, 9], [250, 1]], joins=[0, 1, 2], n_steps=30, page_len=1, max_seqs=3)
+    bd.close(); eng.close()
+
+
+def test_more_sequences_than_one_launch_holds(port):
+    """Eleven sequences: the GEMV launcher goes through the slots in groups of 8 + 3."""
+    ms = PRESETS["tiny_gqa"]
+    rng = np.random.default_rng(8)
+    prompts = [rng.integers(1, ms.vocab, size=int(rng.integers(1, 6))).tolist() for _ in range(11)]
+    eng, bd, _ = run_ragged(port, ms, BF16, F32, 7, prompts, joins=[0] * 11, n_steps=24, page_len=8, max_seqs=11)
+    bd.close(); eng.close()
+
+
+def test_retire_and_readmit_recycles_slots_and_pages(port):
+    """A retired sequence's slot and pages go to the next admission; the survivors are undisturbed."""
+    ms = PRESETS["tiny_gqa"]
+    shape = oracle_shape(ms)
+    blob = port.fill_blob(shape, 11)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_synthetic(11)
+    # 3 slots, pages of 4, and only as many pages as the test needs at its fullest moment (3 sequences of <= 20 positions)
+    bd = BatchDecoder(eng, max_seqs=3, page_len=4, n_pages=15, kv_dtype=F32)
+    a, b, c = bd.add([3]), bd.add([4, 5]), bd.add([6, 7, 8])
+    assert (a, b, c) == (0, 1, 2)
+    bd.step(12)
+    free_before = bd.free_pages
+    want_b, _ = port.model(shape, blob).greedy([4, 5], 13)
+    assert np.array_equal(bd.tokens(b), want_b)
+    bd.remove(b)
+    assert bd.position(b) == -1 and bd.free_pages == free_before + 3       # 12 positions = 3 pages came back
+    with pytest.raises(_lib.SllmError):
+        bd.tokens(b)
+    d = bd.add([9, 9, 9, 9])
+    assert d == b                                                          # lowest free slot
+    bd.step(8)
+    for slot, prompt, n in ((a, [3], 20), (c, [6, 7, 8], 20), (d, [9, 9, 9, 9], 8)):
+        want, want_l = port.model(shape, blob).greedy(prompt, n + 1)
+        assert np.array_equal(bd.tokens(slot), want), slot
+        assert float(np.abs(bd.logits(slot) - want_l).max()) <= logit_tol(want_l, F32)
+    # the pool is now short for 3 more pages: all or nothing, nothing enqueued, positions unchanged
+    assert bd.free_pages == 15 - (5 + 5 + 2)
+    bd.step(4)                                                             # a, c: 24 positions = 6 pages; d: 12 = 3 pages -> 15 used
+    assert bd.free_pages == 0
+    with pytest.raises(_lib.SllmError) as ei:
+        bd.step(1)
+    assert ei.value.code == _lib.ENOMEM and [bd.position(s) for s in (a, c, d)] == [24, 24, 12]
+    bd.remove(a)
+    bd.step(1)
+    assert [bd.position(s) for s in (c, d)] == [25, 13]
+    want, _ = port.model(shape, blob).greedy([6, 7, 8], 26)
+    assert np.array_equal(bd.tokens(c), want)
+    bd.close(); eng.close()
+
+
+def test_batch_of_one_equals_the_engine(port):
+    """A single sequence through the batched path against the per-kernel engine path. The batched GEMV accumulates in
+    the order of the one-sequence kernel and, at position 0, attention is the identity on the one value row, so the
+    first step agrees to rounding noise of the epilogues (1e-6 relative; in practice bit for bit); then the same tokens."""
+    ms = PRESETS["tiny_gqa"]
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32).load_synthetic(5)
+    bd = BatchDecoder(eng, max_seqs=2, page_len=16, kv_dtype=F32)
+    s = bd.add([17])
+    bd.step(1)
+    got = bd.logits(s)
+    want, nxt = eng.forward(17, 0)
+    assert float(np.abs(got - want).max()) <= 1e-6 * max(1.0, float(np.abs(want).max()))
+    assert int(bd.tokens(s)[0]) == nxt
+    q_b, q_e = bd.buffer("query")[s].cpu().numpy(), eng.buffer("query").cpu().numpy()[:ms.hidden]
+    assert float(np.abs(q_b - q_e).max()) <= 1e-6 * max(1.0, float(np.abs(q_e).max()))
+    bd.step(30)
+    assert np.array_equal(bd.tokens(s), eng.greedy([17], 32))
+    bd.close(); eng.close()
+
+
+def test_argument_and_state_errors(port):
+    ms = PRESETS["tiny_gqa"]
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_synthetic(1)
+    mega = Engine(ms, w_dtype=F32, kv_dtype=F32, mega=True).load_synthetic(1)
+    if mega.mode.startswith("megakernel"):
+        with pytest.raises(_lib.SllmError) as ei:
+            BatchDecoder(mega, max_seqs=2)
+        assert ei.value.code == _lib.ENOTSUP
+    mega.close()
+    for bad in (dict(max_seqs=0), dict(max_seqs=65), dict(max_seqs=2, page_len=0, n_pages=4), dict(max_seqs=2, n_pages=0)):
+        with pytest.raises(_lib.SllmError):
+            BatchDecoder(eng, **bad)
+    bd = BatchDecoder(eng, max_seqs=2, page_len=8, kv_dtype=F32)
+    bd.step(3)                                   # no live sequence: nothing to do
+    with pytest.raises(_lib.SllmError):
+        bd.add([ms.vocab])                       # token outside the vocabulary
+    with pytest.raises(_lib.SllmError):
+        bd.add(list(range(1, ms.max_len + 2)))   # prompt longer than max_len
+    s0, s1 = bd.add([1]), bd.add([2])
+    with pytest.raises(_lib.SllmError) as ei:
+        bd.add([3])
+    assert ei.value.code == _lib.ESTATE
+    with pytest.raises(_lib.SllmError):
+        bd.logits(s0)                            # has not stepped yet
+    bd.step(ms.max_len)                          # to the last position
+    assert bd.position(s0) == ms.max_len
+    with pytest.raises(_lib.SllmError) as ei:
+        bd.step(1)
+    assert ei.value.code == _lib.EINVAL
+    with pytest.raises(_lib.SllmError):
+        bd.remove(5)
+    bd.remove(s0); bd.remove(s1)
+    with pytest.raises(_lib.SllmError):
+        bd.remove(s0)
+    bd.close(); eng.close()
+
+
+def test_step_bytes_share_the_weights(port):
+    """B(p) of a batch = the one-sequence B(p) with the weight term counted once."""
+    ms = PRESETS["tiny_gqa"]
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16).load_synthetic(1)
+    bd = BatchDecoder(eng, max_seqs=4, page_len=8, kv_dtype=BF16)
+    for p in ([1], [2], [3]):
+        bd.add(p)
+    bd.step(5)
+    one = ms.step_bytes(5, BF16, BF16)            # the next step of every sequence is at position 5
+    per_seq = 2 * ms.hidden + 2 * 2 * ms.layers * ms.kv_hidden * (5 + 1) + 2 * 2 * ms.layers * ms.kv_hidden   # embedding row, K/V rows read, row written
+    weights = one - per_seq
+    assert abs(bd.step_bytes() - (weights + 3 * per_seq)) <= 8
+    bd.close(); eng.close()
