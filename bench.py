@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--mega-ll", action="store_true", help="single GPU: the barrier-free {value,epoch}-word megakernel instead of the grid-barrier one")
     ap.add_argument("--nccl", action="store_true", help="tensor parallel: NCCL all-reduce instead of the fused peer-memory one")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
+    ap.add_argument("--no-batch", action="store_true", help="skip the secondary batched multi-sequence figure (tools/batch_bench.py in a child process)")
     return ap.parse_args()
 
 
@@ -210,6 +211,21 @@ def workload_config(args, ms):
                         f"{args.wdtype} weights, {args.kvdtype} KV cache, batch-1 greedy decode continuing a {args.prompt_len}-token prompt",
             "prompt_len": args.prompt_len, "weights": args.wdtype, "kv_cache": args.kvdtype, "parallelism": f"tp{args.gpus}",
             "l2": "no flush: every step streams its whole working set (weights+KV >> 126 MB L2) from HBM"}
+
+
+def batch_decode_sample(args):
+    """Secondary figure: aggregate tokens/s of the batched multi-sequence decode (sllm_batch_*, tools/batch_bench.py) on the
+    same model shape and context. Runs in a CHILD process after every timed region of this one and after its engine is
+    gone: whatever happens there (error, time-out) is reported in its place and never costs the headline numbers."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
+           "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", "1,4,8,16", "--steps", "64", "--json"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        if r.returncode != 0:
+            return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"error": repr(ex)[:300]}
 
 
 # ------------------------------------------------------------------------------------------------ our arm --
@@ -385,6 +401,11 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    step_launches = eng.step_launches
+    batch = None
+    if world == 1 and not args.no_batch:
+        eng.close()
+        batch = batch_decode_sample(args)
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -396,9 +417,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.wdtype, "data": "synthetic",
         "config": workload_config(args, ms), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(launches), "launches_per_step": eng.step_launches, "clocks": clocks,
+        "gpu_launches": int(launches), "launches_per_step": step_launches, "clocks": clocks,
         "prefill": prefill, "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
         "mode": mode + ("" if world == 1 else (" tp/nccl-allreduce" if args.nccl else " tp/peer-memory-allreduce")),
+        "batch_decode": batch,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -22,11 +22,11 @@ def logit_tol(want, kv_dtype):
     return (3e-4 if kv_dtype == F32 else 5e-3) * max(1.0, float(np.abs(want).max()))
 
 
-def run_ragged(port, ms, wd, kvd, seed, prompts, joins, n_steps, page_len, max_seqs, n_pages=None):
+def run_ragged(port, ms, wd, kvd, seed, prompts, joins, n_steps, page_len, max_seqs, n_pages=None, threads=1):
     """Sequence i is admitted before step joins[i] and then steps with the others until step n_steps. Returns the engine's
     batch so that callers can look further; asserts tokens and final logits against the oracle of each sequence alone."""
     shape = oracle_shape(ms)
-    blob = port.fill_blob(shape, seed, wd, 64)
+    blob = port.fill_blob(shape, seed, wd, 64, threads=threads)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd).load_synthetic(seed)
     bd = BatchDecoder(eng, max_seqs=max_seqs, page_len=page_len, n_pages=n_pages, kv_dtype=kvd)
     slots = {}
@@ -37,7 +37,7 @@ def run_ragged(port, ms, wd, kvd, seed, prompts, joins, n_steps, page_len, max_s
         bd.step(1)
     for i, prompt in enumerate(prompts):
         n = n_steps - joins[i]                       # steps this sequence took = tokens after its prompt[0]
-        want, want_l = port.model(shape, blob, kv_bf16=(kvd == BF16)).greedy(prompt, n + 1)
+        want, want_l = port.model(shape, blob, threads=threads, kv_bf16=(kvd == BF16)).greedy(prompt, n + 1)
         got = bd.tokens(slots[i])
         assert bd.position(slots[i]) == n
         assert np.array_equal(got, want), (i, np.flatnonzero(got != want)[:5], got[:8], want[:8])
@@ -180,4 +180,77 @@ def test_step_bytes_share_the_weights(port):
     per_seq = 2 * ms.hidden + 2 * 2 * ms.layers * ms.kv_hidden * (5 + 1) + 2 * 2 * ms.layers * ms.kv_hidden   # embedding row, K/V rows read, row written
     weights = one - per_seq
     assert abs(bd.step_bytes() - (weights + 3 * per_seq)) <= 8
+    bd.close(); eng.close()
+
+
+# ---- written after the round's GPU budget was spent: first executed by the round-end run (the tests above ran on a B200) ----
+def test_full_width_llama2_7b_two_layers_batch_of_eight(port):
+    """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers and eight sequences: the shapes
+    where the staged activations need opt-in shared memory (8 x 4096 floats = 128 KB per CTA) and where the down projection
+    (11008 inputs: 5 vectors fit) goes through the slots in groups of 5 + 3. fp32 cache pages, so that token identity does
+    not hinge on bf16 rounding boundaries."""
+    import dataclasses
+    import os
+    ms = dataclasses.replace(PRESETS["llama2-7b"], layers=2, max_len=64)
+    rng = np.random.default_rng(4)
+    prompts = [rng.integers(1, ms.vocab, size=int(rng.integers(1, 5))).tolist() for _ in range(8)]
+    eng, bd, _ = run_ragged(port, ms, BF16, F32, 9, prompts, joins=[0, 0, 0, 1, 1, 2, 3, 5], n_steps=14, page_len=16, max_seqs=8,
+                            threads=os.cpu_count() or 1)
+    assert bd.step_bytes() > 0
+    bd.close(); eng.close()
+
+
+def run_teacher_forced(port, ms, wd, kvd, seed, firsts, joins, n_steps, checkpoints, page_len, max_seqs, threads=1):
+    """Long runs: a greedy stream of hundreds of tokens meets a near-tie sooner or later (margins of 1e-3 on 300-token
+    runs of the synthetic model), so here every sequence is FED the oracle's own stream (a prompt as long as the run) and
+    the logits are compared at checkpoints: a wrong cache row, page, tile or split shows up in every later logit."""
+    shape = oracle_shape(ms)
+    blob = port.fill_blob(shape, seed, wd, 64, threads=threads)
+    fed, want = [], []
+    for i, first in enumerate(firsts):
+        om = port.model(shape, blob, threads=threads, kv_bf16=(kvd == BF16))
+        toks, at = [int(first)], {}
+        for pos in range(n_steps - joins[i]):
+            lg = om.forward(toks[pos], pos)
+            if joins[i] + pos + 1 in checkpoints:
+                at[joins[i] + pos + 1] = lg.copy()
+            toks.append(int(np.argmax(lg)))
+        fed.append(toks[:-1])
+        want.append(at)
+        om.close()
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd).load_synthetic(seed)
+    bd = BatchDecoder(eng, max_seqs=max_seqs, page_len=page_len, kv_dtype=kvd)
+    slots, step = {}, 0
+    for cp in sorted(checkpoints):
+        while step < cp:
+            for i, j in enumerate(joins):
+                if j == step:
+                    slots[i] = bd.add(fed[i])
+            nxt = min([j for j in joins if j > step] + [cp])
+            bd.step(nxt - step)              # several steps per call: pages are taken ahead for all of them
+            step = nxt
+        for i in slots:
+            w = want[i][cp]
+            err = float(np.abs(bd.logits(slots[i]) - w).max())
+            assert err <= logit_tol(w, kvd), (cp, i, err)
+    for i in slots:
+        got = bd.tokens(slots[i])
+        assert np.array_equal(got[:-1], fed[i][1:]), i                  # fed verbatim
+        assert int(got[-1]) == int(np.argmax(bd.logits(slots[i]))), i   # then the arg-max of its own logits
+    return eng, bd
+
+
+@pytest.mark.parametrize("heads,kv_heads", [(8, 8), (8, 2)])
+def test_long_context_many_slots_split_kv(port, heads, kv_heads):
+    """Contexts of up to 300 positions in 20 slots: the attention kernel runs with several KV splits per (slot, head) and
+    their in-kernel merge (8 KV heads: 160 CTAs per split -> 2 splits of up to 150 positions = 3 tiles of 64 each, through
+    pages of 16; 2 KV heads with 4 query heads each: 6 splits), and the GEMV launcher goes through the slots in groups of
+    8 + 8 + 4. Sequences are admitted in two waves so positions differ by 40."""
+    import os
+    ms = ModelShape(1024, 64, 512, 64 * kv_heads, 1408, 330, 2, heads, kv_heads)
+    rng = np.random.default_rng(heads * 100 + kv_heads)
+    firsts = rng.integers(1, ms.vocab, size=20).tolist()
+    joins = [0 if i % 2 == 0 else 40 for i in range(20)]
+    eng, bd = run_teacher_forced(port, ms, BF16, F32, 31, firsts, joins, n_steps=300, checkpoints={70, 150, 230, 300}, page_len=16,
+                                 max_seqs=20, threads=os.cpu_count() or 1)
     bd.close(); eng.close()

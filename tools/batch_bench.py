@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""tools/batch_bench.py — aggregate decode tokens/s of the batched multi-sequence path (sllm_batch_*) against the number
+of sequences stepping together, next to its HBM roofline.
+
+  python tools/batch_bench.py [--config llama2-7b] [--batches 1,2,4,8,16] [--context 512] [--steps 64] [--json]
+
+Every sequence first decodes `context` tokens (untimed), then `steps` tokens are timed with CUDA events on the batch's
+stream; weights are synthetic (bf16 by default), the cache pages bf16. Algorithmic bytes of a step = every weight once
++ per sequence its K/V rows (sllm_batch_step_bytes), so the roofline fraction says how close the shared weight pass
+stays to the HBM rate as the FMA work per weight grows with the batch. With --json the last stdout line is one JSON
+object (bench.py attaches it to its own line as "batch_decode")."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="llama2-7b")
+    ap.add_argument("--wdtype", default="bf16", choices=["f32", "bf16", "int8"])
+    ap.add_argument("--kvdtype", default="bf16", choices=["f32", "bf16"])
+    ap.add_argument("--batches", default="1,2,4,8,16")
+    ap.add_argument("--context", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--page-len", type=int, default=64)
+    ap.add_argument("--json", action="store_true")
+    args = ap.parse_args()
+
+    import dataclasses
+    import numpy as np
+    import torch
+    from simplellminference_b200.batch import BatchDecoder
+    from simplellminference_b200.config import PRESETS, F32, BF16, INT8
+    from simplellminference_b200.engine import Engine
+
+    torch.cuda.set_device(0)
+    wd = {"f32": F32, "bf16": BF16, "int8": INT8}[args.wdtype]
+    kvd = {"f32": F32, "bf16": BF16}[args.kvdtype]
+    batches = [int(b) for b in args.batches.split(",")]
+    need = args.context + args.steps + 8
+    # the engine only lends its weights and RoPE tables here: keep its own (unused) dense cache small
+    ms = dataclasses.replace(PRESETS[args.config], max_len=max(need, 64))
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
+    rng = np.random.default_rng(1)
+    rows = []
+    for B in batches:
+        bd = BatchDecoder(eng, max_seqs=B, page_len=args.page_len, kv_dtype=kvd)
+        for _ in range(B):
+            bd.add([int(rng.integers(1, ms.vocab))])
+        bd.step(args.context)                      # untimed: fills every sequence's pages up to the context
+        torch.cuda.synchronize()
+        bytes0 = bd.step_bytes()
+        launches0 = bd.total_launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        bd.step(args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms_total = ev0.elapsed_time(ev1)
+        step_bytes = 0.5 * (bytes0 + bd.step_bytes())   # mean over the timed positions (linear in the position)
+        t_step = ms_total * 1e-3 / args.steps
+        ach = step_bytes / t_step / 1e9
+        rows.append({"sequences": B, "tokens_per_sec": B * args.steps / (ms_total * 1e-3), "ms_per_step": 1e3 * t_step,
+                     "bytes_per_step": step_bytes, "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak,
+                     "launches_per_step": (bd.total_launches - launches0) / args.steps,
+                     "checksum": int(sum(int(bd.tokens(s)[-1]) for s in range(B)) % 1000003)})
+        if not args.json:
+            r = rows[-1]
+            print(f"B={B:3d}  {r['tokens_per_sec']:9.1f} tok/s  {r['ms_per_step']:7.3f} ms/step  {r['achieved_gbs']:7.0f} GB/s "
+                  f"({100 * r['frac_of_hbm_peak']:.1f} % of {peak:.0f})  {r['launches_per_step']:.0f} launches/step", flush=True)
+        bd.close()
+    out = {"what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, "
+                   f"every sequence at positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; "
+                   "algorithmic bytes = weights once per step + each sequence's K/V rows",
+           "peak_gbs": peak, "peak_source": peak_src, "steps": args.steps, "by_batch": rows}
+    eng.close()
+    if args.json:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
