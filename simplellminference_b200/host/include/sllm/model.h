@@ -14,6 +14,7 @@
 #include "op.h"
 
 struct sllm_engine;
+struct sllm_batch;
 
 namespace model {
 
@@ -73,6 +74,14 @@ public:
     // prompt where the engine cannot batch it. Results agree within the bf16-operand tolerance, not bit for bit.
     void set_batched_prefill(bool on) { batched_prefill_ = on; }
     bool batched_prefill_active() const;
+    // Several prompts at once (additive; the reference's input_token{1} / position{1}, model.h:15-18, generalised): with a
+    // capacity set before init(), the engine keeps its matrices row-major and owns a paged KV cache of n_pages pages of
+    // page_len positions (0 = enough for max_seqs sequences of max_length), and predict_batch() decodes up to max_seqs
+    // prompts per wave over ONE pass of the weights per step (sllm_batch_*). forward() / predict() keep working.
+    void set_batch_capacity(int max_seqs, int page_len = 64, int n_pages = 0);
+    // predict() for every prompt: element i = the max_length tokens that follow prompts[i][0]; each sequence is decoded
+    // exactly as predict() would decode it alone (prompt echo, then first-max arg-max feedback, no EOS stop).
+    std::vector<std::vector<int32_t>> predict_batch(const std::vector<std::vector<int32_t>>& prompts, int max_length);
 
     void init();
     void forward();   // one token at one position: reads input_token / position (CPU tensors), fills model_pred
@@ -101,6 +110,8 @@ protected:
     base::DataType w_dtype_ = base::DataType::kFp32, kv_dtype_ = base::DataType::kFp32;
     bool config_set_ = false, batched_prefill_ = false;
     sllm_engine* engine_ = nullptr;
+    sllm_batch* batch_ = nullptr;
+    int batch_max_seqs_ = 0, batch_page_len_ = 64, batch_n_pages_ = 0;
     size_t n_weight_floats_ = 0;
 };
 

@@ -2,6 +2,7 @@
 // headerless fp32 blob in the reference's tensor order (model.cpp:340-468); forward() is one token at one
 // position; predict() is the greedy loop on token ids.
 #include <cuda_runtime_api.h>
+#include <algorithm>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -22,7 +23,15 @@ LlamaModel::LlamaModel(std::string tokenizer_path, std::string model_path, base:
     : tokenizer_path_(std::move(tokenizer_path)), model_path_(std::move(model_path)), device_type_(device_type) {}
 
 LlamaModel::~LlamaModel() {
+    if (batch_) sllm_batch_destroy(batch_);   // borrows the engine's weights: goes first
     if (engine_) sllm_engine_destroy(engine_);
+}
+
+void LlamaModel::set_batch_capacity(int max_seqs, int page_len, int n_pages) {
+    if (max_seqs < 1 || page_len < 1 || n_pages < 0) LOG("set_batch_capacity: max_seqs and page_len must be positive");
+    batch_max_seqs_ = max_seqs;
+    batch_page_len_ = page_len;
+    batch_n_pages_ = n_pages;
 }
 
 void LlamaModel::set_config(const LlamaModelConfig& config) {
@@ -100,10 +109,15 @@ void LlamaModel::init_mem() {
         ec.group = 64;
         ec.tp_rank = 0;
         ec.tp_size = 1;
-        ec.flags = SLLM_ENGINE_MEGAKERNEL;
+        ec.flags = batch_max_seqs_ > 0 ? 0 : SLLM_ENGINE_MEGAKERNEL;   // the batched kernels read row-major matrices
         if (sllm_engine_create(&ec, kernel::get_stream(), &engine_) != 0) LOG(sllm_last_error());
         if (sllm_engine_load_blob_f32(engine_, static_cast<const float*>(raw_model_data_->weight(0)), (int64_t)n_weight_floats_) != 0)
             LOG(sllm_last_error());
+        if (batch_max_seqs_ > 0) {
+            const int per_seq = (c.max_length + batch_page_len_ - 1) / batch_page_len_;
+            const int n_pages = batch_n_pages_ > 0 ? batch_n_pages_ : batch_max_seqs_ * per_seq;
+            if (sllm_batch_create(engine_, batch_max_seqs_, batch_page_len_, n_pages, ec.kv_dtype, &batch_) != 0) LOG(sllm_last_error());
+        }
         const int L = c.num_hidden_layers, S = c.max_length, kv = c.kv_hidden_size, d = c.hidden_size, I = c.intermediate_size;
         insert_buffer(ModelBufferType::key_cache, engine_view(engine_, 2, {L, S, kv}));
         insert_buffer(ModelBufferType::value_cache, engine_view(engine_, 3, {L, S, kv}));
@@ -234,6 +248,29 @@ void LlamaModel::forward_op_by_op() {
 
 bool LlamaModel::batched_prefill_active() const {
     return batched_prefill_ && engine_ != nullptr && sllm_engine_prefill_supported(engine_) == 1;
+}
+
+std::vector<std::vector<int32_t>> LlamaModel::predict_batch(const std::vector<std::vector<int32_t>>& prompts, int max_length) {
+    if (!batch_) LOG("predict_batch: call set_batch_capacity() before init() (engine mode)");
+    if (max_length < 1 || max_length >= config_->max_length) LOG("predict: max_length must be below the configured context (KV cache size)");
+    std::vector<std::vector<int32_t>> out(prompts.size());
+    for (size_t first = 0; first < prompts.size(); first += (size_t)batch_max_seqs_) {   // waves of up to max_seqs prompts
+        const size_t n = std::min(prompts.size() - first, (size_t)batch_max_seqs_);
+        std::vector<int32_t> slot(n);
+        for (size_t i = 0; i < n; ++i) {
+            const std::vector<int32_t>& p = prompts[first + i];
+            if (p.empty()) LOG("predict: empty prompt");
+            if (sllm_batch_add(batch_, p.data(), (int32_t)p.size(), &slot[i]) != 0) LOG(sllm_last_error());
+        }
+        if (sllm_batch_step(batch_, max_length) != 0) LOG(sllm_last_error());
+        for (size_t i = 0; i < n; ++i) {
+            out[first + i].resize((size_t)max_length);
+            int32_t got = 0;
+            if (sllm_batch_read(batch_, slot[i], out[first + i].data(), max_length, &got) != 0 || got != max_length) LOG(sllm_last_error());
+            if (sllm_batch_remove(batch_, slot[i]) != 0) LOG(sllm_last_error());
+        }
+    }
+    return out;
 }
 
 std::vector<int32_t> LlamaModel::predict(const std::vector<int32_t>& prompt_ids, int max_length) {

@@ -254,3 +254,16 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     eng, bd = run_teacher_forced(port, ms, BF16, F32, 31, firsts, joins, n_steps=300, checkpoints={70, 150, 230, 300}, page_len=16,
                                  max_seqs=20, threads=os.cpu_count() or 1)
     bd.close(); eng.close()
+
+
+def test_cpp_mirror_predict_batch(tmp_path):
+    """model::LlamaModel::predict_batch of the C++ host mirror (waves of prompts through sllm_batch_*) against the oracle per prompt."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sub in (("simplellminference_b200", "csrc"), ("simplellminference_b200", "host"), ("tests", "cpp")):
+        subprocess.run(["make", "-s", "-C", os.path.join(root, *sub)], check=True)
+    r = subprocess.run([os.path.join(root, "tests", "cpp", "_build", "test_batch_mirror")], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout
