@@ -256,6 +256,36 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     bd.close(); eng.close()
 
 
+def test_continuous_batching_matches_oracle_per_request(port):
+    """scheduler.ContinuousBatcher over the real decoder: nine requests through three slots and a pool that cannot hold
+    three full-length requests at once (admissions are deferred), chunks of 5 steps; every request = the oracle alone.
+    Then the same with an EOS id: each result is the oracle's stream cut after the first generated EOS."""
+    from simplellminference_b200.scheduler import ContinuousBatcher
+    ms = PRESETS["tiny_gqa"]
+    shape = oracle_shape(ms)
+    blob = port.fill_blob(shape, 1234)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_synthetic(1234)
+    bd = BatchDecoder(eng, max_seqs=3, page_len=4, n_pages=24, kv_dtype=F32)
+    rng = np.random.default_rng(12)
+    reqs = [(rng.integers(1, ms.vocab, size=int(rng.integers(1, 8))).tolist(), int(rng.integers(5, 36))) for _ in range(9)]
+    want = [port.model(shape, blob).greedy(p, len(p) + m)[0] for p, m in reqs]
+    cb = ContinuousBatcher(bd, chunk=5)
+    ids = [cb.submit(p, m) for p, m in reqs]
+    out = cb.run()
+    for rid, w in zip(ids, want):
+        assert np.array_equal(out[rid], w), rid
+    assert bd.free_pages == 24 and cb.stats.max_live <= 3 and cb.stats.admissions_deferred > 0
+    eos = int(want[0][-1])
+    cb = ContinuousBatcher(bd, eos_id=eos, chunk=5)
+    ids = [cb.submit(p, m) for p, m in reqs]
+    out = cb.run()
+    for rid, w, (p, m) in zip(ids, want, reqs):
+        hit = np.flatnonzero(w[len(p) - 1:] == eos)
+        assert np.array_equal(out[rid], w[:len(p) - 1 + int(hit[0]) + 1] if hit.size else w), rid
+    assert out[ids[0]][-1] == eos and bd.free_pages == 24
+    bd.close(); eng.close()
+
+
 def test_cpp_mirror_predict_batch(tmp_path):
     """model::LlamaModel::predict_batch of the C++ host mirror (waves of prompts through sllm_batch_*) against the oracle per prompt."""
     import os
