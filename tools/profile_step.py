@@ -11,11 +11,27 @@ ap.add_argument("--layers", type=int, default=0)
 ap.add_argument("--mode", default="mega", choices=["mega", "fused"])
 ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--batch", type=int, default=0, help="> 0: that many sequences through the batched decoder (sllm_batch_*) instead of the engine's own step")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 if a.layers:
     ms = dataclasses.replace(ms, layers=a.layers)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+if a.batch:   # every sequence decodes a.pos tokens first (untimed), then a.steps timed steps
+    from simplellminference_b200.batch import BatchDecoder
+    ms = dataclasses.replace(ms, max_len=a.pos + a.steps + 8)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream).load_synthetic(1)
+    bd = BatchDecoder(eng, max_seqs=a.batch, page_len=64, kv_dtype=BF16)
+    for i in range(a.batch):
+        bd.add([1 + i])
+    bd.step(a.pos); torch.cuda.synchronize()
+    nbytes = bd.step_bytes()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); bd.step(a.steps); e1.record(stream); torch.cuda.synchronize()
+    msec = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({"mode": f"batch of {a.batch}", "layers": ms.layers, "step_ms": round(msec, 4), "tokens_per_sec": round(a.batch / msec * 1e3, 1),
+                      "GBps": round(nbytes / msec / 1e6, 0)}))
+    sys.exit(0)
 eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega")).load_synthetic(1)
 eng.set_state(1, a.pos)
 eng.enqueue_steps(2); torch.cuda.synchronize()
