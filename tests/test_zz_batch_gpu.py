@@ -246,13 +246,12 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     their in-kernel merge (8 KV heads: 160 CTAs per split -> 2 splits of up to 150 positions = 3 tiles of 64 each, through
     pages of 16; 2 KV heads with 4 query heads each: 6 splits), and the GEMV launcher goes through the slots in groups of
     8 + 8 + 4. Sequences are admitted in two waves so positions differ by 40."""
-    import os
     ms = ModelShape(1024, 64, 512, 64 * kv_heads, 1408, 330, 2, heads, kv_heads)
     rng = np.random.default_rng(heads * 100 + kv_heads)
     firsts = rng.integers(1, ms.vocab, size=20).tolist()
     joins = [0 if i % 2 == 0 else 40 for i in range(20)]
     eng, bd = run_teacher_forced(port, ms, BF16, F32, 31, firsts, joins, n_steps=300, checkpoints={70, 150, 230, 300}, page_len=16,
-                                 max_seqs=20, threads=os.cpu_count() or 1)
+                                 max_seqs=20)   # oracle single-threaded: its matrices are too small for a thread per row block to pay
     bd.close(); eng.close()
 
 
