@@ -255,6 +255,33 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     bd.close(); eng.close()
 
 
+@pytest.mark.parametrize("name", ["cfg1_stories15M", "cfg2_stories110M", "tiny_gqa", "tiny_gqa_bf16w", "tiny_gqa_int8w", "tiny_mha_hd48"])
+def test_golden_streams_of_the_reference_inside_a_batch(golden_models, name):
+    """The token streams and final logits recorded from the UNMODIFIED reference (tests/golden/models_ref.npz, the fixtures
+    tests/test_engine_gpu.py holds every engine mode to) reproduced by a sequence that shares its steps with two others."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    prompt, n_total, wd = mg.MODEL_RUNS[name]
+    ms = PRESETS[{"cfg1_stories15M": "stories15M", "cfg2_stories110M": "stories110M", "tiny_mha_hd48": "tiny_mha_hd48"}.get(name, "tiny_gqa")]
+    eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64).load_synthetic(mg.SEED)
+    bd = BatchDecoder(eng, max_seqs=3, page_len=16, kv_dtype=F32)
+    other = bd.add([7])
+    gold = bd.add(prompt)
+    bd.step(3)
+    late = bd.add([9, 11])                    # joins while the golden sequence is under way
+    bd.step(n_total - 1 - 3)
+    want, want_l = golden_models[name + "/tokens"], golden_models[name + "/last_logits"]
+    got = bd.tokens(gold)
+    assert np.array_equal(got, want), (np.flatnonzero(got != want)[:5], got[:8], want[:8])
+    err = float(np.abs(bd.logits(gold) - want_l).max())
+    assert err <= logit_tol(want_l, F32), err
+    assert bd.position(other) == n_total - 1 and bd.position(late) == n_total - 4
+    bd.close(); eng.close()
+
+
 def test_continuous_batching_matches_oracle_per_request(port):
     """scheduler.ContinuousBatcher over the real decoder: nine requests through three slots and a pool that cannot hold
     three full-length requests at once (admissions are deferred), chunks of 5 steps; every request = the oracle alone.
