@@ -217,15 +217,22 @@ def batch_decode_sample(args):
     """Secondary figure: aggregate tokens/s of the batched multi-sequence decode (sllm_batch_*, tools/batch_bench.py) on the
     same model shape and context. Runs in a CHILD process after every timed region of this one and after its engine is
     gone: whatever happens there (error, time-out) is reported in its place and never costs the headline numbers."""
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
-           "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", "1,4,8,16", "--steps", "64", "--json"]
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-        if r.returncode != 0:
-            return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
-        return json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception as ex:
-        return {"error": repr(ex)[:300]}
+    def child(extra, batches):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
+               "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", batches, "--steps", "64", "--json"] + extra
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
+            if r.returncode != 0:
+                return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as ex:
+            return {"error": repr(ex)[:300]}
+
+    out = child([], "1,4,8,16")
+    # the same steps replayed as one CUDA graph each (development knob, first measured here): its own child, so that a failure
+    # of the experimental launch path cannot take the plain figures with it
+    out["graph_replay"] = child(["--graph"], "8,16") if "error" not in out else None
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm --

@@ -111,6 +111,10 @@ struct sllm_batch {
     // host mirror
     std::vector<int> host_pos;     // position of the slot's next step; -1 = slot free
     int64_t total_launches = 0;
+    // opt-in (sllm_tune key 5): one CUDA graph per live-slot count, captured the second time that count steps
+    std::vector<cudaGraphExec_t> graphs;   // [max_seqs + 1]
+    std::vector<int> graph_launches;       // kernel nodes of each graph
+    std::vector<char> warmed;              // a direct step with this count has run (modules loaded, attributes set)
 };
 
 template <class T>
@@ -311,6 +315,45 @@ static int enqueue_batch_step(sllm_batch* b, int hi) {
     return SLLM_OK;
 }
 
+static int dispatch_batch_step(sllm_batch* b, int hi) {
+    switch (b->ev.w_dtype) {
+        case SLLM_F32: return enqueue_batch_step<SLLM_F32>(b, hi);
+        case SLLM_BF16: return enqueue_batch_step<SLLM_BF16>(b, hi);
+        default: return enqueue_batch_step<SLLM_INT8>(b, hi);
+    }
+}
+
+namespace sllm { extern int g_tune_batch_graph; }
+
+// One step. Default: the launch sequence itself. With sllm_tune(5, 1): the sequence is a function of `hi` alone (tokens, positions
+// and block tables are read from device memory), so it is captured once per hi and replayed — 5L + 3 launches become one.
+static int batch_step_once(sllm_batch* b, int hi) {
+    if (!g_tune_batch_graph) return dispatch_batch_step(b, hi);
+    if (!b->warmed[hi]) {   // first step with this count runs directly: it loads the kernels and sets their shared-memory attributes
+        b->warmed[hi] = 1;
+        return dispatch_batch_step(b, hi);
+    }
+    if (!b->graphs[hi]) {
+        cudaGraph_t g = nullptr;
+        const int64_t l0 = b->total_launches, gl0 = g_launches;
+        SLLM_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = dispatch_batch_step(b, hi);
+        const cudaError_t ce = cudaStreamEndCapture(b->stream, &g);
+        b->graph_launches[hi] = (int)(b->total_launches - l0);
+        b->total_launches = l0;   // the captured pass launched nothing
+        g_launches = gl0;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        SLLM_CUDA(ce);
+        const cudaError_t ci = cudaGraphInstantiate(&b->graphs[hi], g, 0);
+        cudaGraphDestroy(g);
+        SLLM_CUDA(ci);
+    }
+    SLLM_CUDA(cudaGraphLaunch(b->graphs[hi], b->stream));
+    b->total_launches += b->graph_launches[hi];
+    g_launches += b->graph_launches[hi];
+    return SLLM_OK;
+}
+
 static int live_hi(const sllm_batch* b) {
     int hi = 0;
     for (int s = 0; s < b->max_seqs; ++s)
@@ -342,6 +385,9 @@ int sllm_batch_create(sllm_engine* e, int32_t max_seqs, int32_t page_len, int32_
     b->pages = sllm_kvpages_create(n_pages, page_len, max_seqs, (s.max_len + page_len - 1) / page_len);
     if (!b->pages) { delete b; return SLLM_EINVAL; }
     b->host_pos.assign(max_seqs, -1);
+    b->graphs.assign(max_seqs + 1, nullptr);
+    b->graph_launches.assign(max_seqs + 1, 0);
+    b->warmed.assign(max_seqs + 1, 0);
     batch_layout(b);   // measure
     b->arena_bytes = (b->arena_used + ((size_t)1 << 20) - 1) >> 20 << 20;
     size_t free_b = 0, total_b = 0;
@@ -373,6 +419,8 @@ void sllm_batch_destroy(sllm_batch* b) {
         cudaStreamSynchronize(b->stream);
         cudaFree(b->arena);
     }
+    for (cudaGraphExec_t g : b->graphs)
+        if (g) cudaGraphExecDestroy(g);
     sllm_kvpages_destroy(b->pages);
     delete b;
 }
@@ -433,13 +481,7 @@ int sllm_batch_step(sllm_batch* b, int32_t n_steps) {
                                   cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before the call returns
     }
     for (int i = 0; i < n_steps; ++i) {
-        int rc;
-        switch (b->ev.w_dtype) {
-            case SLLM_F32: rc = enqueue_batch_step<SLLM_F32>(b, hi); break;
-            case SLLM_BF16: rc = enqueue_batch_step<SLLM_BF16>(b, hi); break;
-            default: rc = enqueue_batch_step<SLLM_INT8>(b, hi); break;
-        }
-        if (rc) return rc;
+        if (int rc = batch_step_once(b, hi)) return rc;
         for (int s = 0; s < hi; ++s)
             if (b->host_pos[s] >= 0) b->host_pos[s] += 1;
     }

@@ -323,3 +323,36 @@ def test_cpp_mirror_predict_batch(tmp_path):
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout
+
+
+def test_graph_replay_matches_direct_launches():
+    """Opt-in development knob sllm_tune(5, 1): the step's launch sequence depends on the live-slot count alone (tokens,
+    positions and block tables are device memory), so it is captured into one CUDA graph per count and replayed. Same
+    kernels, same arguments: tokens and logits must be bit-identical to the direct launches."""
+    lib = _lib.load()
+    ms = PRESETS["tiny_gqa"]
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32).load_synthetic(3)
+
+    def run(graph):
+        _lib.check(lib.sllm_tune(5, 1 if graph else 0))
+        try:
+            bd = BatchDecoder(eng, max_seqs=4, page_len=4, kv_dtype=F32)
+            a, b = bd.add([1, 7, 300]), bd.add([5])
+            bd.step(10)                       # two live slots: direct, capture, 8 replays
+            c = bd.add([9, 2])
+            bd.step(20)                       # three: a second graph
+            bd.remove(b)
+            bd.step(5)                        # a hole in the middle: same count, same graph, the slot is skipped on the device
+            out = [(bd.tokens(s).copy(), bd.logits(s).copy()) for s in (a, c)]
+            launches = bd.total_launches
+            bd.close()
+        finally:
+            lib.sllm_tune(5, 0)
+        return out, launches
+
+    direct, n_direct = run(False)
+    replay, n_replay = run(True)
+    assert n_direct == n_replay                       # the accounting counts kernel nodes either way
+    for (t0, l0), (t1, l1) in zip(direct, replay):
+        assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+    eng.close()

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--page-len", type=int, default=64)
     ap.add_argument("--json", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step (sllm_tune key 5, experimental) instead of the launch sequence")
     args = ap.parse_args()
 
     import dataclasses
@@ -55,6 +56,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
+    if args.graph:
+        from simplellminference_b200 import _lib
+        _lib.check(_lib.load().sllm_tune(5, 1))
     rng = np.random.default_rng(1)
     rows = []
     for B in batches:
@@ -83,7 +87,8 @@ def main():
             print(f"B={B:3d}  {r['tokens_per_sec']:9.1f} tok/s  {r['ms_per_step']:7.3f} ms/step  {r['achieved_gbs']:7.0f} GB/s "
                   f"({100 * r['frac_of_hbm_peak']:.1f} % of {peak:.0f})  {r['launches_per_step']:.0f} launches/step", flush=True)
         bd.close()
-    out = {"what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, "
+    out = {"launch": "one CUDA graph per step (sllm_tune 5, experimental)" if args.graph else "direct launch sequence",
+           "what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, "
                    f"every sequence at positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; "
                    "algorithmic bytes = weights once per step + each sequence's K/V rows",
            "peak_gbs": peak, "peak_source": peak_src, "steps": args.steps, "by_batch": rows}
