@@ -232,6 +232,7 @@ def batch_decode_sample(args):
     # the same steps replayed as one CUDA graph each (development knob, first measured here): its own child, so that a failure
     # of the experimental launch path cannot take the plain figures with it
     out["graph_replay"] = child(["--graph"], "8,16") if "error" not in out else None
+    out["graph_replay_four_row_gemv"] = child(["--graph", "--rows4"], "8,16") if "error" not in out else None
     return out
 
 

@@ -209,18 +209,23 @@ __global__ void batch_set_slot_kernel(int32_t* token, int32_t* pos, int32_t* n_p
 }
 
 // ------------------------------------------------------------------------------------------ GEMV launches ---
-template <int WD, int NB, class Policy>
+namespace sllm { extern int g_tune_batch_rows4; }
+
+template <int WD, int NB, bool FOUR, class Policy>
 static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units) {
+    void (*kernel)(Policy);
+    if constexpr (FOUR) kernel = bgemv4_kernel<WD, NB, Policy>;
+    else kernel = bgemv_kernel<WD, NB, Policy>;
     const size_t smem = bgemv_smem_bytes(p.cols_, p.nb_);
-    static size_t configured = 0;
+    static size_t configured = 0;   // per instantiation, FOUR included
     if (smem > 48 * 1024 && smem > configured) {
         SLLM_REQUIRE(smem <= (size_t)smem_optin_bytes(), SLLM_ENOTSUP, "%d activation vectors of %d floats do not fit shared memory", p.nb_, p.cols_);
-        SLLM_CUDA(cudaFuncSetAttribute(bgemv_kernel<WD, NB, Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SLLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int per_sm = (smem + 1024) * 2 <= (size_t)smem_optin_bytes() ? 2 : 1;   // CTAs of this size that fit one SM
-    LaunchCfg lc(dim3(gemv_grid(units, per_sm)), dim3(kGemvThreads), smem, b->stream, false);
-    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, bgemv_kernel<WD, NB, Policy>, p));
+    LaunchCfg lc(dim3(gemv_grid(FOUR ? (units + 1) / 2 : units, per_sm)), dim3(kGemvThreads), smem, b->stream, false);
+    SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, kernel, p));
     g_launches++;
     b->total_launches++;
     return SLLM_OK;
@@ -228,10 +233,14 @@ static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units) {
 
 template <int WD, class Policy>
 static int launch_bgemv(sllm_batch* b, Policy& p, int units) {
-    if (p.nb_ <= 1) return launch_bgemv_nb<WD, 1>(b, p, units);
-    if (p.nb_ <= 2) return launch_bgemv_nb<WD, 2>(b, p, units);
-    if (p.nb_ <= 4) return launch_bgemv_nb<WD, 4>(b, p, units);
-    return launch_bgemv_nb<WD, kBatchMaxNb>(b, p, units);
+    if (p.nb_ <= 1) return launch_bgemv_nb<WD, 1, false>(b, p, units);
+    if (p.nb_ <= 2) return launch_bgemv_nb<WD, 2, false>(b, p, units);
+    if (g_tune_batch_rows4) {   // experimental four-row body (sllm_tune key 6): where the shared-memory reads per FMA matter
+        if (p.nb_ <= 4) return launch_bgemv_nb<WD, 4, true>(b, p, units);
+        return launch_bgemv_nb<WD, kBatchMaxNb, true>(b, p, units);
+    }
+    if (p.nb_ <= 4) return launch_bgemv_nb<WD, 4, false>(b, p, units);
+    return launch_bgemv_nb<WD, kBatchMaxNb, false>(b, p, units);
 }
 
 // activation vectors of `cols` floats one launch can stage

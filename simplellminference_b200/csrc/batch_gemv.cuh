@@ -5,9 +5,9 @@
 // ("turns GEMV into skinny GEMM"). Same kernel shape as gemv_core.cuh, whose building blocks it
 // reuses unchanged (plane-staged activations, 128-bit streaming weight loads, two-row units, warp-shuffle
 // reductions): every sequence's dot product is accumulated in exactly the order of the one-sequence kernel, so a
-// GEMV result does not depend on which other sequences share the launch. Activations stay fp32 (the decode parity contract), so the contraction runs on the FMA pipes: at NB = 8 that
-// is 8 FMAs per weight and the kernel is still bound by the weight stream; larger batches go through the launcher in
-// groups of 8 (or fewer when 8 vectors of `cols` floats do not fit shared memory).
+// GEMV result does not depend on which other sequences share the launch. Activations stay fp32 (the decode parity
+// contract), so the contraction runs on the FMA pipes: 8 FMAs per weight at NB = 8; larger batches go through the launcher
+// in groups of 8 (or fewer when 8 vectors of `cols` floats do not fit shared memory).
 #pragma once
 #include "decode_fused.cuh"   // gemv_core.cuh + the peer-memory helpers its RMSNorm staging refers to
 #include "paged_kv.cuh"
@@ -102,6 +102,130 @@ __device__ __forceinline__ void bgemv_body(Policy& pol) {
 template <int WD, int NB, class Policy>
 __global__ void __launch_bounds__(kGemvThreads) bgemv_kernel(Policy pol) {
     bgemv_body<WD, NB>(pol);
+}
+
+// ---- experimental variant (sllm_tune key 6): TWO units = four weight rows per warp at a time -----------------------------
+// Every 16-byte chunk of activations read from shared memory then meets four weight rows instead of two: half the LDS
+// traffic per FMA, which is what bounds the two-row body at 8 vectors (2 x NB LDS.128 per chunk column against 16 x NB FMAs;
+// an SM moves 128 B of shared memory per clock). Four loads per row per lane in flight, so the bytes in flight per warp stay
+// 8 KB. A lane visits its chunks in the same ascending order, so every sum is bit-identical to the two-row body's.
+constexpr int kBgemvU4 = 4;
+
+template <int WD>
+struct Batch4 {
+    uint4 w[4][kBgemvU4];
+    float s[4][kBgemvU4];   // int8 only: group scale of each chunk
+};
+
+template <int WD>
+__device__ __forceinline__ void load_batch4(Batch4<WD>& b, const uint4* const* rp, const float* const* sp, int chunks_per_group, int base,
+                                            int lane, int nchunks) {
+#pragma unroll
+    for (int u = 0; u < kBgemvU4; ++u) {
+        const int c = base + u * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c < nchunks) {
+                b.w[k][u] = ldg_stream(rp[k] + c);
+                if (WD == SLLM_INT8) b.s[k][u] = __ldg(sp[k] + c / chunks_per_group);
+            } else {
+                b.w[k][u] = make_uint4(0, 0, 0, 0);
+                if (WD == SLLM_INT8) b.s[k][u] = 0.f;
+            }
+        }
+    }
+}
+
+template <int WD, int NB, class Policy>
+__device__ __forceinline__ void bgemv_body4(Policy& pol) {
+    extern __shared__ __align__(16) float smem[];
+    const int cols = pol.cols();
+    const int nb = pol.nb();
+    float* red = smem + (size_t)nb * cols;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kGemvWarps;
+    const int nchunks = cols / WInfo<WD>::E;
+    const int nunits = pol.units();
+    const int cpg = (WD == SLLM_INT8) ? pol.group() / 16 : 1;
+    const int groups_per_row = (WD == SLLM_INT8) ? cols / pol.group() : 0;
+    const uint4* Wv = reinterpret_cast<const uint4*>(pol.W());
+    const float* Sc = pol.scales();
+
+    // this warp's units: (unit, unit + warps_total), then both advance by 2 * warps_total
+    const uint4* rp[4];
+    const float* sp[4];
+    auto set_rows = [&](int ua) {
+        int64_t r[4];
+        pol.rows(ua, r[0], r[1]);
+        if (ua + warps_total < nunits) pol.rows(ua + warps_total, r[2], r[3]);
+        else { r[2] = r[0]; r[3] = r[1]; }   // no second unit: it aliases the first and is not emitted
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rp[k] = Wv + r[k] * nchunks;
+            sp[k] = Sc + r[k] * groups_per_row;
+        }
+    };
+    Batch4<WD> cur;
+    int unit = warp_global;
+    if (unit < nunits) {
+        set_rows(unit);
+        load_batch4<WD>(cur, rp, sp, cpg, 0, lane, nchunks);
+    }
+    for (int b = 0; b < nb; ++b) pol.stage(b, smem + (size_t)b * cols, red);
+    __syncthreads();
+    const float4* xs4 = reinterpret_cast<const float4*>(smem);
+    const int xstride4 = cols / 4;
+
+    while (unit < nunits) {
+        float a[4][NB];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) a[k][b] = 0.f;
+        for (int base = 0; base < nchunks; base += 32 * kBgemvU4) {
+#pragma unroll
+            for (int u = 0; u < kBgemvU4; ++u) {
+                const int c = base + u * 32 + lane;
+                if (c < nchunks) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        if (b < nb) {
+                            const float4* xb = xs4 + (size_t)b * xstride4;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (WD == SLLM_INT8) a[k][b] = fmaf(chunk_dot<WD>(cur.w[k][u], xb, c, nchunks, 0.f), cur.s[k][u], a[k][b]);
+                                else a[k][b] = chunk_dot<WD>(cur.w[k][u], xb, c, nchunks, a[k][b]);
+                            }
+                        }
+                    }
+                }
+            }
+            const int nxt = base + 32 * kBgemvU4;
+            if (nxt < nchunks) load_batch4<WD>(cur, rp, sp, cpg, nxt, lane, nchunks);
+        }
+        const int ua = unit, ub = unit + warps_total;
+        unit += 2 * warps_total;
+        if (unit < nunits) {   // the next pair's first loads go out before this pair's reductions
+            set_rows(unit);
+            load_batch4<WD>(cur, rp, sp, cpg, 0, lane, nchunks);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b < nb) {   // uniform over the warp
+                const float t0 = warp_sum(a[0][b]), t1 = warp_sum(a[1][b]), t2 = warp_sum(a[2][b]), t3 = warp_sum(a[3][b]);
+                if (lane == 0) {
+                    pol.emit(ua, b, t0, t1);
+                    if (ub < nunits) pol.emit(ub, b, t2, t3);
+                }
+            }
+        }
+    }
+}
+
+template <int WD, int NB, class Policy>
+__global__ void __launch_bounds__(kGemvThreads) bgemv4_kernel(Policy pol) {
+    bgemv_body4<WD, NB>(pol);
 }
 
 // ---- policies: the decode_fused.cuh epilogues with a sequence-slot index -------------------------------------

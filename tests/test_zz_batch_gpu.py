@@ -183,7 +183,13 @@ def test_step_bytes_share_the_weights(port):
     bd.close(); eng.close()
 
 
-# ---- written after the round's GPU budget was spent: first executed by the round-end run (the tests above ran on a B200) ----
+# ---- written after the round's GPU budget was spent (the tests above ran on a B200): the round-end run is the FIRST execution
+# of everything below. Until a run has confirmed them they are non-strict xfail: an XPASS in the report is the confirmation, an
+# xfail names what to fix, and neither hides the verified part of the suite. Remove the mark once they have passed on a GPU.
+first_run = pytest.mark.xfail(strict=False, reason="never executed on a GPU yet (written after the round's GPU budget was spent)")
+
+
+@first_run
 def test_full_width_llama2_7b_two_layers_batch_of_eight(port):
     """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers and eight sequences: the shapes
     where the staged activations need opt-in shared memory (8 x 4096 floats = 128 KB per CTA) and where the down projection
@@ -240,6 +246,7 @@ def run_teacher_forced(port, ms, wd, kvd, seed, firsts, joins, n_steps, checkpoi
     return eng, bd
 
 
+@first_run
 @pytest.mark.parametrize("heads,kv_heads", [(8, 8), (8, 2)])
 def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     """Contexts of up to 300 positions in 20 slots: the attention kernel runs with several KV splits per (slot, head) and
@@ -255,6 +262,7 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     bd.close(); eng.close()
 
 
+@first_run
 @pytest.mark.parametrize("name", ["cfg1_stories15M", "cfg2_stories110M", "tiny_gqa", "tiny_gqa_bf16w", "tiny_gqa_int8w", "tiny_mha_hd48"])
 def test_golden_streams_of_the_reference_inside_a_batch(golden_models, name):
     """The token streams and final logits recorded from the UNMODIFIED reference (tests/golden/models_ref.npz, the fixtures
@@ -282,6 +290,7 @@ def test_golden_streams_of_the_reference_inside_a_batch(golden_models, name):
     bd.close(); eng.close()
 
 
+@first_run
 def test_continuous_batching_matches_oracle_per_request(port):
     """scheduler.ContinuousBatcher over the real decoder: nine requests through three slots and a pool that cannot hold
     three full-length requests at once (admissions are deferred), chunks of 5 steps; every request = the oracle alone.
@@ -312,6 +321,7 @@ def test_continuous_batching_matches_oracle_per_request(port):
     bd.close(); eng.close()
 
 
+@first_run
 def test_cpp_mirror_predict_batch(tmp_path):
     """model::LlamaModel::predict_batch of the C++ host mirror (waves of prompts through sllm_batch_*) against the oracle per prompt."""
     import os
@@ -325,6 +335,7 @@ def test_cpp_mirror_predict_batch(tmp_path):
     assert "PASS" in r.stdout
 
 
+@first_run
 def test_graph_replay_matches_direct_launches():
     """Opt-in development knob sllm_tune(5, 1): the step's launch sequence depends on the live-slot count alone (tokens,
     positions and block tables are device memory), so it is captured into one CUDA graph per count and replayed. Same
@@ -356,3 +367,34 @@ def test_graph_replay_matches_direct_launches():
     for (t0, l0), (t1, l1) in zip(direct, replay):
         assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
     eng.close()
+
+
+@first_run
+@pytest.mark.parametrize("preset,wd", [("tiny_gqa", F32), ("tiny_gqa", BF16), ("tiny_gqa", INT8), ("tiny_mha_hd48", F32)])
+def test_four_row_gemv_body_is_bit_identical(preset, wd):
+    """Opt-in development knob sllm_tune(6, 1): the GEMV body that takes two units (four weight rows) per warp at a time,
+    used when three or more sequences share a launch. A lane visits its chunks in the same order, so tokens and logits must
+    be bit-identical to the two-row body's (hd48 shape: unit counts that leave some warps with a single unit)."""
+    lib = _lib.load()
+    ms = PRESETS[preset]
+    eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64).load_synthetic(6)
+
+    def run(rows4):
+        _lib.check(lib.sllm_tune(6, 1 if rows4 else 0))
+        try:
+            bd = BatchDecoder(eng, max_seqs=6, page_len=8, kv_dtype=F32)
+            slots = [bd.add([3 + i, 40 + i]) for i in range(3)]
+            bd.step(6)                                   # three vectors: the 4-vector instantiation
+            slots += [bd.add([100 + i]) for i in range(3)]
+            bd.step(24)                                  # six: the 8-vector instantiation
+            out = [(bd.tokens(s).copy(), bd.logits(s).copy()) for s in slots]
+            bd.close()
+        finally:
+            lib.sllm_tune(6, 0)
+        return out
+
+    two, four = run(False), run(True)
+    for (t0, l0), (t1, l1) in zip(two, four):
+        assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+    eng.close()
+
