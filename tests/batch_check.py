@@ -73,7 +73,17 @@ def main():
              ("batch of one", lambda: T.test_batch_of_one_equals_the_engine(port)),
              ("errors", lambda: T.test_argument_and_state_errors(port)),
              ("step bytes", lambda: T.test_step_bytes_share_the_weights(port)),
-             ("ragged bf16/f32", lambda: T.test_ragged_batch_matches_oracle_per_sequence(port, BF16, F32))]
+             ("ragged bf16/f32", lambda: T.test_ragged_batch_matches_oracle_per_sequence(port, BF16, F32)),
+             # written after the first GPU run of this script
+             ("continuous batching", lambda: T.test_continuous_batching_matches_oracle_per_request(port)),
+             ("graph replay", lambda: T.test_graph_replay_matches_direct_launches()),
+             ("four-row gemv f32", lambda: T.test_four_row_gemv_body_is_bit_identical("tiny_gqa", F32)),
+             ("four-row gemv bf16", lambda: T.test_four_row_gemv_body_is_bit_identical("tiny_gqa", BF16)),
+             ("four-row gemv int8", lambda: T.test_four_row_gemv_body_is_bit_identical("tiny_gqa", INT8)),
+             ("four-row gemv hd48", lambda: T.test_four_row_gemv_body_is_bit_identical("tiny_mha_hd48", F32)),
+             ("full width 7B x 2 layers, 8 sequences", lambda: T.test_full_width_llama2_7b_two_layers_batch_of_eight(port)),
+             ("long context 8 kv heads", lambda: T.test_long_context_many_slots_split_kv(port, 8, 8)),
+             ("long context gqa", lambda: T.test_long_context_many_slots_split_kv(port, 8, 2))]
     ok = 0
     for name, fn in cases:
         try:
