@@ -269,6 +269,11 @@ void sllm_batch_destroy(sllm_batch* b);
 int sllm_batch_add(sllm_batch* b, const int32_t* prompt_host, int32_t n_prompt, int32_t* slot_out);
 /* retire a sequence: its slot and pages are free for the next sllm_batch_add at once (stream order protects them) */
 int sllm_batch_remove(sllm_batch* b, int32_t slot);
+/* Sampling instead of arg-max for one sequence (additive, like sllm_sample_f32; not part of the parity contract): from now on the token
+ * that follows position p of this slot is sllm_sample_f32(logits_p, temperature, top_k, top_p, seed, step = p) — a pure function of the
+ * sequence, whatever its neighbours. temperature <= 0 switches back to arg-max. Prompt tokens are still fed verbatim. Retiring the
+ * sequence clears the setting. */
+int sllm_batch_set_sampling(sllm_batch* b, int32_t slot, float temperature, int32_t top_k, float top_p, uint64_t seed);
 /* n_steps tokens for EVERY live sequence, asynchronous. Takes the pages the steps will write first, for all sequences
  * or none: SLLM_ENOMEM (nothing enqueued) when the pool is short, SLLM_EINVAL when a sequence would pass max_len. */
 int sllm_batch_step(sllm_batch* b, int32_t n_steps);

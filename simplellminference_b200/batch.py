@@ -77,6 +77,10 @@ class BatchDecoder:
     def remove(self, slot: int) -> None:
         _lib.check(self.lib.sllm_batch_remove(self.h, slot))
 
+    def set_sampling(self, slot: int, temperature: float, top_k: int = 0, top_p: float = 0.0, seed: int = 0) -> None:
+        """Draw this sequence's tokens (kernels.sample semantics, keyed by (seed, position)) instead of arg-max; temperature <= 0 = arg-max."""
+        _lib.check(self.lib.sllm_batch_set_sampling(self.h, slot, float(temperature), int(top_k), float(top_p), int(seed)))
+
     def step(self, n_steps: int = 1) -> None:
         _lib.check(self.lib.sllm_batch_step(self.h, n_steps))
 

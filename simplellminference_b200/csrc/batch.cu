@@ -111,6 +111,11 @@ struct sllm_batch {
     // host mirror
     std::vector<int> host_pos;     // position of the slot's next step; -1 = slot free
     int64_t total_launches = 0;
+    // per-slot sampling instead of arg-max (sllm_batch_set_sampling); temperature <= 0 = arg-max
+    std::vector<float> s_temp, s_top_p;
+    std::vector<int32_t> s_top_k;
+    std::vector<uint64_t> s_seed;
+    int n_sampling = 0;            // live slots with temperature > 0
     // opt-in (sllm_tune key 5): one CUDA graph per live-slot count, captured the second time that count steps
     std::vector<cudaGraphExec_t> graphs;   // [max_seqs + 1]
     std::vector<int> graph_launches;       // kernel nodes of each graph
@@ -200,6 +205,19 @@ batch_argmax_feedback_kernel(const float* __restrict__ logits, int V, int32_t* _
         token[slot] = nxt;
         pos[slot] = p + 1;
     }
+}
+
+// Sampling mode: next[slot] was written by sllm_sample_f32 (a draw, or the arg-max for slots that do not sample); same feedback.
+__global__ void batch_feedback_kernel(const int32_t* __restrict__ next, int32_t* __restrict__ token, int32_t* __restrict__ pos,
+                                      const int32_t* __restrict__ n_prompt, const int32_t* __restrict__ prompt, int32_t* __restrict__ history, int S) {
+    const int slot = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const int p = pos[slot];
+    if (p < 0) return;
+    const int nxt = (p + 1 < n_prompt[slot]) ? prompt[(size_t)slot * S + p + 1] : next[slot];
+    history[(size_t)slot * S + p] = nxt;
+    token[slot] = nxt;
+    pos[slot] = p + 1;
 }
 
 __global__ void batch_set_slot_kernel(int32_t* token, int32_t* pos, int32_t* n_prompt, int slot, int tok, int p, int np) {
@@ -316,8 +334,22 @@ static int enqueue_batch_step(sllm_batch* b, int hi) {
         F.x = b->x; F.norm_w = ev.norms + (int64_t)(2 * L) * d; F.eps = ev.shape.eps; F.logits = b->logits; F.nrows = V;
         if (int rc = launch_bgemv<WD>(b, F, (V + 1) / 2)) return rc;
     }
-    batch_argmax_feedback_kernel<<<hi, kArgmaxThreads, 0, b->stream>>>(b->logits, V, b->token, b->pos, b->n_prompt, b->next, b->prompt,
-                                                                      b->history, b->S);
+    if (b->n_sampling == 0) {
+        batch_argmax_feedback_kernel<<<hi, kArgmaxThreads, 0, b->stream>>>(b->logits, V, b->token, b->pos, b->n_prompt, b->next, b->prompt,
+                                                                          b->history, b->S);
+        SLLM_LAUNCH_CHECK();
+        g_launches++;
+        b->total_launches++;
+        return SLLM_OK;
+    }
+    // some slot samples: one draw (or arg-max, temperature 0) per live slot with the op launcher of sample.cu, keyed by (seed, position)
+    for (int s = 0; s < hi; ++s) {
+        if (b->host_pos[s] < 0) continue;
+        if (int rc = sllm_sample_f32(b->logits + (size_t)s * V, V, b->s_temp[s], b->s_top_k[s], b->s_top_p[s], b->s_seed[s],
+                                     (uint64_t)b->host_pos[s], b->next + s, b->stream)) return rc;
+        b->total_launches++;
+    }
+    batch_feedback_kernel<<<hi, 32, 0, b->stream>>>(b->next, b->token, b->pos, b->n_prompt, b->prompt, b->history, b->S);
     SLLM_LAUNCH_CHECK();
     g_launches++;
     b->total_launches++;
@@ -337,7 +369,7 @@ namespace sllm { extern int g_tune_batch_graph; }
 // One step. Default: the launch sequence itself. With sllm_tune(5, 1): the sequence is a function of `hi` alone (tokens, positions
 // and block tables are read from device memory), so it is captured once per hi and replayed — 5L + 3 launches become one.
 static int batch_step_once(sllm_batch* b, int hi) {
-    if (!g_tune_batch_graph) return dispatch_batch_step(b, hi);
+    if (!g_tune_batch_graph || b->n_sampling > 0) return dispatch_batch_step(b, hi);   // a draw's step index is a by-value argument
     if (!b->warmed[hi]) {   // first step with this count runs directly: it loads the kernels and sets their shared-memory attributes
         b->warmed[hi] = 1;
         return dispatch_batch_step(b, hi);
@@ -394,6 +426,10 @@ int sllm_batch_create(sllm_engine* e, int32_t max_seqs, int32_t page_len, int32_
     b->pages = sllm_kvpages_create(n_pages, page_len, max_seqs, (s.max_len + page_len - 1) / page_len);
     if (!b->pages) { delete b; return SLLM_EINVAL; }
     b->host_pos.assign(max_seqs, -1);
+    b->s_temp.assign(max_seqs, 0.f);
+    b->s_top_p.assign(max_seqs, 0.f);
+    b->s_top_k.assign(max_seqs, 0);
+    b->s_seed.assign(max_seqs, 0);
     b->graphs.assign(max_seqs + 1, nullptr);
     b->graph_launches.assign(max_seqs + 1, 0);
     b->warmed.assign(max_seqs + 1, 0);
@@ -463,6 +499,20 @@ int sllm_batch_remove(sllm_batch* b, int32_t slot) {
     // the pages may be handed to another sequence right away: everything that touches them is ordered on the stream
     b->pages->release(slot);
     b->host_pos[slot] = -1;
+    if (b->s_temp[slot] > 0.f) b->n_sampling--;
+    b->s_temp[slot] = 0.f;
+    return SLLM_OK;
+}
+
+int sllm_batch_set_sampling(sllm_batch* b, int32_t slot, float temperature, int32_t top_k, float top_p, uint64_t seed) {
+    SLLM_REQUIRE(b && slot >= 0 && slot < b->max_seqs && b->host_pos[slot] >= 0, SLLM_EINVAL, "batch_set_sampling: slot %d is not in use", slot);
+    SLLM_REQUIRE(top_k >= 0 && top_p >= 0.f && top_p <= 1.f, SLLM_EINVAL, "sample: top_k must be >= 0 and top_p in [0, 1]");
+    const bool was = b->s_temp[slot] > 0.f, is = temperature > 0.f;
+    b->n_sampling += (is ? 1 : 0) - (was ? 1 : 0);
+    b->s_temp[slot] = is ? temperature : 0.f;
+    b->s_top_k[slot] = top_k;
+    b->s_top_p[slot] = top_p;
+    b->s_seed[slot] = seed;
     return SLLM_OK;
 }
 

@@ -22,6 +22,7 @@ class _Request:
     rid: int
     prompt: np.ndarray
     total: int                      # positions this request decodes in all: its steps
+    sampling: dict | None = None    # BatchDecoder.set_sampling keywords (temperature, top_k, top_p, seed); None = arg-max
     slot: int = -1
     tokens: np.ndarray | None = None
     done: bool = False
@@ -52,15 +53,16 @@ class ContinuousBatcher:
         self._next_id = 0
 
     # ---- requests ----
-    def submit(self, prompt_ids, max_new_tokens: int) -> int:
-        """Queue a request: the prompt, then ``max_new_tokens`` generated tokens. Returns its id."""
+    def submit(self, prompt_ids, max_new_tokens: int, sampling: dict | None = None) -> int:
+        """Queue a request: the prompt, then ``max_new_tokens`` generated tokens (arg-max, or drawn with ``sampling`` =
+        the keywords of ``BatchDecoder.set_sampling``). Returns its id."""
         prompt = np.ascontiguousarray(prompt_ids, dtype=np.int32).reshape(-1)
         if prompt.size < 1 or max_new_tokens < 1:
             raise ValueError("a request needs a non-empty prompt and at least one new token")
         total = int(prompt.size) + int(max_new_tokens) - 1   # steps: positions 0 .. total-1 (the last prompt token's step yields the first new one)
         if self._pages_for(total) > self._pool_pages():
             raise ValueError(f"request of {total} positions can never fit the page pool")
-        r = _Request(self._next_id, prompt, total)
+        r = _Request(self._next_id, prompt, total, sampling)
         self._next_id += 1
         self.waiting.append(r)
         return r.rid
@@ -87,6 +89,8 @@ class ContinuousBatcher:
                 return                                   # FIFO: the head waits, nobody overtakes it
             self.waiting.popleft()
             r.slot = self.dec.add(r.prompt)
+            if r.sampling:
+                self.dec.set_sampling(r.slot, **r.sampling)
             self.live[r.slot] = r
         if self.waiting and len(self.live) >= self.dec.max_seqs:
             self.stats.admissions_deferred += 1

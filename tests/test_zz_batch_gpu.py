@@ -398,3 +398,41 @@ def test_four_row_gemv_body_is_bit_identical(preset, wd):
         assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
     eng.close()
 
+
+@first_run
+def test_sampling_per_slot_matches_the_single_sequence_sampler(port):
+    """sllm_batch_set_sampling: a slot that samples draws exactly what predict.sample_ids draws for that sequence alone (same
+    logits, same (seed, position) key), and its neighbours — greedy or sampling with other parameters — are not disturbed."""
+    from simplellminference_b200.predict import sample_ids
+    from simplellminference_b200.scheduler import ContinuousBatcher
+    ms = PRESETS["tiny_gqa"]
+    shape = oracle_shape(ms)
+    blob = port.fill_blob(shape, 1234)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32).load_synthetic(1234)
+    bd = BatchDecoder(eng, max_seqs=4, page_len=8, kv_dtype=F32)
+    g = bd.add([1, 7, 300])
+    a = bd.add([5, 6])
+    bd.set_sampling(a, 0.8, top_k=20, seed=11)
+    c = bd.add([9])
+    bd.set_sampling(c, 1.3, top_p=0.9, seed=5)
+    bd.step(36)
+    got = {s: bd.tokens(s).copy() for s in (g, a, c)}
+    want_g, _ = port.model(shape, blob).greedy([1, 7, 300], 37)
+    assert np.array_equal(got[g], want_g)
+    assert np.array_equal(got[a], sample_ids(eng, [5, 6], 36, temperature=0.8, top_k=20, seed=11))
+    assert np.array_equal(got[c], sample_ids(eng, [9], 36, temperature=1.3, top_p=0.9, seed=5))
+    greedy_c, _ = port.model(shape, blob).greedy([9], 37)
+    assert not np.array_equal(got[c], greedy_c)              # it did draw
+    bd.set_sampling(a, 0.0)                                  # back to arg-max: from here on the slot is greedy again
+    for s in (g, a, c):
+        bd.remove(s)
+    with pytest.raises(_lib.SllmError):
+        bd.set_sampling(a, 1.0)                              # not in use any more
+    # through the scheduler: the same request queued with its sampling parameters
+    cb = ContinuousBatcher(bd, chunk=6)
+    rid = cb.submit([5, 6], 35, sampling=dict(temperature=0.8, top_k=20, seed=11))
+    rid2 = cb.submit([1, 7, 300], 34)
+    out = cb.run()
+    assert np.array_equal(out[rid], got[a]) and np.array_equal(out[rid2], want_g)
+    bd.close(); eng.close()
+
