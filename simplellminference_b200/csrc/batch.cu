@@ -13,6 +13,10 @@
 // needs (tokens, positions, block tables) lives in device memory, so n steps are n launch sequences with no host
 // round trip; the host only hands out pages ahead of the steps it enqueues.
 //
+// Options: a slot may sample instead of taking the arg-max (sllm_batch_set_sampling: one sllm_sample_f32 per live slot keyed by
+// (seed, position)); development knobs sllm_tune 5 (replay the step as one CUDA graph per live-slot count) and 6 (GEMV body with
+// four weight rows per warp), both off until measured.
+//
 // Pages: sllm_kvpages is plain host bookkeeping (free stack + per-sequence page lists), exported on its own so that it
 // is testable without a GPU. The device pools are [pages][layers][kv_heads][page_len][head_dim] (paged_kv.cuh).
 #include <algorithm>
