@@ -233,6 +233,7 @@ def batch_decode_sample(args):
     # of the experimental launch path cannot take the plain figures with it
     out["graph_replay"] = child(["--graph"], "8,16") if "error" not in out else None
     out["graph_replay_four_row_gemv"] = child(["--graph", "--rows4"], "8,16") if "error" not in out else None
+    out["graph_replay_four_row_gemv_split_down"] = child(["--graph", "--rows4", "--ksplit"], "8,16") if "error" not in out else None
     return out
 
 

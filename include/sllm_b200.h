@@ -50,7 +50,8 @@ int sllm_abi_version(void);
  * the N extent of a tile (multiple of 32, 0 = cost model), key 2 = two-SM tiles (1 / 0 force / forbid, -1 = by T), key 3 = programmatic
  * dependent launch (1 default), key 4 = K split of the residual-epilogue GEMMs (0 never, n up to n ranges, -1 cost model); batched decode:
  * key 5 = replay one CUDA graph per live-slot count instead of the launch sequence, key 6 = GEMV body with four weight rows per warp at
- * a time when 3 or more sequences share a launch (both 0 by default: experimental until measured) */
+ * a time when 3 or more sequences share a launch, key 7 (with key 6) = down projection with K cut in two over grid.y when more sequences
+ * are live than whole rows fit shared memory, so that Wdown is read once (all 0 by default: experimental until measured) */
 int sllm_tune(int32_t key, int32_t value);
 /* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
 int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);

@@ -112,6 +112,7 @@ struct sllm_batch {
     float *x = nullptr, *h = nullptr, *q = nullptr, *att = nullptr, *swi = nullptr, *logits = nullptr;
     int32_t *token = nullptr, *pos = nullptr, *n_prompt = nullptr, *next = nullptr, *block_table = nullptr, *prompt = nullptr, *history = nullptr;
     void* mha_ws = nullptr;
+    float* part = nullptr;
     // host mirror
     std::vector<int> host_pos;     // position of the slot's next step; -1 = slot free
     int64_t total_launches = 0;
@@ -151,6 +152,7 @@ static void batch_layout(sllm_batch* b) {   // first pass (arena == nullptr) onl
     b->prompt = bcarve<int32_t>(b, 4 * ms * b->S);
     b->history = bcarve<int32_t>(b, 4 * ms * b->S);
     b->mha_ws = bcarve<void>(b, mha_paged_workspace_bytes(b->max_seqs, b->H, b->KVH, b->hd));
+    b->part = bcarve<float>(b, 4 * 2 * ms * b->d);   // K-split partial sums of the down projection (sllm_tune key 7)
     // the two arrays that start at -1 (no position, no page) come last: one memset of 0xFF covers both
     b->pos = bcarve<int32_t>(b, 4 * ms);
     b->block_table = bcarve<int32_t>(b, 4 * ms * b->pages->max_pages);
@@ -224,6 +226,12 @@ __global__ void batch_feedback_kernel(const int32_t* __restrict__ next, int32_t*
     pos[slot] = p + 1;
 }
 
+// x = h + (p0 + p1): the two K halves of the split down projection (sllm_tune key 7)
+__global__ void batch_add_partials_kernel(const float* __restrict__ resid, const float* __restrict__ p0, const float* __restrict__ p1,
+                                          float* __restrict__ y, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = resid[i] + (p0[i] + p1[i]);
+}
+
 __global__ void batch_set_slot_kernel(int32_t* token, int32_t* pos, int32_t* n_prompt, int slot, int tok, int p, int np) {
     token[slot] = tok;
     pos[slot] = p;
@@ -231,10 +239,10 @@ __global__ void batch_set_slot_kernel(int32_t* token, int32_t* pos, int32_t* n_p
 }
 
 // ------------------------------------------------------------------------------------------ GEMV launches ---
-namespace sllm { extern int g_tune_batch_rows4; }
+namespace sllm { extern int g_tune_batch_rows4, g_tune_batch_ksplit; }
 
 template <int WD, int NB, bool FOUR, class Policy>
-static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units) {
+static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units, int grid_y = 1) {
     void (*kernel)(Policy);
     if constexpr (FOUR) kernel = bgemv4_kernel<WD, NB, Policy>;
     else kernel = bgemv_kernel<WD, NB, Policy>;
@@ -246,7 +254,7 @@ static int launch_bgemv_nb(sllm_batch* b, Policy& p, int units) {
         configured = smem;
     }
     const int per_sm = (smem + 1024) * 2 <= (size_t)smem_optin_bytes() ? 2 : 1;   // CTAs of this size that fit one SM
-    LaunchCfg lc(dim3(gemv_grid(FOUR ? (units + 1) / 2 : units, per_sm)), dim3(kGemvThreads), smem, b->stream, false);
+    LaunchCfg lc(dim3(gemv_grid(FOUR ? (units + 1) / 2 : units, per_sm), grid_y), dim3(kGemvThreads), smem, b->stream, false);
     SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, kernel, p));
     g_launches++;
     b->total_launches++;
@@ -324,6 +332,27 @@ static int enqueue_batch_step(sllm_batch* b, int hi) {
             D.h = b->h; D.norm_w = ev.norms + (int64_t)(2 * l + 1) * d; D.eps = ev.shape.eps; D.s_out = b->swi; D.inter = I;
             if (int rc = launch_bgemv<WD>(b, D, I)) return rc;
         }
+        const int E_w = WInfo<WD>::E, half = I / 2;
+        const bool split_down = g_tune_batch_ksplit && g_tune_batch_rows4 && hi > g_i && hi > 2 && I % (2 * E_w) == 0 &&
+                                (WD != SLLM_INT8 || half % ev.group == 0) && fit_nb(half) > g_i;
+        if (split_down) {   // E' (experimental): K halves over grid.y, then x = h + (p0 + p1)
+            const int g_h = fit_nb(half);
+            for (int b0 = 0; b0 < hi; b0 += g_h) {
+                BDownSplitPolicy<WD> E{};
+                E.W_ = layer_w(b, ev.wdown, d, I, l); E.sc_ = layer_sc(b, ev.wdown_sc, d, I, l);
+                E.grp_ = ev.group; E.cols_ = half; E.nb_ = std::min(g_h, hi - b0); E.b0 = b0;
+                E.x = b->swi; E.part = b->part; E.nrows = d; E.row_cols_ = I; E.slots_total = b->max_seqs;
+                int rc;
+                if (E.nb_ <= 4) rc = launch_bgemv_nb<WD, 4, true>(b, E, (d + 1) / 2, 2);
+                else rc = launch_bgemv_nb<WD, kBatchMaxNb, true>(b, E, (d + 1) / 2, 2);
+                if (rc) return rc;
+            }
+            const int n = hi * d;
+            batch_add_partials_kernel<<<std::min((n + 255) / 256, 4 * sm_count()), 256, 0, b->stream>>>(b->h, b->part, b->part + (size_t)b->max_seqs * d, b->x, n);
+            SLLM_LAUNCH_CHECK();
+            g_launches++;
+            b->total_launches++;
+        } else
         for (int b0 = 0; b0 < hi; b0 += g_i) {   // E: x = Wdown.s + h
             BResidualPolicy<WD> E{};
             E.W_ = layer_w(b, ev.wdown, d, I, l); E.sc_ = layer_sc(b, ev.wdown_sc, d, I, l);

@@ -152,6 +152,11 @@ __device__ __forceinline__ void bgemv_body4(Policy& pol) {
     const uint4* Wv = reinterpret_cast<const uint4*>(pol.W());
     const float* Sc = pol.scales();
 
+    // a policy may contract only a column range [col0, col0 + cols) of rows that are row_cols long (K split over grid.y)
+    const int row_chunks = pol.row_cols() / WInfo<WD>::E, chunk0 = pol.col0() / WInfo<WD>::E;
+    const int row_groups = (WD == SLLM_INT8) ? pol.row_cols() / pol.group() : 0, group0 = (WD == SLLM_INT8) ? pol.col0() / pol.group() : 0;
+    (void)groups_per_row;
+
     // this warp's units: (unit, unit + warps_total), then both advance by 2 * warps_total
     const uint4* rp[4];
     const float* sp[4];
@@ -162,8 +167,8 @@ __device__ __forceinline__ void bgemv_body4(Policy& pol) {
         else { r[2] = r[0]; r[3] = r[1]; }   // no second unit: it aliases the first and is not emitted
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            rp[k] = Wv + r[k] * nchunks;
-            sp[k] = Sc + r[k] * groups_per_row;
+            rp[k] = Wv + r[k] * row_chunks + chunk0;
+            sp[k] = Sc + r[k] * row_groups + group0;
         }
     };
     Batch4<WD> cur;
@@ -233,6 +238,8 @@ __global__ void __launch_bounds__(kGemvThreads) bgemv4_kernel(Policy pol) {
 struct BatchBase : GemvBase {
     int nb_, b0;
     __device__ int nb() const { return nb_; }
+    __device__ int row_cols() const { return cols_; }   // length of a stored weight row (four-row body only: see BDownSplitPolicy)
+    __device__ int col0() const { return 0; }           // first column this launch contracts
 };
 
 // A: RMSNorm -> [Wq;Wk;Wv] -> RoPE(q, k) -> q buffer, K/V rows of position pos[s] in the slot's page
@@ -317,6 +324,26 @@ struct BResidualPolicy : BatchBase {
         const size_t o = (size_t)(b0 + b) * nrows + 2 * (size_t)u;
         y[o] = resid[o] + s0;  // add_kernel.cpp:10-13: out = in1 + in2
         if (2 * u + 1 < nrows) y[o + 1] = resid[o + 1] + s1;
+    }
+};
+
+// E', experimental (sllm_tune key 7, four-row body only): the down projection with K cut in two over grid.y, so that 8 vectors
+// of HALF a row fit shared memory and Wdown is read once for up to 8 sequences instead of once per 5. Each half writes its
+// partial sums; batch_add_partials_kernel then forms x = h + (p0 + p1). cols_ = the half's length.
+template <int WD>
+struct BDownSplitPolicy : BatchBase {
+    const float* x;       // GEMV input [slots][row_cols_]
+    float* part;          // [2][slots_total][nrows] partial sums
+    int nrows, row_cols_, slots_total;
+    __device__ int row_cols() const { return row_cols_; }
+    __device__ int col0() const { return (int)blockIdx.y * cols_; }
+    __device__ int units() const { return (nrows + 1) >> 1; }
+    __device__ void rows(int u, int64_t& r0, int64_t& r1) const { r0 = 2 * (int64_t)u; r1 = min(2 * u + 1, nrows - 1); }
+    __device__ void stage(int b, float* xs, float*) const { stage_x_plain<WD>(xs, x + (size_t)(b0 + b) * row_cols_ + col0(), cols_); }
+    __device__ void emit(int u, int b, float s0, float s1) const {
+        const size_t o = ((size_t)blockIdx.y * slots_total + (b0 + b)) * nrows + 2 * (size_t)u;
+        part[o] = s0;
+        if (2 * u + 1 < nrows) part[o + 1] = s1;
     }
 };
 

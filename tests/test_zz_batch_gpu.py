@@ -436,3 +436,22 @@ def test_sampling_per_slot_matches_the_single_sequence_sampler(port):
     assert np.array_equal(out[rid], got[a]) and np.array_equal(out[rid2], want_g)
     bd.close(); eng.close()
 
+
+@first_run
+@pytest.mark.parametrize("wd", [F32, BF16, INT8])
+def test_split_down_projection_matches_oracle(port, wd):
+    """Opt-in development knobs sllm_tune(6, 1) + (7, 1): with an intermediate size whose rows do not fit shared memory eight
+    times (8192 floats: 7 fit), eight live sequences take the down projection with K cut in two over grid.y (eight half rows
+    fit) and x = h + (p0 + p1). A different summation split, so the check is the oracle per sequence, not bit-identity."""
+    lib = _lib.load()
+    ms = ModelShape(512, 32, 128, 64, 8192, 48, 2, 4, 2)
+    prompts = [[3 + i, 90 + 2 * i] for i in range(9)]
+    for key in (6, 7):
+        _lib.check(lib.sllm_tune(key, 1))
+    try:
+        eng, bd, _ = run_ragged(port, ms, wd, F32, 23, prompts, joins=[0] * 8 + [5], n_steps=20, page_len=8, max_seqs=9)   # seed: oracle margins >= 7e-3
+        bd.close(); eng.close()
+    finally:
+        for key in (6, 7):
+            lib.sllm_tune(key, 0)
+

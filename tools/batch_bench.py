@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--json", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step (sllm_tune key 5, experimental) instead of the launch sequence")
     ap.add_argument("--rows4", action="store_true", help="GEMV body with four weight rows per warp at a time for >= 3 sequences (sllm_tune key 6, experimental)")
+    ap.add_argument("--ksplit", action="store_true", help="with --rows4: down projection with K cut in two over grid.y (sllm_tune key 7, experimental)")
     args = ap.parse_args()
 
     import dataclasses
@@ -57,10 +58,11 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
-    if args.graph or args.rows4:
+    if args.graph or args.rows4 or args.ksplit:
         from simplellminference_b200 import _lib
         _lib.check(_lib.load().sllm_tune(5, 1 if args.graph else 0))
         _lib.check(_lib.load().sllm_tune(6, 1 if args.rows4 else 0))
+        _lib.check(_lib.load().sllm_tune(7, 1 if args.ksplit else 0))
     rng = np.random.default_rng(1)
     rows = []
     for B in batches:
@@ -91,6 +93,7 @@ def main():
         bd.close()
     out = {"launch": "one CUDA graph per step (sllm_tune 5, experimental)" if args.graph else "direct launch sequence",
            "gemv_body": "four weight rows per warp for >= 3 sequences (sllm_tune 6, experimental)" if args.rows4 else "two weight rows per warp",
+           "down_projection": "K halves over grid.y when whole rows do not fit (sllm_tune 7, experimental)" if args.ksplit else "whole rows, in groups that fit shared memory",
            "what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, "
                    f"every sequence at positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; "
                    "algorithmic bytes = weights once per step + each sequence's K/V rows",
