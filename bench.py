@@ -215,25 +215,34 @@ def workload_config(args, ms):
 
 def batch_decode_sample(args):
     """Secondary figure: aggregate tokens/s of the batched multi-sequence decode (sllm_batch_*, tools/batch_bench.py) on the
-    same model shape and context. Runs in a CHILD process after every timed region of this one and after its engine is
-    gone: whatever happens there (error, time-out) is reported in its place and never costs the headline numbers."""
-    def child(extra, batches):
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
-               "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", batches, "--steps", "64", "--json"] + extra
+    same model shape and context: plain (1 / 4 / 8 / 16 sequences), then the experimental launch / kernel variants (8 / 16).
+    Runs in ONE child process after every timed region of this one and after its engine is gone; the child prints a JSON line
+    per variant as it goes, so whatever happens there (error, time-out) costs only the variants not yet printed and never
+    the headline numbers."""
+    variants = ["plain", "graph", "graph+rows4", "graph+rows4+ksplit"]
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
+           "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", "1,4,8,16", "--exp-batches", "8,16",
+           "--variants", ",".join(variants), "--steps", "64", "--json"]
+    stdout, note = "", None
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        stdout = r.stdout or ""
+        if r.returncode != 0:
+            note = f"exit {r.returncode}: {(r.stderr or '').strip()[-300:]}"
+    except subprocess.TimeoutExpired as ex:
+        stdout = ex.stdout.decode(errors="replace") if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+        note = "timed out after 240 s"
+    except Exception as ex:
+        note = repr(ex)[:300]
+    got = {}
+    for ln in stdout.splitlines():
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
-            if r.returncode != 0:
-                return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
-            return json.loads(r.stdout.strip().splitlines()[-1])
-        except Exception as ex:
-            return {"error": repr(ex)[:300]}
-
-    out = child([], "1,4,8,16")
-    # the same steps replayed as one CUDA graph each (development knob, first measured here): its own child, so that a failure
-    # of the experimental launch path cannot take the plain figures with it
-    out["graph_replay"] = child(["--graph"], "8,16") if "error" not in out else None
-    out["graph_replay_four_row_gemv"] = child(["--graph", "--rows4"], "8,16") if "error" not in out else None
-    out["graph_replay_four_row_gemv_split_down"] = child(["--graph", "--rows4", "--ksplit"], "8,16") if "error" not in out else None
+            d = json.loads(ln)
+            got[d["variant"]] = d
+        except Exception:
+            continue
+    out = got.get("plain") or {"error": note or "no output"}
+    out["experimental"] = {v: got.get(v) or {"error": note or "not reached"} for v in variants[1:]}
     return out
 
 

@@ -3,12 +3,14 @@
 of sequences stepping together, next to its HBM roofline.
 
   python tools/batch_bench.py [--config llama2-7b] [--batches 1,2,4,8,16] [--context 512] [--steps 64] [--json]
+                              [--variants plain,graph,graph+rows4,graph+rows4+ksplit] [--exp-batches 8,16]
 
 Every sequence first decodes `context` tokens (untimed), then `steps` tokens are timed with CUDA events on the batch's
 stream; weights are synthetic (bf16 by default), the cache pages bf16. Algorithmic bytes of a step = every weight once
 + per sequence its K/V rows (sllm_batch_step_bytes), so the roofline fraction says how close the shared weight pass
-stays to the HBM rate as the FMA work per weight grows with the batch. With --json the last stdout line is one JSON
-object (bench.py attaches it to its own line as "batch_decode")."""
+stays to the HBM rate as the FMA work per weight grows with the batch. Variants other than "plain" switch on the
+experimental development knobs (sllm_tune 5 / 6 / 7). With --json every variant prints one JSON line as soon as it is
+done (bench.py attaches them to its own line as "batch_decode"; a variant that crashes loses only itself and its successors)."""
 from __future__ import annotations
 
 import argparse
@@ -20,24 +22,32 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+VARIANTS = {   # name -> sllm_tune keys switched on (5 graph replay, 6 four-row GEMV body, 7 K-split down projection: all experimental)
+    "plain": (),
+    "graph": (5,),
+    "graph+rows4": (5, 6),
+    "graph+rows4+ksplit": (5, 6, 7),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="llama2-7b")
     ap.add_argument("--wdtype", default="bf16", choices=["f32", "bf16", "int8"])
     ap.add_argument("--kvdtype", default="bf16", choices=["f32", "bf16"])
-    ap.add_argument("--batches", default="1,2,4,8,16")
+    ap.add_argument("--batches", default="1,2,4,8,16", help="sequence counts for the plain variant")
+    ap.add_argument("--exp-batches", default="8,16", help="sequence counts for the experimental variants")
+    ap.add_argument("--variants", default="plain", help="comma list out of: " + ", ".join(VARIANTS))
     ap.add_argument("--context", type=int, default=512)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--page-len", type=int, default=64)
-    ap.add_argument("--json", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step (sllm_tune key 5, experimental) instead of the launch sequence")
-    ap.add_argument("--rows4", action="store_true", help="GEMV body with four weight rows per warp at a time for >= 3 sequences (sllm_tune key 6, experimental)")
-    ap.add_argument("--ksplit", action="store_true", help="with --rows4: down projection with K cut in two over grid.y (sllm_tune key 7, experimental)")
+    ap.add_argument("--json", action="store_true", help="one JSON line per variant on stdout, printed as soon as the variant is done")
     args = ap.parse_args()
 
     import dataclasses
     import numpy as np
     import torch
+    from simplellminference_b200 import _lib
     from simplellminference_b200.batch import BatchDecoder
     from simplellminference_b200.config import PRESETS, F32, BF16, INT8
     from simplellminference_b200.engine import Engine
@@ -45,7 +55,10 @@ def main():
     torch.cuda.set_device(0)
     wd = {"f32": F32, "bf16": BF16, "int8": INT8}[args.wdtype]
     kvd = {"f32": F32, "bf16": BF16}[args.kvdtype]
-    batches = [int(b) for b in args.batches.split(",")]
+    variants = [v.strip() for v in args.variants.split(",") if v.strip()]
+    for v in variants:
+        if v not in VARIANTS:
+            raise SystemExit(f"unknown variant {v!r}")
     need = args.context + args.steps + 8
     # the engine only lends its weights and RoPE tables here: keep its own (unused) dense cache small
     ms = dataclasses.replace(PRESETS[args.config], max_len=max(need, 64))
@@ -58,49 +71,47 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
-    if args.graph or args.rows4 or args.ksplit:
-        from simplellminference_b200 import _lib
-        _lib.check(_lib.load().sllm_tune(5, 1 if args.graph else 0))
-        _lib.check(_lib.load().sllm_tune(6, 1 if args.rows4 else 0))
-        _lib.check(_lib.load().sllm_tune(7, 1 if args.ksplit else 0))
-    rng = np.random.default_rng(1)
-    rows = []
-    for B in batches:
-        bd = BatchDecoder(eng, max_seqs=B, page_len=args.page_len, kv_dtype=kvd)
-        for _ in range(B):
-            bd.add([int(rng.integers(1, ms.vocab))])
-        bd.step(args.context)                      # untimed: fills every sequence's pages up to the context
-        torch.cuda.synchronize()
-        bytes0 = bd.step_bytes()
-        launches0 = bd.total_launches
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        bd.step(args.steps)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        ms_total = ev0.elapsed_time(ev1)
-        step_bytes = 0.5 * (bytes0 + bd.step_bytes())   # mean over the timed positions (linear in the position)
-        t_step = ms_total * 1e-3 / args.steps
-        ach = step_bytes / t_step / 1e9
-        rows.append({"sequences": B, "tokens_per_sec": B * args.steps / (ms_total * 1e-3), "ms_per_step": 1e3 * t_step,
-                     "bytes_per_step": step_bytes, "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak,
-                     "launches_per_step": (bd.total_launches - launches0) / args.steps,
-                     "checksum": int(sum(int(bd.tokens(s)[-1]) for s in range(B)) % 1000003)})
-        if not args.json:
-            r = rows[-1]
-            print(f"B={B:3d}  {r['tokens_per_sec']:9.1f} tok/s  {r['ms_per_step']:7.3f} ms/step  {r['achieved_gbs']:7.0f} GB/s "
-                  f"({100 * r['frac_of_hbm_peak']:.1f} % of {peak:.0f})  {r['launches_per_step']:.0f} launches/step", flush=True)
-        bd.close()
-    out = {"launch": "one CUDA graph per step (sllm_tune 5, experimental)" if args.graph else "direct launch sequence",
-           "gemv_body": "four weight rows per warp for >= 3 sequences (sllm_tune 6, experimental)" if args.rows4 else "two weight rows per warp",
-           "down_projection": "K halves over grid.y when whole rows do not fit (sllm_tune 7, experimental)" if args.ksplit else "whole rows, in groups that fit shared memory",
-           "what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, "
-                   f"every sequence at positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; "
-                   "algorithmic bytes = weights once per step + each sequence's K/V rows",
-           "peak_gbs": peak, "peak_source": peak_src, "steps": args.steps, "by_batch": rows}
+    lib = _lib.load()
+    for v in variants:
+        for key in (5, 6, 7):
+            _lib.check(lib.sllm_tune(key, 1 if key in VARIANTS[v] else 0))
+        rng = np.random.default_rng(1)
+        rows = []
+        for B in [int(b) for b in (args.batches if v == "plain" else args.exp_batches).split(",")]:
+            bd = BatchDecoder(eng, max_seqs=B, page_len=args.page_len, kv_dtype=kvd)
+            for _ in range(B):
+                bd.add([int(rng.integers(1, ms.vocab))])
+            bd.step(args.context)                      # untimed: fills every sequence's pages up to the context
+            torch.cuda.synchronize()
+            bytes0 = bd.step_bytes()
+            launches0 = bd.total_launches
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            bd.step(args.steps)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms_total = ev0.elapsed_time(ev1)
+            step_bytes = 0.5 * (bytes0 + bd.step_bytes())   # mean over the timed positions (linear in the position)
+            t_step = ms_total * 1e-3 / args.steps
+            ach = step_bytes / t_step / 1e9
+            rows.append({"sequences": B, "tokens_per_sec": B * args.steps / (ms_total * 1e-3), "ms_per_step": 1e3 * t_step,
+                         "bytes_per_step": step_bytes, "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak,
+                         "kernels_per_step": (bd.total_launches - launches0) / args.steps,
+                         "checksum": int(sum(int(bd.tokens(s)[-1]) for s in range(B)) % 1000003)})
+            if not args.json:
+                r = rows[-1]
+                print(f"{v:20s} B={B:3d}  {r['tokens_per_sec']:9.1f} tok/s  {r['ms_per_step']:7.3f} ms/step  {r['achieved_gbs']:7.0f} GB/s "
+                      f"({100 * r['frac_of_hbm_peak']:.1f} % of {peak:.0f})  {r['kernels_per_step']:.0f} kernels/step", flush=True)
+            bd.close()
+        if args.json:
+            print(json.dumps({"variant": v, "tune_keys_on": list(VARIANTS[v]),
+                              "what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, every sequence at "
+                                      f"positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; algorithmic bytes = weights "
+                                      "once per step + each sequence's K/V rows",
+                              "peak_gbs": peak, "peak_source": peak_src, "steps": args.steps, "by_batch": rows}), flush=True)
+    for key in (5, 6, 7):
+        lib.sllm_tune(key, 0)
     eng.close()
-    if args.json:
-        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
