@@ -72,7 +72,7 @@ def main():
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
     lib = _lib.load()
-    for v in variants:
+    def run_variant(v):
         for key in (5, 6, 7):
             _lib.check(lib.sllm_tune(key, 1 if key in VARIANTS[v] else 0))
         rng = np.random.default_rng(1)
@@ -109,9 +109,22 @@ def main():
                                       f"positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; algorithmic bytes = weights "
                                       "once per step + each sequence's K/V rows",
                               "peak_gbs": peak, "peak_source": peak_src, "steps": args.steps, "by_batch": rows}), flush=True)
+
+    failed = 0
+    for v in variants:
+        try:
+            run_variant(v)
+        except Exception as ex:   # an error that left the CUDA context usable must not cost the variants after it
+            failed += 1
+            if args.json:
+                print(json.dumps({"variant": v, "error": repr(ex)[:300]}), flush=True)
+            else:
+                print(f"{v}: FAILED {ex!r}", flush=True)
     for key in (5, 6, 7):
         lib.sllm_tune(key, 0)
     eng.close()
+    if failed:
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":
