@@ -425,7 +425,7 @@ def run_ours(args):
         eng.close()
         batch = batch_decode_sample(args)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only (it costs ~10 s of host time)
         try:
             cpu = cpu_reference_sample(ms, P, 5, 1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -14,6 +14,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _gpu_watchdog(request):
+    """A GPU test that is stuck inside a CUDA call cannot be interrupted by pytest-timeout's signal method (the handler
+    only runs once the C call returns), and a process that never exits holds the GPU box until it is killed from outside.
+    So every gpu-marked test also arms a hard watchdog: stacks are dumped and the process exits if one test runs for
+    25 minutes (far beyond the slowest test; the per-test pytest timeouts stay the normal mechanism)."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import faulthandler
+    faulthandler.dump_traceback_later(1500, exit=True)
+    try:
+        yield
+    finally:
+        faulthandler.cancel_dump_traceback_later()
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _scratch_cwd(tmp_path_factory):
     # the reference's forward() opens layer_outputs_cpu.txt in the cwd on every call (model.cpp:42)
