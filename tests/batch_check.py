@@ -83,7 +83,15 @@ def main():
              ("four-row gemv hd48", lambda: T.test_four_row_gemv_body_is_bit_identical("tiny_mha_hd48", F32)),
              ("full width 7B x 2 layers, 8 sequences", lambda: T.test_full_width_llama2_7b_two_layers_batch_of_eight(port)),
              ("long context 8 kv heads", lambda: T.test_long_context_many_slots_split_kv(port, 8, 8)),
-             ("long context gqa", lambda: T.test_long_context_many_slots_split_kv(port, 8, 2))]
+             ("long context gqa", lambda: T.test_long_context_many_slots_split_kv(port, 8, 2)),
+             ("per-slot sampling", lambda: T.test_sampling_per_slot_matches_the_single_sequence_sampler(port)),
+             ("split down f32", lambda: T.test_split_down_projection_matches_oracle(port, F32)),
+             ("split down bf16", lambda: T.test_split_down_projection_matches_oracle(port, BF16)),
+             ("split down int8", lambda: T.test_split_down_projection_matches_oracle(port, INT8))]
+    import numpy as _np
+    gm = dict(_np.load(os.path.join(ROOT, "tests", "golden", "models_ref.npz")))
+    for gname in ("cfg1_stories15M", "cfg2_stories110M", "tiny_gqa", "tiny_gqa_bf16w", "tiny_gqa_int8w", "tiny_mha_hd48"):
+        cases.append((f"golden stream {gname}", lambda gname=gname: T.test_golden_streams_of_the_reference_inside_a_batch(gm, gname)))
     ok = 0
     for name, fn in cases:
         try:
