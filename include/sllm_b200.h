@@ -222,6 +222,19 @@ int sllm_engine_read_tokens(sllm_engine* e, int32_t* tokens_out_host, int32_t n)
 int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt_host, int32_t n, int32_t start_pos);
 int sllm_engine_prefill_supported(const sllm_engine* e);
 
+/* How the persistent decode megakernel (SLLM_ENGINE_MEGAKERNEL; replaces the layer loop of LlamaModel::forward,
+ * source/model/model.cpp:48-139, by one launch per token) would run a shape — host arithmetic only, no launch, and no device
+ * either when the two device facts are passed in (sm_count_or_0 / smem_optin_or_0 > 0; 0 = ask the current device):
+ * *ok = 1 and grid (= CTAs = SMs), dynamic shared memory per CTA, KV splits per head of the attention phase; or *ok = 0 with the
+ * reason in sllm_last_error (the engine then runs the per-kernel fused path: sllm_engine_mode()). tp_size > 1 plans one rank's shard. */
+int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t sm_count_or_0,
+                   int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit);
+/* The tiled weight layout of that kernel for one [rows][cols] matrix (kind: 0 qkv, 1 wo, 2 [up; gate], 3 down, 4 classifier):
+ * tiles of r physical rows x sc 16-byte chunks, ks K slices per row, tile_rows tile rows, one tile = tile_bytes contiguous bytes
+ * (= one TMA bulk copy = one ring slot), the matrix = tile_rows * ks * tile_bytes = matrix_bytes (zero padding included). */
+int sllm_mega_tile_geometry(int32_t rows, int32_t cols, int32_t kind, int32_t w_dtype, int32_t* ks, int32_t* sc, int32_t* r,
+                            int32_t* tile_rows, int32_t* tile_bytes, int64_t* matrix_bytes);
+
 /* The two prefill kernels on their own (device pointers), for op-level parity tests:
  * C[T][N] (fp32) = A[T][K] (bf16) . W[N][K]^T (bf16, row-major) on tcgen05; bn = 0 (auto), 128 or 256 = N tile. */
 int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, int32_t T, int32_t N, int32_t K, int32_t bn,

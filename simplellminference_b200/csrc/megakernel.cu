@@ -659,6 +659,12 @@ static void fill_desc(PhaseDesc& ds, const void* W, int rows, int cols, int kind
 
 // can the megakernel run this shape? (everything else keeps using the per-kernel fused path)
 MegaPlan mega_plan(int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len) {
+    return mega_plan_for(sm_count(), smem_optin_bytes(), w_dtype, group, kv_dtype, d, hd, q_loc, kv_loc, I_loc, V_loc, H_loc, KVH_loc, max_len);
+}
+
+// the plan as a pure function of the device facts (SM count, opt-in shared memory per block): testable without a device
+MegaPlan mega_plan_for(int sms, int smem_optin, int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc,
+                       int H_loc, int KVH_loc, int max_len) {
     MegaPlan pl;
     if (w_dtype == SLLM_INT8 && group != 64) { pl.why = "int8 group size other than 64"; return pl; }
     const int E = w_dtype == SLLM_F32 ? 4 : w_dtype == SLLM_BF16 ? 8 : 16;
@@ -675,11 +681,11 @@ MegaPlan mega_plan(int w_dtype, int group, int kv_dtype, int d, int hd, int q_lo
     const int kesz = kv_dtype == SLLM_F32 ? 4 : 2;
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaSmem SL = mega_smem_layout(hd, g, kesz);
-    if (SL.total > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
+    if (SL.total > (size_t)smem_optin) { pl.why = "shared memory"; return pl; }
     if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
     if ((size_t)std::max(d, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 2 || kv_loc % 2) { pl.why = "odd dims"; return pl; }
-    pl.grid = sm_count();
+    pl.grid = sms;
     pl.smem = SL.total;
     // splits: fill the grid once, never more splits than 64-position tiles at full context
     int ns = pl.grid / KVH_loc;
@@ -840,3 +846,49 @@ int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t 
 }
 
 }  // namespace sllm
+
+// ---- the host-side plan through the C ABI (pure arithmetic, no launch, no device needed when the facts are passed in) ----
+extern "C" {
+
+int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t sm_count_or_0,
+                   int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit) {
+    using namespace sllm;
+    SLLM_REQUIRE(shape && ok, SLLM_EINVAL, "mega_plan: null argument");
+    SLLM_REQUIRE(w_dtype == SLLM_F32 || w_dtype == SLLM_BF16 || w_dtype == SLLM_INT8, SLLM_EINVAL, "mega_plan: weight dtype %d", w_dtype);
+    SLLM_REQUIRE(kv_dtype == SLLM_F32 || kv_dtype == SLLM_BF16, SLLM_EINVAL, "mega_plan: kv dtype %d", kv_dtype);
+    SLLM_REQUIRE(tp_size >= 1 && shape->heads > 0 && shape->kv_heads > 0 && shape->head_dim > 0 && shape->heads % shape->kv_heads == 0 &&
+                     shape->heads % tp_size == 0 && shape->kv_heads % tp_size == 0 && shape->inter % tp_size == 0 && shape->vocab % tp_size == 0,
+                 SLLM_EINVAL, "mega_plan: heads=%d kv_heads=%d inter=%d vocab=%d must divide by tp_size=%d", shape->heads, shape->kv_heads,
+                 shape->inter, shape->vocab, tp_size);
+    const int H_loc = shape->heads / tp_size, KVH_loc = shape->kv_heads / tp_size;
+    const MegaPlan pl = mega_plan_for(sm_count_or_0 > 0 ? sm_count_or_0 : sm_count(), smem_optin_or_0 > 0 ? smem_optin_or_0 : smem_optin_bytes(),
+                                      w_dtype, group, kv_dtype, shape->hidden, shape->head_dim, H_loc * shape->head_dim, KVH_loc * shape->head_dim,
+                                      shape->inter / tp_size, shape->vocab / tp_size, H_loc, KVH_loc, shape->max_len);
+    *ok = pl.ok ? 1 : 0;
+    if (grid) *grid = pl.grid;
+    if (smem_bytes) *smem_bytes = (int64_t)pl.smem;
+    if (nsplit) *nsplit = pl.nsplit;
+    if (!pl.ok) set_error("megakernel cannot take this shape: %s", pl.why);
+    return SLLM_OK;
+}
+
+int sllm_mega_tile_geometry(int32_t rows, int32_t cols, int32_t kind, int32_t w_dtype, int32_t* ks, int32_t* sc, int32_t* r, int32_t* tile_rows,
+                            int32_t* tile_bytes, int64_t* matrix_bytes) {
+    using namespace sllm;
+    SLLM_REQUIRE(rows >= 1 && cols >= 1 && kind >= PH_QKV && kind <= PH_CLS, SLLM_EINVAL, "mega_tile_geometry: rows=%d cols=%d kind=%d", rows, cols, kind);
+    SLLM_REQUIRE(w_dtype == SLLM_F32 || w_dtype == SLLM_BF16 || w_dtype == SLLM_INT8, SLLM_EINVAL, "mega_tile_geometry: weight dtype %d", w_dtype);
+    const int E = w_dtype == SLLM_F32 ? 4 : w_dtype == SLLM_BF16 ? 8 : 16;
+    SLLM_REQUIRE(cols % E == 0, SLLM_EINVAL, "mega_tile_geometry: cols=%d is not a multiple of %d (16 bytes of weights)", cols, E);
+    const TileGeom g = mega_tile_geom(phys_rows(rows, kind), cols, w_dtype);
+    SLLM_REQUIRE(g.KS * g.SC >= g.nchunks && g.tile_bytes <= kSlotBytes, SLLM_ENOTSUP,
+                 "mega_tile_geometry: rows of %d columns are longer than 32 KB (a two-row tile must fit a %d-byte ring slot)", cols, kSlotBytes);
+    if (ks) *ks = g.KS;
+    if (sc) *sc = g.SC;
+    if (r) *r = g.R;
+    if (tile_rows) *tile_rows = g.ntr;
+    if (tile_bytes) *tile_bytes = g.tile_bytes;
+    if (matrix_bytes) *matrix_bytes = (int64_t)g.bytes;
+    return SLLM_OK;
+}
+
+}  // extern "C"

@@ -95,6 +95,8 @@ struct MegaPlan {
 };
 
 MegaPlan mega_plan(int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int H_loc, int KVH_loc, int max_len);
+MegaPlan mega_plan_for(int sms, int smem_optin, int w_dtype, int group, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc,
+                       int H_loc, int KVH_loc, int max_len);
 void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, const void* wo, const void* wug, const void* wdown,
                       const void* cls, int d, int q_loc, int kv_loc, int I_loc, int V_loc);
 // row-major [rows][cols] (storage dtype) -> tiled layout in unit order. kind: PH_* (row pairing rule).
