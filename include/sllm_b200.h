@@ -226,9 +226,11 @@ int sllm_engine_prefill_supported(const sllm_engine* e);
  * source/model/model.cpp:48-139, by one launch per token) would run a shape — host arithmetic only, no launch, and no device
  * either when the two device facts are passed in (sm_count_or_0 / smem_optin_or_0 > 0; 0 = ask the current device):
  * *ok = 1 and grid (= CTAs = SMs), dynamic shared memory per CTA, KV splits per head of the attention phase; or *ok = 0 with the
- * reason in sllm_last_error (the engine then runs the per-kernel fused path: sllm_engine_mode()). tp_size > 1 plans one rank's shard. */
-int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t sm_count_or_0,
-                   int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit);
+ * reason in sllm_last_error (the engine then runs the per-kernel fused path: sllm_engine_mode()). word_based = 0: the grid-barrier kernel
+ * (one GPU); 1: the barrier-free {value, epoch}-word kernel (SLLM_ENGINE_MEGA_LL; the one that runs under tensor parallelism,
+ * tp_size > 1 plans one rank's shard; its grid may be smaller than the SM count: every CTA must own a tile row of every phase). */
+int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t word_based,
+                   int32_t sm_count_or_0, int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit);
 /* The tiled weight layout of that kernel for one [rows][cols] matrix (kind: 0 qkv, 1 wo, 2 [up; gate], 3 down, 4 classifier):
  * tiles of r physical rows x sc 16-byte chunks, ks K slices per row, tile_rows tile rows, one tile = tile_bytes contiguous bytes
  * (= one TMA bulk copy = one ring slot), the matrix = tile_rows * ks * tile_bytes = matrix_bytes (zero padding included). */

@@ -677,7 +677,7 @@ MegaPlan mega_plan_for(int sms, int smem_optin, int w_dtype, int group, int kv_d
         }
     }
     const int g = H_loc / KVH_loc;
-    if (g > 8 || hd % 16 || hd > 256) { pl.why = "head shape"; return pl; }
+    if ((g != 1 && g != 2 && g != 4 && g != 8) || hd % 16 || hd > 256) { pl.why = "head shape"; return pl; }   // the instantiated query-head group sizes (mega_launch)
     const int kesz = kv_dtype == SLLM_F32 ? 4 : 2;
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaSmem SL = mega_smem_layout(hd, g, kesz);
@@ -850,8 +850,8 @@ int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t 
 // ---- the host-side plan through the C ABI (pure arithmetic, no launch, no device needed when the facts are passed in) ----
 extern "C" {
 
-int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t sm_count_or_0,
-                   int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit) {
+int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int32_t kv_dtype, int32_t tp_size, int32_t word_based,
+                   int32_t sm_count_or_0, int32_t smem_optin_or_0, int32_t* ok, int32_t* grid, int64_t* smem_bytes, int32_t* nsplit) {
     using namespace sllm;
     SLLM_REQUIRE(shape && ok, SLLM_EINVAL, "mega_plan: null argument");
     SLLM_REQUIRE(w_dtype == SLLM_F32 || w_dtype == SLLM_BF16 || w_dtype == SLLM_INT8, SLLM_EINVAL, "mega_plan: weight dtype %d", w_dtype);
@@ -861,9 +861,21 @@ int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int3
                  SLLM_EINVAL, "mega_plan: heads=%d kv_heads=%d inter=%d vocab=%d must divide by tp_size=%d", shape->heads, shape->kv_heads,
                  shape->inter, shape->vocab, tp_size);
     const int H_loc = shape->heads / tp_size, KVH_loc = shape->kv_heads / tp_size;
-    const MegaPlan pl = mega_plan_for(sm_count_or_0 > 0 ? sm_count_or_0 : sm_count(), smem_optin_or_0 > 0 ? smem_optin_or_0 : smem_optin_bytes(),
-                                      w_dtype, group, kv_dtype, shape->hidden, shape->head_dim, H_loc * shape->head_dim, KVH_loc * shape->head_dim,
-                                      shape->inter / tp_size, shape->vocab / tp_size, H_loc, KVH_loc, shape->max_len);
+    const int sms = sm_count_or_0 > 0 ? sm_count_or_0 : sm_count(), smem = smem_optin_or_0 > 0 ? smem_optin_or_0 : smem_optin_bytes();
+    SLLM_REQUIRE(tp_size == 1 || word_based, SLLM_EINVAL, "mega_plan: under tensor parallelism only the word-based kernel runs (it carries the all-reduce)");
+    if (word_based) {   // megakernel_ll.cu; rank 0's shard (v0 = 0: every rank's vocabulary offset is a multiple of the same V_loc)
+        const MegaLLPlan ll = mega_ll_plan_for(sms, smem, w_dtype, kv_dtype, shape->hidden, shape->head_dim, H_loc * shape->head_dim,
+                                               KVH_loc * shape->head_dim, shape->inter / tp_size, shape->vocab / tp_size, 0, H_loc, KVH_loc,
+                                               shape->max_len, tp_size);
+        *ok = ll.ok ? 1 : 0;
+        if (grid) *grid = ll.grid;
+        if (smem_bytes) *smem_bytes = (int64_t)ll.smem;
+        if (nsplit) *nsplit = ll.nsplit;
+        if (!ll.ok) set_error("the word-based megakernel cannot take this shape: %s", ll.why);
+        return SLLM_OK;
+    }
+    const MegaPlan pl = mega_plan_for(sms, smem, w_dtype, group, kv_dtype, shape->hidden, shape->head_dim, H_loc * shape->head_dim,
+                                      KVH_loc * shape->head_dim, shape->inter / tp_size, shape->vocab / tp_size, H_loc, KVH_loc, shape->max_len);
     *ok = pl.ok ? 1 : 0;
     if (grid) *grid = pl.grid;
     if (smem_bytes) *smem_bytes = (int64_t)pl.smem;

@@ -83,6 +83,8 @@ struct MegaLLPlan {
 };
 MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0, int H_loc, int KVH_loc,
                         int max_len, int tp);
+MegaLLPlan mega_ll_plan_for(int sms, int smem_optin, int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0,
+                            int H_loc, int KVH_loc, int max_len, int tp);
 int mega_ll_launch(const MegaLLParams& p, int g, int grid, size_t smem, cudaStream_t st);
 
 struct MegaPlan {

@@ -767,6 +767,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
 // ------------------------------------------------------------------------------------------- host ----
 MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0, int H_loc, int KVH_loc,
                         int max_len, int tp) {
+    return mega_ll_plan_for(sm_count(), smem_optin_bytes(), w_dtype, kv_dtype, d, hd, q_loc, kv_loc, I_loc, V_loc, v0, H_loc, KVH_loc, max_len, tp);
+}
+
+// the plan as a pure function of the device facts (testable without a device: sllm_mega_plan)
+MegaLLPlan mega_ll_plan_for(int sms, int smem_optin, int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0,
+                            int H_loc, int KVH_loc, int max_len, int tp) {
     MegaLLPlan pl;
     if (w_dtype == SLLM_INT8) { pl.why = "int8 weights"; return pl; }
     if (tp > kMaxTp) { pl.why = "more than 8 ranks"; return pl; }
@@ -782,13 +788,13 @@ MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int
     const int kesz = kv_dtype == SLLM_F32 ? 4 : 2;
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaLLSmem SL = mega_ll_smem_layout(d, hd, g, kesz);
-    if (SL.total + 1024 > (size_t)smem_optin_bytes()) { pl.why = "shared memory"; return pl; }
+    if (SL.total + 1024 > (size_t)smem_optin) { pl.why = "shared memory"; return pl; }
     if ((size_t)g * hd * 4 + (size_t)g * kAttTile * 4 + 256 > (size_t)kRoundUnits * 2 * kMegaWarps * 4) { pl.why = "attention scratch (q/p)"; return pl; }
     if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
     if ((size_t)std::max(q_loc, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 4 || kv_loc % 2 || I_loc % 4 || d % 4) { pl.why = "dims not multiples of 4"; return pl; }
     // every CTA must own >= 1 tile row of every weight phase (see the safety argument at the top of this file)
-    int grid = sm_count();
+    int grid = sms;
     const int rows_kind[4][3] = {{q_loc + 2 * kv_loc, d, PH_QKV}, {d, q_loc, PH_WO}, {2 * I_loc, d, PH_GATEUP}, {d, I_loc, PH_DOWN}};
     for (auto& rk : rows_kind) grid = std::min(grid, mega_tile_geom(rk[2] == PH_GATEUP ? rk[0] : ((rk[0] + 1) / 2) * 2, rk[1], w_dtype).ntr);
     const TileGeom cg = mega_tile_geom(((V_loc + 1) / 2) * 2, d, w_dtype);

@@ -20,10 +20,12 @@ def c_shape(ms):
     return _lib.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, ms.layers, ms.heads, ms.kv_heads, ms.eps, ms.theta)
 
 
-def plan(ms, wd, kvd, tp=1, group=64, sms=B200_SMS, smem=B200_SMEM):
+def plan(ms, wd, kvd, tp=1, group=64, sms=B200_SMS, smem=B200_SMEM, word_based=None):
+    """word_based None: what the engine picks (the grid-barrier kernel on one GPU, the word-based one under tensor parallelism)"""
     lib = _lib.load()
     ok, grid, nsplit, nbytes = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
-    _lib.check(lib.sllm_mega_plan(C.byref(c_shape(ms)), wd, group, kvd, tp, sms, smem, C.byref(ok), C.byref(grid), C.byref(nbytes), C.byref(nsplit)))
+    wb = int(tp > 1) if word_based is None else int(word_based)
+    _lib.check(lib.sllm_mega_plan(C.byref(c_shape(ms)), wd, group, kvd, tp, wb, sms, smem, C.byref(ok), C.byref(grid), C.byref(nbytes), C.byref(nsplit)))
     why = lib.sllm_last_error().decode() if not ok.value else ""
     return bool(ok.value), grid.value, nbytes.value, nsplit.value, why
 
@@ -37,8 +39,8 @@ def geometry(rows, cols, kind, wd):
 
 @pytest.mark.parametrize("name,wd,kvd,tp", [
     ("stories110M", F32, F32, 1), ("tinyllama-1.1b", BF16, BF16, 1), ("tinyllama-1.1b", INT8, BF16, 1),
-    ("llama2-7b", BF16, BF16, 1), ("llama2-7b", INT8, BF16, 1), ("llama2-7b", BF16, BF16, 2), ("llama2-7b", BF16, BF16, 8),
-    ("llama3-8b", BF16, BF16, 1), ("llama3-8b", BF16, BF16, 8)])
+    ("llama2-7b", BF16, BF16, 1), ("llama2-7b", INT8, BF16, 1), ("llama2-7b", BF16, BF16, 2), ("llama2-7b", BF16, BF16, 4),
+    ("llama2-7b", BF16, BF16, 8), ("llama3-8b", BF16, BF16, 1), ("llama3-8b", BF16, BF16, 8)])
 def test_benchmark_configurations_run_as_one_launch_per_token(name, wd, kvd, tp):
     """Every BASELINE.json configuration that is benchmarked through the megakernel gets a plan on a B200: one CTA per SM, within
     the opt-in shared memory, and at most one 64-position tile per KV split at full context."""
@@ -72,8 +74,31 @@ def test_shapes_the_megakernel_declines_say_why():
     assert not ok and why
     lib = _lib.load()
     one = C.c_int32()
-    assert lib.sllm_mega_plan(C.byref(c_shape(ms)), BF16, 64, BF16, 3, B200_SMS, B200_SMEM, C.byref(one), None, None, None) != 0   # 32 heads over 3 ranks
-    assert lib.sllm_mega_plan(None, BF16, 64, BF16, 1, B200_SMS, B200_SMEM, C.byref(one), None, None, None) != 0
+    assert lib.sllm_mega_plan(C.byref(c_shape(ms)), BF16, 64, BF16, 3, 1, B200_SMS, B200_SMEM, C.byref(one), None, None, None) != 0   # 32 heads over 3 ranks
+    assert lib.sllm_mega_plan(C.byref(c_shape(ms)), BF16, 64, BF16, 2, 0, B200_SMS, B200_SMEM, C.byref(one), None, None, None) != 0   # TP needs the word-based kernel
+    assert lib.sllm_mega_plan(None, BF16, 64, BF16, 1, 0, B200_SMS, B200_SMEM, C.byref(one), None, None, None) != 0
+
+
+def test_query_head_groups_that_are_not_instantiated_fall_back():
+    """Both kernels are instantiated for 1, 2, 4 or 8 query heads per KV head: a plan for 3 must say no (the engine then runs the
+    per-kernel path) instead of saying yes and failing at the first launch."""
+    ms = dataclasses.replace(PRESETS["tinyllama-1.1b"], heads=12, kv_heads=4, hidden=768, kv_hidden=256)
+    for wb in (0, 1):
+        ok, *_, why = plan(ms, BF16, BF16, word_based=wb)
+        assert not ok and "head shape" in why
+
+
+def test_word_based_kernel_plans():
+    """The barrier-free kernel: no int8 weights; on one GPU it takes the headline shape too (opt-in SLLM_ENGINE_MEGA_LL); its grid
+    shrinks to the smallest phase's tile rows when a shard has fewer of them than SMs."""
+    ms = PRESETS["llama2-7b"]
+    ok, grid, nbytes, nsplit, why = plan(ms, BF16, BF16, word_based=1)
+    assert ok and grid == B200_SMS and nbytes + 1024 <= B200_SMEM, why
+    ok, *_, why = plan(ms, INT8, BF16, word_based=1)
+    assert not ok and "int8" in why
+    tiny = PRESETS["tiny_gqa"]                       # 128 x 128 wo: 64 two-row units in tiles of four rows = 32 tile rows
+    ok, grid, *_ = plan(tiny, F32, F32, word_based=1)
+    assert ok and 1 <= grid < B200_SMS
 
 
 @pytest.mark.parametrize("wd", [F32, BF16, INT8])
