@@ -308,6 +308,10 @@ int32_t sllm_batch_position(const sllm_batch* b, int32_t slot);   /* position of
  * 0..pos it reads and the row it writes (SURVEY.md 8d B(p) with the weight term shared) */
 int64_t sllm_batch_step_bytes(const sllm_batch* b);
 int64_t sllm_batch_total_launches(const sllm_batch* b);
+/* Device bytes sllm_batch_create(max_seqs, page_len, n_pages, kv_dtype) takes on an engine of this shape (the two page pools
+ * [n_pages][layers][kv_heads][page_len][head_dim], per-slot activations and logits, attention workspace; rounded up to 1 MiB) —
+ * host arithmetic only, so that a host sizes n_pages against sllm_device_info's free HBM first; -1 = bad argument. */
+int64_t sllm_batch_arena_bytes(const sllm_shape* shape, int32_t max_seqs, int32_t page_len, int32_t n_pages, int32_t kv_dtype);
 
 /* Introspection for parity tests and the roofline: named buffers follow the reference's ModelBufferType
  * numbering (include/model/model.h:14-34); returns a device pointer and its element count/dtype. */

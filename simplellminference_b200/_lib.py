@@ -97,6 +97,7 @@ SIGNATURES = {
     "sllm_batch_position": (_I, [_P, _I]),
     "sllm_batch_step_bytes": (_L, [_P]),
     "sllm_batch_total_launches": (_L, [_P]),
+    "sllm_batch_arena_bytes": (_L, [C.POINTER(Shape), _I, _I, _I, _I]),
     "sllm_engine_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     "sllm_engine_step_bytes": (_L, [_P, _I]),
     "sllm_engine_enqueue_kernel": (C.c_int, [_P, _I, _I]),

@@ -55,6 +55,29 @@ class KvPages:
             pass
 
 
+def arena_bytes(shape, max_seqs: int, page_len: int, n_pages: int, kv_dtype: int = BF16) -> int:
+    """Device bytes a ``BatchDecoder`` of these parameters takes on an engine of ``shape`` (host arithmetic, no GPU)."""
+    lib = _lib.load()
+    cs = _lib.Shape(shape.vocab, shape.head_dim, shape.hidden, shape.kv_hidden, shape.inter, shape.max_len, shape.layers, shape.heads,
+                    shape.kv_heads, shape.eps, shape.theta)
+    n = int(lib.sllm_batch_arena_bytes(C.byref(cs), max_seqs, page_len, n_pages, kv_dtype))
+    if n < 0:
+        raise _lib.SllmError(_lib.EINVAL, lib.sllm_last_error().decode(errors="replace"))
+    return n
+
+
+def pages_that_fit(shape, max_seqs: int, page_len: int, hbm_bytes: int, kv_dtype: int = BF16) -> int:
+    """Largest page pool (``n_pages``) whose decoder fits ``hbm_bytes`` of device memory, capped at what ``max_seqs`` sequences of
+    ``shape.max_len`` positions can ever hold; 0 if not even one page per slot fits. The pools grow linearly in ``n_pages``."""
+    cap = max_seqs * -(-shape.max_len // page_len)
+    fixed = arena_bytes(shape, max_seqs, page_len, 1, kv_dtype)
+    per_page = 2 * shape.layers * shape.kv_heads * page_len * shape.head_dim * (4 if kv_dtype != BF16 else 2)
+    n = min(cap, int(max(0, hbm_bytes - fixed) // per_page) + 1)
+    while n > 0 and arena_bytes(shape, max_seqs, page_len, n, kv_dtype) > hbm_bytes:   # the 1 MiB / 256-byte round-ups
+        n -= 1
+    return n if n >= max_seqs else 0
+
+
 class BatchDecoder:
     """Up to ``max_seqs`` sequences stepping together over the weights of ``engine`` (one GPU, not a megakernel engine)."""
 

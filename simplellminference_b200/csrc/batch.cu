@@ -621,6 +621,28 @@ int32_t sllm_batch_free_pages(const sllm_batch* b) { return b ? sllm_kvpages_fre
 int32_t sllm_batch_position(const sllm_batch* b, int32_t slot) { return (b && slot >= 0 && slot < b->max_seqs) ? b->host_pos[slot] : -1; }
 int64_t sllm_batch_total_launches(const sllm_batch* b) { return b ? b->total_launches : 0; }
 
+// Device bytes sllm_batch_create would take (page pools + per-slot buffers + attention workspace), as pure arithmetic: lets a
+// host size n_pages against the free HBM (sllm_device_info) before creating anything. Same layout pass as the real one.
+int64_t sllm_batch_arena_bytes(const sllm_shape* shape, int32_t max_seqs, int32_t page_len, int32_t n_pages, int32_t kv_dtype) {
+    if (!shape || max_seqs < 1 || max_seqs > kBatchMaxSeqs || page_len < 1 || n_pages < 1 || (kv_dtype != SLLM_F32 && kv_dtype != SLLM_BF16) ||
+        shape->head_dim < 1 || shape->heads < 1 || shape->kv_heads < 1 || shape->max_len < 1) {
+        set_error("batch_arena_bytes: bad argument (max_seqs %d, page_len %d, n_pages %d, kv dtype %d)", max_seqs, page_len, n_pages, kv_dtype);
+        return -1;
+    }
+    sllm_batch b;
+    sllm_kvpages kp;
+    kp.n_pages = n_pages; kp.page_len = page_len; kp.max_seqs = max_seqs; kp.max_pages = (shape->max_len + page_len - 1) / page_len;
+    b.pages = &kp;
+    b.max_seqs = max_seqs;
+    b.kv_dtype = kv_dtype;
+    b.esz_kv = kv_dtype == SLLM_F32 ? 4 : 2;
+    b.d = shape->hidden; b.hd = shape->head_dim; b.L = shape->layers; b.S = shape->max_len; b.V = shape->vocab; b.H = shape->heads; b.KVH = shape->kv_heads;
+    b.I = shape->inter; b.q_dim = shape->heads * shape->head_dim; b.kv_dim = shape->kv_heads * shape->head_dim;
+    batch_layout(&b);   // arena == nullptr: measures only
+    b.pages = nullptr;
+    return (int64_t)((b.arena_used + ((size_t)1 << 20) - 1) >> 20 << 20);
+}
+
 int64_t sllm_batch_step_bytes(const sllm_batch* b) {
     if (!b) return 0;
     const double bw = b->ev.w_dtype == SLLM_F32 ? 4.0 : b->ev.w_dtype == SLLM_BF16 ? 2.0 : 1.0 + 4.0 / b->ev.group;

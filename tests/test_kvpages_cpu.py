@@ -94,3 +94,28 @@ def test_random_walk_keeps_the_invariants():
             assert kp.held(q) == -(-length[q] // page_len) == int((t[q] >= 0).sum())
             assert (t[q, :kp.held(q)] >= 0).all()      # a sequence's pages are a prefix of its row
     kp.close()
+
+
+def test_arena_bytes_and_page_budget_for_180gb():
+    """sllm_batch_arena_bytes: the decoder's device footprint as host arithmetic (the layout pass of sllm_batch_create without an
+    arena), and the page pool a budget of HBM can carry."""
+    from simplellminference_b200.batch import arena_bytes, pages_that_fit
+    from simplellminference_b200.config import BF16, F32, PRESETS
+    ms = PRESETS["llama2-7b"]
+    per_page_bf16 = 2 * ms.layers * ms.kv_heads * 64 * ms.head_dim * 2            # K and V of 64 positions, all layers and heads: 32 MiB
+    assert per_page_bf16 == 32 << 20
+    a1, a2 = arena_bytes(ms, 16, 64, 100, BF16), arena_bytes(ms, 16, 64, 101, BF16)
+    assert a2 - a1 == per_page_bf16 and a1 % (1 << 20) == 0
+    assert arena_bytes(ms, 16, 64, 100, F32) - a1 == 100 * per_page_bf16          # fp32 pages are twice as large
+    fixed = a1 - 100 * per_page_bf16                                              # per-slot buffers + workspace: logits dominate
+    assert 16 * ms.vocab * 4 <= fixed < 64 << 20
+    # 180 GB of HBM minus 13.5 GB of bf16 weights: 64 slots of 4096 positions would need 4096 pages = 128 GiB -> they all fit
+    budget = 180 * 10**9 - 14 * 10**9
+    assert pages_that_fit(ms, 64, 64, budget, BF16) == 64 * 64
+    assert pages_that_fit(ms, 64, 64, budget, F32) == (budget - (arena_bytes(ms, 64, 64, 1, F32) - 2 * per_page_bf16)) // (2 * per_page_bf16)
+    small = pages_that_fit(ms, 64, 64, 10 * 10**9, BF16)
+    assert 64 <= small < 64 * 64 and arena_bytes(ms, 64, 64, small, BF16) <= 10 * 10**9 < arena_bytes(ms, 64, 64, small + 1, BF16)
+    assert pages_that_fit(ms, 64, 64, 1 << 30, BF16) == 0                         # not even one page per slot
+    assert _lib.load().sllm_batch_arena_bytes(None, 1, 1, 1, BF16) == -1
+    with pytest.raises(_lib.SllmError):
+        arena_bytes(ms, 65, 64, 10, BF16)
