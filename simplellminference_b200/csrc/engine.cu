@@ -592,6 +592,15 @@ static int mega_stage_end(sllm_engine* e) {
     return SLLM_OK;
 }
 
+// a load that failed half way: give the row-major staging copy back (the engine stays without weights)
+static void mega_stage_abort(sllm_engine* e) {
+    if (!e->emb.rm) return;
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->emb.rm);
+    Matrix* ms[5] = {&e->emb, &e->wqkv, &e->wo, &e->wug, &e->wdown};
+    for (Matrix* m : ms) m->rm = nullptr;
+}
+
 static int setup_mega(sllm_engine* e) {
     std::vector<PhaseDesc> host((size_t)4 * e->L + 1);
     // the classifier streams this rank's vocab rows [v0, v0+V_loc) of the (tiled, full) embedding matrix
@@ -763,6 +772,7 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->ll_block) cudaFree(e->ll_block);
     if (e->pf_ws) cudaFree(e->pf_ws);
     if (e->pf) pf_cache_destroy(e->pf);
+    if (e->emb.rm) cudaFree(e->emb.rm);   // a weight load that failed half way
     if (e->arena) cudaFree(e->arena);
     if (e->trace) cudaFree(e->trace);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -774,7 +784,7 @@ int sllm_engine_load_synthetic(sllm_engine* e, uint64_t seed) {
     if (int rc = mega_stage_begin(e)) return rc;
     for (const ShardSpec& p : shard_plan(e))
         if (int rc = sllm_synth_fill(&e->cfg.shape, seed, p.seg, p.first_row, p.n_rows, p.src_row_len, p.col0, p.row_len, p.dst,
-                                     e->cfg.w_dtype, p.sc, e->cfg.group, e->stream)) return rc;
+                                     e->cfg.w_dtype, p.sc, e->cfg.group, e->stream)) { mega_stage_abort(e); return rc; }
     return finish_weights(e);
 }
 
@@ -786,7 +796,7 @@ int sllm_engine_load_blob_f32(sllm_engine* e, const float* blob, int64_t n_float
     if (int rc0 = mega_stage_begin(e)) return rc0;
     const size_t stage_bytes = (size_t)64 << 20;
     float* stage = nullptr;
-    SLLM_CUDA(cudaMalloc(&stage, stage_bytes));
+    if (cudaError_t ce = cudaMalloc(&stage, stage_bytes)) { mega_stage_abort(e); return cuda_fail(ce, "cudaMalloc(upload staging)", __FILE__, __LINE__); }
     int rc = SLLM_OK;
     for (const ShardSpec& p : shard_plan(e)) {
         const float* src = blob + segment_offset(s, p.seg);
@@ -805,7 +815,7 @@ int sllm_engine_load_blob_f32(sllm_engine* e, const float* blob, int64_t n_float
         if (rc) break;
     }
     cudaFree(stage);
-    if (rc) return rc;
+    if (rc) { mega_stage_abort(e); return rc; }
     return finish_weights(e);
 }
 
