@@ -106,3 +106,76 @@ def test_synthetic_weights_contract(port):
     # moments: Irwin-Hall(4) scaled to unit variance
     big = port.fill_segment(mg.SHAPES["cfg1_stories15M"], 0, 0, 1 << 20)
     assert abs(big.mean()) < 5e-3 and abs(big.std() - 1.0) < 5e-3
+
+
+def test_port_vs_reference_live_random_shapes(port, ref):
+    """Property test (hypothesis): every op of the C restatement against the compiled reference on random shapes — head_dim not a
+    power of two, grouped-query attention with 1..8 query heads per KV head, every position of the context, ties in the arg-max,
+    RoPE at theta 1e4 / 5e5 — bit for bit. The reference rotates k over q's length (Appendix D of SURVEY.md), so RoPE is compared
+    with k.size == q.size, where both agree by construction."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.integers(0, 2**31 - 1), st.sampled_from([8, 16, 24, 48, 64, 80, 128]), st.integers(1, 4), st.sampled_from([1, 2, 3, 4, 8]),
+           st.integers(1, 40), st.sampled_from([10000.0, 500000.0]))
+    def run(seed, hd, kvh, g, S, theta):
+        rng = np.random.default_rng(seed)
+        f = lambda *s: rng.standard_normal(s).astype(np.float32)
+        H, L = kvh * g, 2
+        layer, pos = int(rng.integers(0, L)), int(rng.integers(0, S))
+        q, kc, vc = f(H * hd), f(L, S, kvh * hd), f(L, S, kvh * hd)
+        assert np.array_equal(port.mha(q, kc, vc, layer, pos, hd, H, kvh), ref.mha(q, kc, vc, layer, pos, hd, H, kvh))
+        sp, cp = port.rope_cache(hd, S, theta)
+        sr, cr = ref.rope_cache(hd, S, theta)
+        assert np.array_equal(sp, sr) and np.array_equal(cp, cr)
+        k = f(H * hd)
+        (qa, ka), (qb, kb) = port.rope(q, k, pos, sp, cp, hd), ref.rope(q, k, pos, sr, cr, hd)
+        assert np.array_equal(qa, qb) and np.array_equal(ka, kb)
+        V, d = int(rng.integers(2, 200)), int(rng.integers(1, 300))
+        table, tok = f(V, d), int(rng.integers(0, V))
+        assert np.array_equal(port.embedding(tok, table), ref.embedding(tok, table))
+        x, w, W = f(d), f(d), f(int(rng.integers(1, 20)), d)
+        assert np.array_equal(port.rmsnorm(x, w, 1e-5), ref.rmsnorm(x, w, 1e-5))
+        assert np.array_equal(port.matmul(x, W), ref.matmul(x, W))
+        assert np.array_equal(port.swiglu(x, 6 * w), ref.swiglu(x, 6 * w)) and np.array_equal(port.add(x, w), ref.add(x, w))
+        lg = np.round(f(V) * 2) / 2                      # coarse values: ties are the rule, the first maximum must win
+        assert port.argmax(lg) == ref.argmax(lg) == int(np.argmax(lg))
+
+    run()
+
+
+def test_port_model_vs_reference_live_random_shapes(port, ref):
+    """The whole forward loop (LlamaModel::forward, model.cpp:40-140) on random small model shapes, weight types and prompts:
+    token streams, final logits, residual stream and the cache rows inside the parity domain (positions <= S - H/KVH: beyond it
+    the reference's RoPE over-run corrupts rows) — bit for bit."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.integers(0, 2**31 - 1), st.sampled_from([8, 16, 48]), st.integers(1, 3), st.sampled_from([1, 2, 4]), st.integers(1, 3),
+           st.sampled_from([loader.F32, loader.BF16, loader.INT8]))
+    def run(seed, hd, kvh, g, layers, wd):
+        rng = np.random.default_rng(seed)
+        if kvh * g > hd:
+            kvh = max(1, hd // g)                 # heads <= head_dim: the reference's score scratch is {head_dim, S} used as [heads][S]
+        H = kvh * g                               # (model.cpp:279, mha_kernel.cpp:48) - more heads than that overrun its heap block
+        d, kv = H * hd, kvh * hd
+        inter = 64 * int(rng.integers(1, 4))
+        if wd == loader.INT8 and d % 64:
+            wd = loader.BF16                      # int8 groups of 64 need rows that are multiples of 64
+        S = int(rng.integers(g + 3, 30))
+        shape = loader.Shape(int(rng.integers(16, 400)), hd, d, kv, inter, S, layers, H, kvh, 1e-5, 10000.0)
+        blob = port.fill_blob(shape, int(seed % 1000), wd, 64)
+        n_total = S - g + 1                       # last position fed = n_total - 2 <= S - g
+        prompt = rng.integers(0, shape.vocab, size=int(rng.integers(1, min(4, n_total - 1) + 1))).tolist()
+        a, b = port.model(shape, blob), ref.model(shape, blob)
+        ta, la = a.greedy(prompt, n_total)
+        tb, lb = b.greedy(prompt, n_total)
+        assert np.array_equal(ta, tb) and np.array_equal(la, lb)
+        assert np.array_equal(a.read(4, 0, d), b.read(4, 0, d))
+        n = layers * S * kv
+        for buf in (2, 3):
+            ka, kb = a.read(buf, 0, n).reshape(layers, S, kv), b.read(buf, 0, n).reshape(layers, S, kv)
+            assert np.array_equal(ka[:, :n_total - 1], kb[:, :n_total - 1])
+        a.close(); b.close()
+
+    run()
