@@ -8,7 +8,7 @@
 #
 # Order: 1 the never-executed batched-decode tests (progressive log: tests/batch_check.py), 2 the bench line,
 # 3 batched throughput with every experimental variant, 4 the whole GPU suite, 5 per-phase timeline of the decode
-# megakernel, 6 launch list + ncu --set full of the batched GEMV and the paged attention kernel.
+# megakernel + the fusion probe (reductions vs barrier, clusters, L2 vs HBM ingest: DESIGN.md section 10), 6 launch list + ncu --set full of the batched GEMV and the paged attention kernel.
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -33,6 +33,7 @@ step 300 batch_bench      python tools/batch_bench.py --batches 1,2,4,8,16,32 --
 [ "$MODE" = quick ] && exit 0
 step 1500 pytest_gpu      python -m pytest tests -q -m gpu -rxXs --junitxml="$OUT/pytest_gpu.xml"
 step 180 mega_trace       python tools/mega_trace.py
+step 180 fusion_probe     tools/microbench/_build/fusion_probe 2000
 # ---- profiler passes (after the plain commands above have run)
 PS="python tools/profile_step.py --layers 2 --pos 512 --steps 2"
 step 120 batch8_plain     $PS --batch 8
