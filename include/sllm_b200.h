@@ -168,6 +168,12 @@ typedef struct {
                                     (megakernel_ll.cu) instead of the grid-barrier one (megakernel.cu, faster on one GPU).
                                     Under tensor parallelism (MEGAKERNEL | P2P_ALLREDUCE) the word version is the only
                                     one: it carries the all-reduce inside the kernel */
+#define SLLM_ENGINE_MEGA_FUSE_DOWN 64u /* experimental, with MEGAKERNEL on one GPU (fp32 / bf16 weights, hidden size = 2^k x 512 bytes per
+                                    row <= 8 KB): the down projection runs inside the gate_up phase as a K-split over the values each
+                                    CTA produced, partial outputs added to the residual stream with red.global.add — four grid barriers
+                                    per layer instead of five, but a summation order that is not fixed (logits vary in the last bits
+                                    from run to run). Costs a second, transposed copy of the down matrices. Off until measured;
+                                    sllm_engine_mode() says "megakernel(fused-down)" when it is in effect */
 #define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
 
 typedef struct sllm_engine sllm_engine;

@@ -54,6 +54,8 @@ struct sllm_engine {
     bool fused = true, use_graph = true, pdl = true;
     bool mega = false;            // persistent one-launch-per-token kernel (megakernel.cu / megakernel_ll.cu)
     bool mega_ll = false;         // barrier-free {value, epoch}-word version (also the tensor-parallel one)
+    bool mega_fuse = false;       // experimental: down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN)
+    void* wdown_t = nullptr;      // its transposed per-layer matrices (megakernel.cuh "PH_DOWN_T"); wdown stays for the batched prefill
     MegaLLPlan ll_plan{};
     MegaLLParams ll_params{};
     uint8_t* ll_block = nullptr;  // this rank's word area (own cudaMalloc: exported through CUDA IPC under TP)
@@ -177,6 +179,7 @@ static void layout(sllm_engine* e) {
     e->phases_dev = carve<PhaseDesc>(e, sizeof(PhaseDesc) * (size_t)(4 * L + 1));
     e->prompt_dev = carve<int32_t>(e, 4 * (size_t)S);
     e->history_dev = carve<int32_t>(e, 4 * (size_t)S);
+    e->wdown_t = e->mega_fuse ? carve<void>(e, (size_t)L * mega_down_t_bytes(e->d, e->I_loc, e->cfg.w_dtype)) : nullptr;
 }
 
 static int count_launch(sllm_engine* e) {
@@ -480,7 +483,7 @@ static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
         SLLM_REQUIRE(!e->mega_ll || e->ll_ready, SLLM_ESTATE, "tensor-parallel megakernel: peer areas not exchanged yet (sllm_engine_p2p_import)");
         for (int i = 0; i < n; ++i) {
             const int rc = e->mega_ll ? mega_ll_launch(e->ll_params, e->H_loc / e->KVH_loc, e->ll_plan.grid, e->ll_plan.smem, e->stream)
-                                      : mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream);
+                                      : mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream, e->mega_fuse);
             if (rc) return rc;
             e->total_launches++;
         }
@@ -584,6 +587,12 @@ static int mega_stage_end(sllm_engine* e) {
                              reinterpret_cast<uint8_t*>(m->w) + (size_t)l * tiled, (int)m->rows, (int)m->cols, m->kind, e->cfg.w_dtype, e->hd,
                              e->q_loc, e->kv_loc, e->I_loc, e->stream);
     }
+    if (e->mega_fuse) {   // the fused kernel's transposed copy of every layer's down matrix, from the same row-major staging copy
+        const size_t per_layer = mega_down_t_bytes(e->d, e->I_loc, e->cfg.w_dtype);
+        for (int64_t l = 0; l < e->wdown.layers && rc == SLLM_OK; ++l)
+            rc = mega_repack_down_t(reinterpret_cast<uint8_t*>(e->wdown.rm) + wbytes(e->cfg.w_dtype, l * e->wdown.rows * e->wdown.cols),
+                                    reinterpret_cast<uint8_t*>(e->wdown_t) + (size_t)l * per_layer, e->d, e->I_loc, e->cfg.w_dtype, e->stream);
+    }
     cudaError_t ce = cudaStreamSynchronize(e->stream);
     cudaFree(e->emb.rm);
     for (Matrix* m : ms) m->rm = nullptr;
@@ -608,6 +617,10 @@ static int setup_mega(sllm_engine* e) {
     const uint8_t* cls = reinterpret_cast<const uint8_t*>(e->emb.w) + (size_t)(e->v0 / eg.R) * eg.KS * eg.tile_bytes;
     mega_fill_phases(host.data(), e->L, e->cfg.w_dtype, e->wqkv.w, e->wo.w, e->wug.w, e->wdown.w, cls, e->d, e->q_loc, e->kv_loc,
                      e->I_loc, e->V_loc);
+    if (e->mega_fuse)
+        for (int l = 0; l < e->L; ++l)
+            mega_fill_down_t(host[(size_t)4 * l + 3], reinterpret_cast<const uint8_t*>(e->wdown_t) + (size_t)l * mega_down_t_bytes(e->d, e->I_loc, e->cfg.w_dtype),
+                             e->d, e->I_loc, l, e->cfg.w_dtype);
     if (e->mega_ll) {
         MegaLLParams& q = e->ll_params;
         q.phases = e->phases_dev;
@@ -729,6 +742,9 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
             e->mega = e->mega_plan_.ok;
         }
         if (e->mega) e->p2p_mode = false;   // the megakernel carries its own in-kernel all-reduce
+        const int g_q = e->H_loc / e->KVH_loc;
+        e->mega_fuse = e->mega && !e->mega_ll && (cfg->flags & SLLM_ENGINE_MEGA_FUSE_DOWN) && mega_fuse_down_ok(cfg->w_dtype, e->d, e->I_loc) &&
+                       (g_q == 1 || g_q == 2 || g_q == 4 || g_q == 8);
     }
     layout(e);  // measure
     e->arena_bytes = align_up(e->arena_used, 1 << 20);
@@ -1156,7 +1172,7 @@ int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos
 
 const char* sllm_engine_mode(const sllm_engine* e) {
     if (!e) return "null";
-    if (e->mega) return e->mega_ll ? "megakernel(ll)" : "megakernel";
+    if (e->mega) return e->mega_ll ? "megakernel(ll)" : e->mega_fuse ? "megakernel(fused-down)" : "megakernel";
     if (!e->fused) return "unfused";
     return e->use_graph ? (e->pdl ? "fused+graph+pdl" : "fused+graph") : (e->pdl ? "fused+pdl" : "fused");
 }

@@ -139,6 +139,37 @@ __device__ __forceinline__ void cta_tiles(const PhaseDesc& ph, int cta, int ncta
     g1 = (int)(((int64_t)ph.ntr * (cta + 1)) / ncta);
 }
 
+// the split a phase's tile rows get in the kernel that fuses the down projection into the gate_up phase: gate_up follows the split
+// of the (transposed) down matrix, whose tile rows are kFuseJT units, so that a CTA multiplies exactly the values it produced
+template <bool FUSE>
+__device__ __forceinline__ void phase_tiles(const PhaseDesc& ph, int cta, int ncta, int& g0, int& g1) {
+    if (FUSE && ph.kind == PH_GATEUP) {
+        const int per = kFuseJT / (ph.R >> 1);        // gate_up tile rows (R / 2 units each) per down tile row
+        const int ntr_e = ph.nunits / kFuseJT;
+        g0 = (int)(((int64_t)ntr_e * cta) / ncta) * per;
+        g1 = (int)(((int64_t)ntr_e * (cta + 1)) / ncta) * per;
+    } else {
+        cta_tiles(ph, cta, ncta, g0, g1);
+    }
+}
+
+// acc[e] += w_e * s for the E weights of one 16-byte chunk (fp32 / bf16 storage)
+template <int WD>
+__device__ __forceinline__ void axpy_chunk(const uint4 w, float s, float* acc) {
+    if (WD == SLLM_F32) {
+        acc[0] = fmaf(__uint_as_float(w.x), s, acc[0]); acc[1] = fmaf(__uint_as_float(w.y), s, acc[1]);
+        acc[2] = fmaf(__uint_as_float(w.z), s, acc[2]); acc[3] = fmaf(__uint_as_float(w.w), s, acc[3]);
+    } else {
+        acc[0] = fmaf(bf16_lo(w.x), s, acc[0]); acc[1] = fmaf(bf16_hi(w.x), s, acc[1]);
+        acc[2] = fmaf(bf16_lo(w.y), s, acc[2]); acc[3] = fmaf(bf16_hi(w.y), s, acc[3]);
+        acc[4] = fmaf(bf16_lo(w.z), s, acc[4]); acc[5] = fmaf(bf16_hi(w.z), s, acc[5]);
+        acc[6] = fmaf(bf16_lo(w.w), s, acc[6]); acc[7] = fmaf(bf16_hi(w.w), s, acc[7]);
+    }
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int KVD> struct MKv;
 template <> struct MKv<SLLM_F32> { static constexpr int ESZ = 4, VEC = 4; };
 template <> struct MKv<SLLM_BF16> { static constexpr int ESZ = 2, VEC = 8; };

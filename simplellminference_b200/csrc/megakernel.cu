@@ -52,7 +52,9 @@ struct ProdState {
     int row_bytes, sbytes, u0, u1, upp, RG, nslots, kind;
 };
 
-template <int WD, int KVD, int G>
+// FUSE (experimental, SLLM_ENGINE_MEGA_FUSE_DOWN): the down projection runs inside the gate_up phase's CTA as a K-split over the
+// values that CTA produced (megakernel.cuh "PH_DOWN_T"): four grid barriers per layer instead of five, no staging of swi.
+template <int WD, int KVD, int G, bool FUSE>
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaParams p) {
     constexpr int E = WInfo<WD>::E;                 // weights per 16-byte chunk
     constexpr int CPL = (WD == SLLM_INT8) ? 2 : kCplMax;   // max chunks per lane per row slice (x of a lane: CPL * E = 32 registers)
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             const PhaseDesc ph = p.phases[pr_wp];
             const int ks = warp & (ph.KS - 1), rg = warp / ph.KS, RG = kMegaWarps / ph.KS;
             int g0, g1;
-            cta_tiles(ph, cta, ncta, g0, g1);
+            phase_tiles<FUSE>(ph, cta, ncta, g0, g1);
             pr_left = (g1 - g0 - rg + RG - 1) / RG;       // tile rows g0+rg, g0+rg+RG, ... < g1
             pr_ptr = ph.W + ((size_t)(g0 + rg) * ph.KS + ks) * ph.tile_bytes;
             pr_step = (uint32_t)RG * ph.KS * ph.tile_bytes;
@@ -132,6 +134,45 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
         const bool normed = (ph.kind == PH_QKV || ph.kind == PH_GATEUP || ph.kind == PH_CLS);
         const int ev = wp + l + (ph.kind != PH_QKV && ph.kind != PH_CLS ? 1 : 0) + (ph.kind == PH_CLS ? 0 : 0);   // event slot: weight phases and attention phases in order
         MEGA_STAMP(ev, 0);
+        if constexpr (FUSE) {
+            if (ph.kind == PH_DOWN_T) {
+                // x += Wdown[:, this CTA's units] . swi[this CTA's units]: the gate_up epilogue left the values in shared memory (xs),
+                // the wo epilogue left h in x. A lane owns E outputs; its warp streams the (tile row, stripe) tiles of stripe ks.
+                int g0, g1;
+                cta_tiles(ph, cta, ncta, g0, g1);
+                MEGA_STAMP(ev, 1);   // no prologue: nothing to stage
+                float acc[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = 0.f;
+                bool any = false;
+#pragma unroll 1
+                for (int j = g0 + rg; j < g1; j += RG) {
+                    const int si = cons_count & (kSlots - 1);
+                    mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
+                    const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
+                    const float* sw = xs + (size_t)(j - g0) * kFuseJT;
+#pragma unroll
+                    for (int jj = 0; jj < kFuseJT; ++jj) axpy_chunk<WD>(*reinterpret_cast<const uint4*>(sp + jj * 512), sw[jj], acc);
+                    any = true;
+                    cons_count++;
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_async_smem();
+                        produce_one();
+                    }
+                }
+                MEGA_STAMP(ev, 3);
+                if (any) {
+                    float* dst = p.x + (size_t)(ks * 32 + lane) * E;
+                    red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+                    if (E == 8) red_add_v4(dst + 4, acc[E - 4], acc[E - 3], acc[E - 2], acc[E - 1]);
+                }
+                MEGA_STAMP(ev, 4);
+                grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+                MEGA_STAMP(ev, 5);
+                continue;
+            }
+        }
         // norm weights of this lane's columns: constant data, requested before anything that has to wait
         float nwr[CPL][E];
         if (normed) {
@@ -266,7 +307,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
         MEGA_STAMP(ev, 1);   // prologue done
         // ---- 2. stream this CTA's tile rows through the rings, round by round ------------------------------
         int g0, g1;
-        cta_tiles(ph, cta, ncta, g0, g1);
+        phase_tiles<FUSE>(ph, cta, ncta, g0, g1);
         const int upp = ph.R >> 1;
         const int u0 = g0 * upp;
         const int n = max(0, min(ph.nunits, g1 * upp) - u0);   // real units of this CTA
@@ -389,10 +430,18 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                     }
                 } else if (ph.kind == PH_WO) {
                     const int r = 2 * u;
-                    p.h[r] = __ldcg(p.x + r) + s0;                            // add_kernel.cpp:10-13
-                    if (r + 1 < ph.nrows) p.h[r + 1] = __ldcg(p.x + r + 1) + s1;
+                    const float h0 = __ldcg(p.x + r) + s0;                    // add_kernel.cpp:10-13
+                    p.h[r] = h0;
+                    if constexpr (FUSE) p.x[r] = h0;                          // the fused down phase adds its partial sums onto h
+                    if (r + 1 < ph.nrows) {
+                        const float h1 = __ldcg(p.x + r + 1) + s1;
+                        p.h[r + 1] = h1;
+                        if constexpr (FUSE) p.x[r + 1] = h1;
+                    }
                 } else if (ph.kind == PH_GATEUP) {
-                    p.swi[u] = (1.0f / (1.0f + expf(-s1))) * s0;              // swiglu_kernel.cpp:12-13
+                    const float sv = (1.0f / (1.0f + expf(-s1))) * s0;        // swiglu_kernel.cpp:12-13
+                    p.swi[u] = sv;
+                    if constexpr (FUSE) xs[rbase + t] = sv;                   // stays in this CTA for the fused down phase
                 } else if (ph.kind == PH_DOWN) {
                     const int r = 2 * u;
                     p.x[r] = s0 + __ldcg(p.h + r);
@@ -450,6 +499,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             break;
         }
         MEGA_STAMP(ev, 4);   // epilogue done
+        if (FUSE && ph.kind == PH_GATEUP) {   // its consumer is this CTA itself (the round's trailing __syncthreads published xs)
+            MEGA_STAMP(ev, 5);
+            continue;
+        }
         grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
         MEGA_STAMP(ev, 5);   // barrier passed
         if (ph.kind != PH_QKV) continue;
@@ -800,11 +853,66 @@ int mega_repack(const void* src, const float* scales, void* dst, int rows, int c
     return SLLM_OK;
 }
 
-template <int WD, int KVD, int G>
+// ---- transposed down matrix of the fused kernel (megakernel.cuh "PH_DOWN_T") ---------------------------------------------
+bool mega_fuse_down_ok(int w_dtype, int d, int I_loc) {
+    if (w_dtype != SLLM_F32 && w_dtype != SLLM_BF16) return false;
+    const int row_bytes = d * (w_dtype == SLLM_F32 ? 4 : 2);
+    if (row_bytes % 512) return false;
+    const int stripes = row_bytes / 512;                       // one stripe = 32 lanes x 16 bytes of outputs
+    if (stripes < 1 || stripes > kMegaWarps || (stripes & (stripes - 1))) return false;
+    return I_loc % kFuseJT == 0 && I_loc >= kFuseJT;
+}
+size_t mega_down_t_bytes(int d, int I_loc, int w_dtype) { return (size_t)d * I_loc * (w_dtype == SLLM_F32 ? 4 : 2); }
+
+void mega_fill_down_t(PhaseDesc& ds, const void* Wt, int d, int I_loc, int layer, int w_dtype) {
+    const int esz = w_dtype == SLLM_F32 ? 4 : 2;
+    ds.W = reinterpret_cast<const uint8_t*>(Wt);
+    ds.nchunks = d * esz / 16;
+    ds.nunits = I_loc;                 // inputs j
+    ds.nrows = d;
+    ds.kind = PH_DOWN_T;
+    ds.layer = layer;
+    ds.KS = d * esz / 512;             // stripes
+    ds.SC = 32;
+    ds.R = kFuseJT;
+    ds.ntr = I_loc / kFuseJT;
+    ds.tile_bytes = kFuseJT * 512;
+    ds.srow = 0;
+}
+
+template <class T>
+__global__ void repack_down_t_kernel(const T* __restrict__ src, T* __restrict__ dst, int d, int I, int E, int KS) {
+    const int64_t total = (int64_t)d * I;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % E);
+        const int lane = (int)((i / E) % 32);
+        const int jj = (int)((i / ((int64_t)E * 32)) % kFuseJT);
+        const int ks = (int)((i / ((int64_t)E * 32 * kFuseJT)) % KS);
+        const int64_t g = i / ((int64_t)E * 32 * kFuseJT * KS);
+        const int r = (ks * 32 + lane) * E + e;
+        const int64_t j = g * kFuseJT + jj;
+        dst[i] = src[(int64_t)r * I + j];
+    }
+}
+
+int mega_repack_down_t(const void* src, void* dst, int d, int I_loc, int w_dtype, cudaStream_t st) {
+    SLLM_REQUIRE(mega_fuse_down_ok(w_dtype, d, I_loc), SLLM_ENOTSUP, "fused down projection: shape d=%d I=%d weight type %d not supported", d, I_loc, w_dtype);
+    const int64_t total = (int64_t)d * I_loc;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    if (w_dtype == SLLM_F32)
+        repack_down_t_kernel<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), d, I_loc, 4, d * 4 / 512);
+    else
+        repack_down_t_kernel<uint16_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), reinterpret_cast<uint16_t*>(dst), d, I_loc, 8, d * 2 / 512);
+    g_launches++;
+    SLLM_LAUNCH_CHECK();
+    return SLLM_OK;
+}
+
+template <int WD, int KVD, int G, bool FUSE = false>
 static int mega_launch_t(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
     if (smem > configured) {
-        SLLM_CUDA(cudaFuncSetAttribute(mega_step_kernel<WD, KVD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SLLM_CUDA(cudaFuncSetAttribute(mega_step_kernel<WD, KVD, G, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -817,12 +925,35 @@ static int mega_launch_t(const MegaParams& p, int grid, size_t smem, cudaStream_
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SLLM_CUDA(cudaLaunchKernelEx(&cfg, mega_step_kernel<WD, KVD, G>, p));
+    SLLM_CUDA(cudaLaunchKernelEx(&cfg, mega_step_kernel<WD, KVD, G, FUSE>, p));
     g_launches++;
     return SLLM_OK;
 }
 
-int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st) {
+int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down) {
+    if (fuse_down) {   // experimental kernel: fp32 / bf16 weights only (mega_fuse_down_ok)
+#define MEGA_F(GG)                                                                                                      \
+    case GG:                                                                                                            \
+        if (p.w_dtype == SLLM_F32) {                                                                                    \
+            return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_F32, SLLM_F32, GG, true>(p, grid, smem, st)              \
+                                          : mega_launch_t<SLLM_F32, SLLM_BF16, GG, true>(p, grid, smem, st);            \
+        }                                                                                                               \
+        if (p.w_dtype == SLLM_BF16) {                                                                                   \
+            return p.kv_dtype == SLLM_F32 ? mega_launch_t<SLLM_BF16, SLLM_F32, GG, true>(p, grid, smem, st)             \
+                                          : mega_launch_t<SLLM_BF16, SLLM_BF16, GG, true>(p, grid, smem, st);           \
+        }                                                                                                               \
+        break;
+        switch (g) {
+            MEGA_F(1)
+            MEGA_F(2)
+            MEGA_F(4)
+            MEGA_F(8)
+            default: break;
+        }
+#undef MEGA_F
+        set_error("megakernel with the fused down projection: weight type %d / %d query heads per KV head not instantiated", p.w_dtype, g);
+        return SLLM_ENOTSUP;
+    }
 #define MEGA_G(GG)                                                                                        \
     case GG:                                                                                              \
         if (p.w_dtype == SLLM_F32) {                                                                      \

@@ -105,7 +105,20 @@ void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, con
 // scales_rowmajor: int8 only, fp32 [rows][cols/64] (the tiled layout carries each tile's scales behind its weights)
 int mega_repack(const void* src_rowmajor, const float* scales_rowmajor, void* dst_tiled, int rows, int cols, int kind, int w_dtype, int hd,
                 int q_loc, int kv_loc, int I_loc, cudaStream_t st);
-enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4 };
-int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st);
+enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4, PH_DOWN_T = 5 };
+int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down = false);
+
+// ---- experimental: down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN) ---------------------------------
+// K-split of Wdown over the CTAs: a CTA multiplies the columns of Wdown that belong to the sigma(gate)*up values IT produced and
+// adds its partial output vector into the residual stream with red.global.add.v4.f32, so gate_up -> down needs no grid barrier, no
+// activation staging and no cross-lane reduction. Layout of the transposed matrix ("PH_DOWN_T"): tile row g = kFuseJT consecutive
+// inputs j; K slice ks = a stripe of 32 lanes x 16 bytes of outputs r (d = KS * 32 * E outputs, KS a power of two <= 16); tile
+// (g, ks) = kFuseJT x 512 bytes, contiguous at (g * KS + ks) * tile_bytes: element e of lane `lane` in row jj of the tile is
+// Wdown[(ks * 32 + lane) * E + e][g * kFuseJT + jj]. A lane owns E outputs for the whole phase.
+constexpr int kFuseJT = 4;
+bool mega_fuse_down_ok(int w_dtype, int d, int I_loc);
+size_t mega_down_t_bytes(int d, int I_loc, int w_dtype);
+void mega_fill_down_t(PhaseDesc& ds, const void* Wt, int d, int I_loc, int layer, int w_dtype);
+int mega_repack_down_t(const void* src_rowmajor /* [d][I_loc] */, void* dst, int d, int I_loc, int w_dtype, cudaStream_t st);
 
 }  // namespace sllm

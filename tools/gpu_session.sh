@@ -34,6 +34,10 @@ step 300 batch_bench      python tools/batch_bench.py --batches 1,2,4,8,16,32 --
 step 1500 pytest_gpu      python -m pytest tests -q -m gpu -rxXs --junitxml="$OUT/pytest_gpu.xml"
 step 180 mega_trace       python tools/mega_trace.py
 step 180 fusion_probe     tools/microbench/_build/fusion_probe 2000
+# experimental megakernel with the down projection fused into the gate_up phase: parity first, then the same bench line and timeline
+step 600 fuse_tests       python -m pytest tests/test_zy_mega_fuse_gpu.py -q -rxXs -p no:cacheprovider
+step 420 bench_fuse       python bench.py --mega-fuse-down --no-batch --no-cpu-baseline
+step 180 mega_trace_fuse  python tools/mega_trace.py --fuse-down
 # ---- profiler passes (after the plain commands above have run)
 PS="python tools/profile_step.py --layers 2 --pos 512 --steps 2"
 step 120 batch8_plain     $PS --batch 8
