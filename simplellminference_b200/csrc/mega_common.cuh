@@ -153,6 +153,13 @@ __device__ __forceinline__ void phase_tiles(const PhaseDesc& ph, int cta, int nc
     }
 }
 
+// tile rows [a, b) of the transposed down matrix that row group rg of RG takes out of a CTA's [g0, g1): contiguous shares
+__device__ __forceinline__ void down_t_rows(int g0, int g1, int rg, int RG, int& a, int& b) {
+    const int cnt = g1 - g0;
+    a = g0 + (cnt * rg) / RG;
+    b = g0 + (cnt * (rg + 1)) / RG;
+}
+
 // acc[e] += w_e * s for the E weights of one 16-byte chunk (fp32 / bf16 storage)
 template <int WD>
 __device__ __forceinline__ void axpy_chunk(const uint4 w, float s, float* acc) {

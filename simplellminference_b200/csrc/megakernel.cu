@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
     unsigned pr_count = 0;                // slots issued so far
     const uint8_t* pr_ptr = nullptr;      // next tile of this warp's (ks, rg) sub-stream
     uint32_t pr_step = 0, pr_bytes = 0;
+    uint32_t pr_tail = 0;                 // FUSE: bytes of the LAST copy of a transposed-down stream (a whole slot otherwise)
     auto produce_one = [&]() {   // lane 0 only: arm the next slot of this warp's stream (if any is left)
         while (pr_left <= 0) {                            // enter the next phase this warp has work in
             if (++pr_wp >= nwp) { pr_wp = nwp; return; }
@@ -103,12 +104,29 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             const int ks = warp & (ph.KS - 1), rg = warp / ph.KS, RG = kMegaWarps / ph.KS;
             int g0, g1;
             phase_tiles<FUSE>(ph, cta, ncta, g0, g1);
+            if constexpr (FUSE) {
+                pr_tail = 0;
+                if (ph.kind == PH_DOWN_T) {   // stripe-major matrix: this warp's tile rows [a, b) are ONE contiguous byte range, copied a slot at a time
+                    int a, b;
+                    down_t_rows(g0, g1, rg, RG, a, b);
+                    const uint32_t len = (uint32_t)(b - a) * (uint32_t)ph.tile_bytes;
+                    pr_left = (int)((len + kSlotBytes - 1) / kSlotBytes);
+                    pr_ptr = ph.W + ((size_t)ks * ph.ntr + a) * ph.tile_bytes;
+                    pr_step = kSlotBytes;
+                    pr_bytes = kSlotBytes;
+                    pr_tail = len - (uint32_t)(pr_left - 1) * kSlotBytes;
+                    continue;
+                }
+            }
             pr_left = (g1 - g0 - rg + RG - 1) / RG;       // tile rows g0+rg, g0+rg+RG, ... < g1
             pr_ptr = ph.W + ((size_t)(g0 + rg) * ph.KS + ks) * ph.tile_bytes;
             pr_step = (uint32_t)RG * ph.KS * ph.tile_bytes;
             pr_bytes = (uint32_t)ph.tile_bytes;
         }
         const int si = pr_count & (kSlots - 1);
+        if constexpr (FUSE) {
+            if (pr_tail && pr_left == 1) pr_bytes = pr_tail;
+        }
         mb_expect(my_bar + si, pr_bytes);
         tma_g2s(my_ring + (size_t)si * kSlotBytes, pr_ptr, pr_bytes, my_bar + si);
         pr_ptr += pr_step;
@@ -145,14 +163,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
 #pragma unroll
                 for (int e = 0; e < E; ++e) acc[e] = 0.f;
                 bool any = false;
+                int ja, jb;
+                down_t_rows(g0, g1, rg, RG, ja, jb);      // this warp's tile rows: contiguous in the stripe-major matrix
+                constexpr int kRowsPerSlot = kSlotBytes / (kFuseJT * 512);
 #pragma unroll 1
-                for (int j = g0 + rg; j < g1; j += RG) {
+                for (int j = ja; j < jb; j += kRowsPerSlot) {
                     const int si = cons_count & (kSlots - 1);
                     mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
                     const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
                     const float* sw = xs + (size_t)(j - g0) * kFuseJT;
+                    const int nj = min(kRowsPerSlot, jb - j) * kFuseJT;   // inputs in this slot (the last copy may hold fewer tile rows)
+#pragma unroll 1
+                    for (int j4 = 0; j4 < nj; j4 += kFuseJT) {
 #pragma unroll
-                    for (int jj = 0; jj < kFuseJT; ++jj) axpy_chunk<WD>(*reinterpret_cast<const uint4*>(sp + jj * 512), sw[jj], acc);
+                        for (int jj = 0; jj < kFuseJT; ++jj)
+                            axpy_chunk<WD>(*reinterpret_cast<const uint4*>(sp + (j4 + jj) * 512), sw[j4 + jj], acc);
+                    }
                     any = true;
                     cons_count++;
                     __syncwarp();
@@ -884,11 +910,12 @@ template <class T>
 __global__ void repack_down_t_kernel(const T* __restrict__ src, T* __restrict__ dst, int d, int I, int E, int KS) {
     const int64_t total = (int64_t)d * I;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ntr = I / kFuseJT;                                   // stripe-major: [ks][g][jj][lane][e]
         const int e = (int)(i % E);
         const int lane = (int)((i / E) % 32);
         const int jj = (int)((i / ((int64_t)E * 32)) % kFuseJT);
-        const int ks = (int)((i / ((int64_t)E * 32 * kFuseJT)) % KS);
-        const int64_t g = i / ((int64_t)E * 32 * kFuseJT * KS);
+        const int64_t g = (i / ((int64_t)E * 32 * kFuseJT)) % ntr;
+        const int ks = (int)(i / ((int64_t)E * 32 * kFuseJT * ntr));
         const int r = (ks * 32 + lane) * E + e;
         const int64_t j = g * kFuseJT + jj;
         dst[i] = src[(int64_t)r * I + j];

@@ -113,8 +113,10 @@ int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t 
 // adds its partial output vector into the residual stream with red.global.add.v4.f32, so gate_up -> down needs no grid barrier, no
 // activation staging and no cross-lane reduction. Layout of the transposed matrix ("PH_DOWN_T"): tile row g = kFuseJT consecutive
 // inputs j; K slice ks = a stripe of 32 lanes x 16 bytes of outputs r (d = KS * 32 * E outputs, KS a power of two <= 16); tile
-// (g, ks) = kFuseJT x 512 bytes, contiguous at (g * KS + ks) * tile_bytes: element e of lane `lane` in row jj of the tile is
-// Wdown[(ks * 32 + lane) * E + e][g * kFuseJT + jj]. A lane owns E outputs for the whole phase.
+// (g, ks) = kFuseJT x 512 bytes; the matrix is STRIPE-MAJOR, tile (g, ks) at (ks * ntr + g) * tile_bytes, so that the tile rows a
+// warp takes (a contiguous share of its CTA's range) are one contiguous byte range that it copies a whole ring slot (two tile rows)
+// at a time. Element e of lane `lane` in row jj of the tile is Wdown[(ks * 32 + lane) * E + e][g * kFuseJT + jj]. A lane owns E
+// outputs for the whole phase.
 constexpr int kFuseJT = 4;
 bool mega_fuse_down_ok(int w_dtype, int d, int I_loc);
 size_t mega_down_t_bytes(int d, int I_loc, int w_dtype);

@@ -1,5 +1,5 @@
 """The index arithmetic of the experimental fused down projection of the decode megakernel (SLLM_ENGINE_MEGA_FUSE_DOWN), restated in
-numpy: the transposed tile layout written by repack_down_t_kernel (csrc/megakernel.cu), the tile rows a CTA / warp / lane consumes in
+numpy: the transposed, stripe-major tile layout written by repack_down_t_kernel (csrc/megakernel.cu), the tile rows a CTA / warp / lane consumes in
 the PH_DOWN_T phase, and the split of the gate_up phase that must hand every CTA exactly the units whose columns it then multiplies
 (csrc/mega_common.cuh phase_tiles). The sum over all CTAs, warps and lanes must be Wdown . swi, with every input used exactly once.
 A restatement cannot prove the CUDA code right (tests/test_zy_mega_fuse_gpu.py does that on a GPU); it pins the layout contract the
@@ -25,10 +25,11 @@ def test_fused_down_layout_and_split(d, inter, E, ncta, R_gateup):
     RG = WARPS // KS
     i = np.arange(d * inter)                                        # repack_down_t_kernel: destination element index
     e, lane, jj = i % E, (i // E) % 32, (i // (E * 32)) % JT
-    ks, g = (i // (E * 32 * JT)) % KS, i // (E * 32 * JT * KS)
+    ntr_e, upp = inter // JT, R_gateup // 2
+    g, ks = (i // (E * 32 * JT)) % ntr_e, i // (E * 32 * JT * ntr_e)      # stripe-major: [ks][g][jj][lane][e]
     dst = W.reshape(-1)[((ks * 32 + lane) * E + e) * inter + (g * JT + jj)]
     tile = JT * 32 * E                                              # elements of one (tile row, stripe) tile = 2 KB
-    ntr_e, upp = inter // JT, R_gateup // 2
+    rows_per_slot = 2                                               # a 4 KB ring slot = two tile rows of one stripe
     per = JT // upp                                                 # gate_up tile rows per down tile row
     x, used = np.zeros(d), np.zeros(inter, int)
     for cta in range(ncta):
@@ -42,10 +43,18 @@ def test_fused_down_layout_and_split(d, inter, E, ncta, R_gateup):
         for warp in range(WARPS):
             ks_, rg = warp & (KS - 1), warp // KS
             acc = np.zeros((32, E))
-            for jt in range(g0 + rg, g1, RG):                       # producer and consumer walk the same tile rows
-                base = (jt * KS + ks_) * tile
-                for jj_ in range(JT):
-                    acc += dst[base + jj_ * 32 * E: base + (jj_ + 1) * 32 * E].reshape(32, E).astype(np.float64) * float(xs[(jt - g0) * JT + jj_])
+            cnt = g1 - g0
+            a, b = g0 + (cnt * rg) // RG, g0 + (cnt * (rg + 1)) // RG     # down_t_rows: a contiguous share of the CTA's tile rows
+            ptr, left = (ks_ * ntr_e + a) * tile, (b - a) * tile          # the producer's byte range, in elements
+            for jt in range(a, b, rows_per_slot):                         # one ring slot per iteration
+                n_el = min(rows_per_slot * tile, left)                    # the last copy may hold a single tile row
+                slot = dst[ptr:ptr + n_el]
+                ptr, left = ptr + n_el, left - n_el
+                nj = min(rows_per_slot, b - jt) * JT
+                assert nj * 32 * E == n_el
+                for j_ in range(nj):
+                    acc += slot[j_ * 32 * E:(j_ + 1) * 32 * E].reshape(32, E).astype(np.float64) * float(xs[(jt - g0) * JT + j_])
+            assert left == 0
             x[ks_ * 32 * E:(ks_ + 1) * 32 * E] += acc.reshape(-1)   # red.global.add.v4.f32 into x + (ks * 32 + lane) * E
     assert (used == 1).all()
     assert np.allclose(x, W.astype(np.float64) @ swi.astype(np.float64), atol=1e-9)
