@@ -35,7 +35,7 @@ step 1500 pytest_gpu      python -m pytest tests -q -m gpu -rxXs --junitxml="$OU
 step 180 mega_trace       python tools/mega_trace.py
 step 180 fusion_probe     tools/microbench/_build/fusion_probe 2000
 # experimental megakernel with the down projection fused into the gate_up phase: parity first, then the same bench line and timeline
-step 600 fuse_tests       python -m pytest tests/test_zy_mega_fuse_gpu.py -q -rxXs -p no:cacheprovider
+step 600 fuse_check       python tests/fuse_check.py "$OUT/fuse_check_progress.log"
 step 420 bench_fuse       python bench.py --mega-fuse-down --no-batch --no-cpu-baseline
 step 180 mega_trace_fuse  python tools/mega_trace.py --fuse-down
 # ---- profiler passes (after the plain commands above have run)
