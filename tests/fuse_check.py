@@ -2,7 +2,7 @@
 progressive log: `python tests/fuse_check.py [logfile]`. First a localisation — one forward at position 0 of a ONE-layer model through
 the verified megakernel and through the fused one on the same weights, buffer by buffer (ffn_input = h after wo, swi_output =
 sigma(gate)*up, emb_output = the residual stream after the down projection, model_pred), for each stripe count — so that a wrong
-stage is named; then every case of tests/test_zy_mega_fuse_gpu.py in turn. Not collected by pytest (no test_ prefix)."""
+stage is named; then every case of tests/test_zzz_mega_fuse_gpu.py in turn. Not collected by pytest (no test_ prefix)."""
 import dataclasses
 import os
 import sys
@@ -65,7 +65,7 @@ def main():
             log(f"{name}: localisation FAILED:\n" + traceback.format_exc(limit=6))
 
     # ---- 2. the test functions
-    import test_zy_mega_fuse_gpu as T
+    import test_zzz_mega_fuse_gpu as T
     cases = [("golden stream tiny_gqa", T.test_golden_stream_of_the_reference),
              ("fallback shapes", T.test_shapes_it_does_not_take_fall_back_visibly)]
     for d, heads, kvh, inter, wd in [(256, 4, 2, 704, BF16), (512, 8, 8, 1408, BF16), (1024, 16, 4, 2824, BF16), (256, 4, 4, 516, F32)]:

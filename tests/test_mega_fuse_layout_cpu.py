@@ -2,7 +2,7 @@
 numpy: the transposed, stripe-major tile layout written by repack_down_t_kernel (csrc/megakernel.cu), the tile rows a CTA / warp / lane consumes in
 the PH_DOWN_T phase, and the split of the gate_up phase that must hand every CTA exactly the units whose columns it then multiplies
 (csrc/mega_common.cuh phase_tiles). The sum over all CTAs, warps and lanes must be Wdown . swi, with every input used exactly once.
-A restatement cannot prove the CUDA code right (tests/test_zy_mega_fuse_gpu.py does that on a GPU); it pins the layout contract the
+A restatement cannot prove the CUDA code right (tests/test_zzz_mega_fuse_gpu.py does that on a GPU); it pins the layout contract the
 two sides of the kernel were written against."""
 import numpy as np
 import pytest

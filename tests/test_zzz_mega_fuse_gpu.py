@@ -5,6 +5,8 @@ five. The summation order of the down projection is not fixed, so runs are not b
 contract of tests/test_engine_gpu.py: token stream IDENTICAL to the reference / the oracle, logits within 3e-4 * max|logit|
 (fp32 cache) or 5e-3 (bf16 cache).
 
+(The file sorts after every other GPU test on purpose: a fault of this never-run kernel must not poison the CUDA context of verified tests.)
+
 Written after the round's GPU budget was spent: never executed on a GPU yet, hence non-strict xfail (an XPASS in the report is the
 confirmation; remove the mark then). The kernels without the flag are untouched: their SASS is byte-identical to the verified build."""
 import importlib.util
