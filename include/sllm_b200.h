@@ -21,7 +21,12 @@
  *    host (emb_kernel.cu:15, rope_kernel.cu:49). With the *_dev pointer NULL the by-value argument is used;
  *  - activations, RoPE tables and accumulators are fp32. Matrix weights are stored as fp32, bf16 or
  *    int8-with-group-scales (SLLM_F32 / SLLM_BF16 / SLLM_INT8); the KV cache as fp32 or bf16.
- *  - there is NO CPU fallback anywhere behind this header.
+ *  - there is NO CPU fallback anywhere behind this header;
+ *  - threading: the model of the reference (source/model/model.cpp drives one model from one host thread) and of the
+ *    tensor-parallel runtime here — ONE process per GPU, one host thread driving an engine / batch at a time. The library keeps
+ *    per-process caches of device facts and of per-kernel shared-memory attributes for the device that was current at first use, and
+ *    the development knobs of sllm_tune are process-wide: do not drive two devices, or one engine from two threads, in one process.
+ *    Pure-arithmetic entry points (sllm_*_plan, sllm_mega_tile_geometry, sllm_batch_arena_bytes, sllm_kvpages_*) touch no device.
  */
 #ifndef SLLM_B200_H
 #define SLLM_B200_H
