@@ -5,6 +5,7 @@
 #
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'            (one GPU)
 #   bash tools/gpu_session.sh quick                                  (tests of the batched decode + bench only)
+#   gpurun --gpus 8 --timeout 3000 -- 'bash tools/gpu_session.sh'   (adds tensor-parallel parity + bench at 2 / 4 / 8 GPUs at the end)
 #
 # Order: 1 the never-executed batched-decode tests (progressive log: tests/batch_check.py), 2 the bench line,
 # 3 batched throughput with every experimental variant, 4 the whole GPU suite, 5 per-phase timeline of the decode
@@ -44,4 +45,13 @@ step 120 batch8_plain     $PS --batch 8
 step 300 batch8_launches  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/batch8_launches.csv" $PS --batch 8
 step 600 batch8_ncu_gemv  ncu --set full --clock-control none --import-source on -k regex:bgemv -s 40 -c 6 -o "$OUT/batch8_bgemv" -f $PS --batch 8
 step 400 batch8_ncu_mha   ncu --set full --clock-control none --import-source on -k regex:mha_paged -s 8 -c 2 -o "$OUT/batch8_mha_paged" -f $PS --batch 8
+# ---- more than one GPU on the box (gpurun --gpus N): tensor-parallel parity and the bench line at every power of two up to N
+NGPU=$(nvidia-smi -L 2>/dev/null | wc -l)
+for n in 2 4 8; do
+    [ "$NGPU" -ge "$n" ] || break
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n))"
+    step 900 "tp${n}_check" $TR tests/tp_check.py
+    step 600 "tp${n}_bench" $TR bench.py --gpus "$n"
+    grep -h '^{' "$OUT/tp${n}_bench.log" | tail -1 > "$OUT/tp${n}_bench.json"
+done
 echo "session done" | tee -a "$OUT/session_steps.txt"
