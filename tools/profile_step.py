@@ -11,6 +11,7 @@ ap.add_argument("--layers", type=int, default=0)
 ap.add_argument("--mode", default="mega", choices=["mega", "fused"])
 ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--fuse-down", action="store_true", help="mega mode: the experimental kernel with the down projection fused into the gate_up phase")
 ap.add_argument("--batch", type=int, default=0, help="> 0: that many sequences through the batched decoder (sllm_batch_*) instead of the engine's own step")
 a = ap.parse_args()
 ms = PRESETS[a.config]
@@ -32,7 +33,7 @@ if a.batch:   # every sequence decodes a.pos tokens first (untimed), then a.step
     print(json.dumps({"mode": f"batch of {a.batch}", "layers": ms.layers, "step_ms": round(msec, 4), "tokens_per_sec": round(a.batch / msec * 1e3, 1),
                       "GBps": round(nbytes / msec / 1e6, 0)}))
     sys.exit(0)
-eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega")).load_synthetic(1)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega"), mega_fuse_down=a.fuse_down).load_synthetic(1)
 eng.set_state(1, a.pos)
 eng.enqueue_steps(2); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
