@@ -248,6 +248,12 @@ int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int3
 int sllm_mega_tile_geometry(int32_t rows, int32_t cols, int32_t kind, int32_t w_dtype, int32_t* ks, int32_t* sc, int32_t* r,
                             int32_t* tile_rows, int32_t* tile_bytes, int64_t* matrix_bytes);
 
+/* Development aid for the experimental SLLM_ENGINE_MEGA_FUSE_DOWN kernel: its transposed, stripe-major copy of a row-major
+ * [d][inter] down matrix (device pointers; fp32 / bf16; d * element size = 2^k * 512 bytes <= 8 KB, inter % 4 == 0). Element e of lane
+ * `lane`, input jj of tile row g, output stripe ks — at index (((ks * (inter/4) + g) * 4 + jj) * 32 + lane) * E + e, E = 16 bytes of
+ * elements — is W[(ks * 32 + lane) * E + e][g * 4 + jj]. */
+int sllm_mega_repack_down_t(const void* src_rowmajor, void* dst, int32_t d, int32_t inter, int32_t w_dtype, sllm_stream_t stream);
+
 /* The two prefill kernels on their own (device pointers), for op-level parity tests:
  * C[T][N] (fp32) = A[T][K] (bf16) . W[N][K]^T (bf16, row-major) on tcgen05; bn = 0 (auto), 128 or 256 = N tile. */
 int sllm_prefill_gemm_bf16(const void* A, const void* W, float* C, int32_t T, int32_t N, int32_t K, int32_t bn,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "sllm_prefill_gemm_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "sllm_prefill_gemm_plan": (C.c_int, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "sllm_mega_plan": (C.c_int, [C.POINTER(Shape), _I, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), C.POINTER(_I)]),
+    "sllm_mega_repack_down_t": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "sllm_mega_tile_geometry": (C.c_int, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
     "sllm_prefill_attention": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "sllm_kvpages_create": (_P, [_I, _I, _I, _I]),

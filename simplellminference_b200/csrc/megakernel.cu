@@ -1042,6 +1042,13 @@ int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int3
     return SLLM_OK;
 }
 
+/* development aid: the transposed, stripe-major down matrix of the fused kernel from a row-major [d][inter] one (device pointers) */
+int sllm_mega_repack_down_t(const void* src_rowmajor, void* dst, int32_t d, int32_t inter, int32_t w_dtype, sllm_stream_t stream) {
+    using namespace sllm;
+    SLLM_REQUIRE(src_rowmajor && dst, SLLM_EINVAL, "mega_repack_down_t: null pointer");
+    return mega_repack_down_t(src_rowmajor, dst, d, inter, w_dtype, as_stream(stream));
+}
+
 int sllm_mega_tile_geometry(int32_t rows, int32_t cols, int32_t kind, int32_t w_dtype, int32_t* ks, int32_t* sc, int32_t* r, int32_t* tile_rows,
                             int32_t* tile_bytes, int64_t* matrix_bytes) {
     using namespace sllm;

@@ -66,7 +66,9 @@ def main():
 
     # ---- 2. the test functions
     import test_zzz_mega_fuse_gpu as T
-    cases = [("golden stream tiny_gqa", T.test_golden_stream_of_the_reference),
+    cases = [(f"transposed layout d={d} inter={inter} {dt}", lambda d=d, inter=inter, dt=dt: T.test_transposed_down_layout(d, inter, dt))
+             for d, inter, dt in [(128, 384, "f32"), (256, 704, "bf16"), (4096, 11008, "bf16"), (2048, 5632, "f32")]]
+    cases += [("golden stream tiny_gqa", T.test_golden_stream_of_the_reference),
              ("fallback shapes", T.test_shapes_it_does_not_take_fall_back_visibly)]
     for d, heads, kvh, inter, wd in [(256, 4, 2, 704, BF16), (512, 8, 8, 1408, BF16), (1024, 16, 4, 2824, BF16), (256, 4, 4, 516, F32)]:
         cases.append((f"oracle d={d} inter={inter} wd={wd}", lambda d=d, heads=heads, kvh=kvh, inter=inter, wd=wd: T.test_stripe_counts_against_the_oracle(port, d, heads, kvh, inter, wd)))

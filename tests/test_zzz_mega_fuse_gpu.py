@@ -27,6 +27,27 @@ mg = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(mg)
 
 
+@pytest.mark.parametrize("d,inter,dt", [(128, 384, "f32"), (256, 704, "bf16"), (4096, 11008, "bf16"), (2048, 5632, "f32")])
+def test_transposed_down_layout(d, inter, dt):
+    """The repack kernel alone against the index formula of include/sllm_b200.h (and of tests/test_mega_fuse_layout_cpu.py): bit copy."""
+    import ctypes as C
+    import torch
+    from simplellminference_b200 import _lib
+    lib = _lib.load()
+    tdt, E, wd = (torch.float32, 4, F32) if dt == "f32" else (torch.bfloat16, 8, BF16)
+    W = torch.randn(d, inter, device="cuda").to(tdt).contiguous()
+    out = torch.empty(d * inter, device="cuda", dtype=tdt)
+    _lib.check(lib.sllm_mega_repack_down_t(W.data_ptr(), out.data_ptr(), d, inter, wd, None))
+    torch.cuda.synchronize()
+    i = torch.arange(d * inter, device="cuda")
+    ntr = inter // 4
+    e, lane, jj = i % E, (i // E) % 32, (i // (E * 32)) % 4
+    g, ks = (i // (E * 32 * 4)) % ntr, i // (E * 32 * 4 * ntr)
+    want = W.reshape(-1)[((ks * 32 + lane) * E + e) * inter + (g * 4 + jj)]
+    assert torch.equal(out.view(torch.int16 if dt == "bf16" else torch.int32), want.view(torch.int16 if dt == "bf16" else torch.int32))
+    assert lib.sllm_mega_repack_down_t(W.data_ptr(), out.data_ptr(), 768, 2048, F32, None) != 0     # six stripes: not a power of two
+
+
 def test_golden_stream_of_the_reference():
     """tiny_gqa fp32 (hidden 128 = one 512-byte stripe, 16 row groups): the token stream and logits recorded from the UNMODIFIED reference."""
     golden = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "models_ref.npz")))
