@@ -84,8 +84,16 @@ class BatchDecoder:
     def __init__(self, engine: Engine, max_seqs: int, page_len: int = 64, n_pages: int | None = None, kv_dtype: int = BF16):
         self.lib = _lib.load()
         self.engine = engine   # keeps the weights alive
-        if n_pages is None:    # enough for every slot to reach the engine's max_len
+        if n_pages is None:    # enough for every slot to reach the engine's max_len ...
             n_pages = max_seqs * ((engine.shape.max_len + page_len - 1) // page_len)
+            if arena_bytes(engine.shape, max_seqs, page_len, n_pages, kv_dtype) > (8 << 30):
+                # ... unless that is a large pool (64 Llama-2-7B sequences of 4096 positions = 128 GiB): then as many pages as 90 % of the
+                # free HBM carries (sllm_device_info), never fewer than one per slot
+                free = C.c_size_t(0)
+                if self.lib.sllm_device_info(None, None, None, C.byref(free)) == 0 and free.value:
+                    fit = pages_that_fit(engine.shape, max_seqs, page_len, int(free.value * 0.9), kv_dtype)
+                    if fit:
+                        n_pages = min(n_pages, fit)
         h = C.c_void_p()
         _lib.check(self.lib.sllm_batch_create(engine.h, max_seqs, page_len, n_pages, kv_dtype, C.byref(h)))
         self.h = h
