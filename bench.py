@@ -16,6 +16,8 @@ token feedback on the device); `e2e` = the same metric through the reference-fac
 pos) per token with host buffers: H2D of token+position, D2H of the next token, a host sync per token.
 `roofline` = the dominant kernel (gate_up GEMV) timed alone with CUDA events, cycling over the layers so its
 weights always come from HBM; `step_roofline` = whole-step algorithmic bytes B(p) / step time.
+Secondary keys measured in child processes AFTER every timed region (N = 1; a failure there costs only its own key):
+`batch_decode` (tools/batch_bench.py) and `experiments` (tools/fuse_bench.py, tools/microbench/fusion_probe); --no-batch skips them.
 """
 from __future__ import annotations
 
@@ -54,7 +56,8 @@ def parse():
     ap.add_argument("--mega-fuse-down", action="store_true", help="single GPU, experimental: the megakernel variant with the down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN)")
     ap.add_argument("--nccl", action="store_true", help="tensor parallel: NCCL all-reduce instead of the fused peer-memory one")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
-    ap.add_argument("--no-batch", action="store_true", help="skip the secondary batched multi-sequence figure (tools/batch_bench.py in a child process)")
+    ap.add_argument("--no-batch", action="store_true", help="skip the secondary figures measured in child processes after the timed regions (batched multi-sequence decode: "
+                                                            "tools/batch_bench.py; experimental fused-down megakernel: tools/fuse_bench.py; tools/microbench/fusion_probe)")
     return ap.parse_args()
 
 
@@ -247,6 +250,48 @@ def batch_decode_sample(args):
     return out
 
 
+def _child_json_lines(cmd, timeout):
+    """Runs a secondary measurement in a child process; returns (parsed JSON lines of its stdout, note on how it ended or None)."""
+    stdout, note = "", None
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        stdout = r.stdout or ""
+        if r.returncode != 0:
+            note = f"exit {r.returncode}: {(r.stderr or '').strip()[-300:]}"
+    except subprocess.TimeoutExpired as ex:
+        stdout = ex.stdout.decode(errors="replace") if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+        note = f"timed out after {timeout} s"
+    except Exception as ex:
+        note = repr(ex)[:300]
+    out = []
+    for ln in stdout.splitlines():
+        try:
+            out.append(json.loads(ln))
+        except Exception:
+            continue
+    return out, note
+
+
+def experiments_sample(args, main_checksum, K, W):
+    """Secondary, N = 1 only, each in its own child process after every timed region of the main arm (nothing here can touch the headline):
+    (1) the experimental megakernel with the down projection fused into the gate_up phase on the main arm's exact workload — tokens/s and
+    whether its tokens equal the main arm's; (2) tools/microbench/fusion_probe — what combining 148 partial vectors with vector reductions
+    costs against the grid barrier, cluster co-residency, TMA ingest from L2-resident against HBM-resident tiles."""
+    out = {}
+    if args.wdtype in ("f32", "bf16"):
+        lines, note = _child_json_lines([sys.executable, os.path.join(ROOT, "tools", "fuse_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
+                                         "--kvdtype", args.kvdtype, "--prompt-len", str(args.prompt_len), "--steps", str(K), "--warmup", str(W),
+                                         "--expect-checksum", str(main_checksum)], 180)
+        out["fused_down"] = lines[-1] if lines else {"error": note or "no output"}
+        if lines and note:
+            out["fused_down"]["note"] = note
+    probe = os.path.join(ROOT, "tools", "microbench", "_build", "fusion_probe")
+    if os.path.exists(probe):
+        lines, note = _child_json_lines([probe, "1000"], 90)
+        out["fusion_probe"] = lines if lines else {"error": note or "no output"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm --
 def run_ours(args):
     import numpy as np
@@ -421,10 +466,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     step_launches = eng.step_launches
-    batch = None
+    batch = experiments = None
     if world == 1 and not args.no_batch:
         eng.close()
         batch = batch_decode_sample(args)
+        if mode == "megakernel":   # the default arm: measure the opt-in variant of the same kernel beside it
+            try:
+                experiments = experiments_sample(args, int(np.sum(tokens.astype(np.int64)) % 1000003), K, W)
+            except Exception as ex:   # secondary: never lose the line over it
+                experiments = {"error": repr(ex)[:300]}
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only (it costs ~10 s of host time)
         try:
@@ -439,7 +489,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "launches_per_step": step_launches, "clocks": clocks,
         "prefill": prefill, "prompt_tokens_per_sec_token_by_token": P / t_prompt, "token_checksum": int(np.sum(tokens.astype(np.int64)) % 1000003),
         "mode": mode + ("" if world == 1 else (" tp/nccl-allreduce" if args.nccl else " tp/peer-memory-allreduce")),
-        "batch_decode": batch,
+        "batch_decode": batch, "experiments": experiments,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

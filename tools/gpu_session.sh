@@ -27,7 +27,7 @@ step() {   # step <seconds> <name> <command...>: run under a timeout, log, never
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > "$OUT/gpu.txt" 2>&1
 
 step 600 batch_check      python tests/batch_check.py "$OUT/batch_check_progress.log"
-step 420 bench            python bench.py
+step 900 bench            python bench.py
 grep -h '^{' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 step 300 batch_bench      python tools/batch_bench.py --batches 1,2,4,8,16,32 --exp-batches 4,8,16,32 \
                           --variants plain,graph,graph+rows4,graph+rows4+ksplit --json
