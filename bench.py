@@ -227,32 +227,32 @@ def batch_decode_sample(args):
     cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
            "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", "1,4,8,16", "--exp-batches", "8,16",
            "--variants", ",".join(variants), "--steps", "64", "--json"]
-    stdout, note = "", None
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-        stdout = r.stdout or ""
-        if r.returncode != 0:
-            note = f"exit {r.returncode}: {(r.stderr or '').strip()[-300:]}"
-    except subprocess.TimeoutExpired as ex:
-        stdout = ex.stdout.decode(errors="replace") if isinstance(ex.stdout, bytes) else (ex.stdout or "")
-        note = "timed out after 240 s"
-    except Exception as ex:
-        note = repr(ex)[:300]
-    got = {}
-    for ln in stdout.splitlines():
-        try:
-            d = json.loads(ln)
-            got[d["variant"]] = d
-        except Exception:
-            continue
+    lines, note = _child_json_lines(cmd, 200)
+    got = {d["variant"]: d for d in lines if isinstance(d, dict) and "variant" in d}
     out = got.get("plain") or {"error": note or "no output"}
     out["experimental"] = {v: got.get(v) or {"error": note or "not reached"} for v in variants[1:]}
     return out
 
 
+SECONDARY_BUDGET_S = 300.0   # wall-clock budget shared by ALL secondary child processes: the worst case adds this much to the run, no more
+_secondary_deadline = None
+
+
+def _secondary_timeout(cap):
+    """Seconds a secondary child may take: its own cap, cut to what is left of the shared budget (0 = skip it)."""
+    global _secondary_deadline
+    if _secondary_deadline is None:
+        _secondary_deadline = time.monotonic() + SECONDARY_BUDGET_S
+    left = _secondary_deadline - time.monotonic()
+    return 0 if left < 20 else int(min(cap, left))
+
+
 def _child_json_lines(cmd, timeout):
     """Runs a secondary measurement in a child process; returns (parsed JSON lines of its stdout, note on how it ended or None)."""
     stdout, note = "", None
+    timeout = _secondary_timeout(timeout)
+    if timeout == 0:
+        return [], "skipped: the shared time budget of the secondary measurements is spent"
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
         stdout = r.stdout or ""
@@ -281,13 +281,13 @@ def experiments_sample(args, main_checksum, K, W):
     if args.wdtype in ("f32", "bf16"):
         lines, note = _child_json_lines([sys.executable, os.path.join(ROOT, "tools", "fuse_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
                                          "--kvdtype", args.kvdtype, "--prompt-len", str(args.prompt_len), "--steps", str(K), "--warmup", str(W),
-                                         "--expect-checksum", str(main_checksum)], 180)
+                                         "--expect-checksum", str(main_checksum)], 120)
         out["fused_down"] = lines[-1] if lines else {"error": note or "no output"}
         if lines and note:
             out["fused_down"]["note"] = note
     probe = os.path.join(ROOT, "tools", "microbench", "_build", "fusion_probe")
     if os.path.exists(probe):
-        lines, note = _child_json_lines([probe, "1000"], 90)
+        lines, note = _child_json_lines([probe, "1000"], 60)
         out["fusion_probe"] = lines if lines else {"error": note or "no output"}
     return out
 
