@@ -272,11 +272,29 @@ def _child_json_lines(cmd, timeout):
     return out, note
 
 
+def _child_text(cmd, timeout, max_lines=60):
+    """Like _child_json_lines for a tool that prints a short human-readable report: its stdout lines (or the reason there are none)."""
+    timeout = _secondary_timeout(timeout)
+    if timeout == 0:
+        return ["skipped: the shared time budget of the secondary measurements is spent"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        lines = [ln.rstrip()[:400] for ln in (r.stdout or "").splitlines() if ln.strip()][:max_lines]
+        if r.returncode != 0:
+            lines.append(f"exit {r.returncode}: {(r.stderr or '').strip()[-300:]}")
+        return lines
+    except subprocess.TimeoutExpired:
+        return [f"timed out after {timeout} s"]
+    except Exception as ex:
+        return [repr(ex)[:300]]
+
+
 def experiments_sample(args, main_checksum, K, W):
     """Secondary, N = 1 only, each in its own child process after every timed region of the main arm (nothing here can touch the headline):
     (1) the experimental megakernel with the down projection fused into the gate_up phase on the main arm's exact workload — tokens/s and
     whether its tokens equal the main arm's; (2) tools/microbench/fusion_probe — what combining 148 partial vectors with vector reductions
-    costs against the grid barrier, cluster co-residency, TMA ingest from L2-resident against HBM-resident tiles."""
+    costs against the grid barrier, cluster co-residency, TMA ingest from L2-resident against HBM-resident tiles (DESIGN.md section 10);
+    (3) the per-phase timelines of both kernels."""
     out = {}
     if args.wdtype in ("f32", "bf16"):
         lines, note = _child_json_lines([sys.executable, os.path.join(ROOT, "tools", "fuse_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
@@ -289,6 +307,11 @@ def experiments_sample(args, main_checksum, K, W):
     if os.path.exists(probe):
         lines, note = _child_json_lines([probe, "1000"], 60)
         out["fusion_probe"] = lines if lines else {"error": note or "no output"}
+    # (3) where the time of a decode step goes: per-phase timeline (%globaltimer stamps) of the default megakernel and of the fused one,
+    # four layers of the same widths (tools/mega_trace.py)
+    if args.config == "llama2-7b" and args.wdtype == "bf16" and args.kvdtype == "bf16":
+        trace = [sys.executable, os.path.join(ROOT, "tools", "mega_trace.py"), "--pos", str(args.prompt_len)]
+        out["mega_trace"] = {"megakernel": _child_text(trace, 60), "megakernel(fused-down)": _child_text(trace + ["--fuse-down"], 60)}
     return out
 
 
