@@ -234,7 +234,7 @@ def batch_decode_sample(args):
     return out
 
 
-SECONDARY_BUDGET_S = 300.0   # wall-clock budget shared by ALL secondary child processes: the worst case adds this much to the run, no more
+SECONDARY_BUDGET_S = 240.0   # wall-clock budget shared by ALL secondary child processes: the worst case adds this much to the run, no more
 _secondary_deadline = None
 
 
