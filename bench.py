@@ -307,12 +307,17 @@ def experiments_sample(args, main_checksum, K, W):
     if os.path.exists(probe):
         lines, note = _child_json_lines([probe, "1000"], 60)
         out["fusion_probe"] = lines if lines else {"error": note or "no output"}
-    # (3) where the time of a decode step goes: per-phase timeline (%globaltimer stamps) of the default megakernel and of the fused one,
-    # four layers of the same widths (tools/mega_trace.py)
-    if args.config == "llama2-7b" and args.wdtype == "bf16" and args.kvdtype == "bf16":
-        trace = [sys.executable, os.path.join(ROOT, "tools", "mega_trace.py"), "--pos", str(args.prompt_len)]
-        out["mega_trace"] = {"megakernel": _child_text(trace, 60), "megakernel(fused-down)": _child_text(trace + ["--fuse-down"], 60)}
     return out
+
+
+def trace_sample(args):
+    """(3) where the time of a decode step goes: per-phase timeline (%globaltimer stamps) of the default megakernel and of the fused one,
+    four layers of the same widths (tools/mega_trace.py). Last in line for the shared budget: the longest-running child (the batched
+    decoder) goes before it, the two short experiments before that."""
+    if not (args.config == "llama2-7b" and args.wdtype == "bf16" and args.kvdtype == "bf16"):
+        return None
+    trace = [sys.executable, os.path.join(ROOT, "tools", "mega_trace.py"), "--pos", str(args.prompt_len)]
+    return {"megakernel": _child_text(trace, 60), "megakernel(fused-down)": _child_text(trace + ["--fuse-down"], 60)}
 
 
 # ------------------------------------------------------------------------------------------------ our arm --
@@ -492,12 +497,14 @@ def run_ours(args):
     batch = experiments = None
     if world == 1 and not args.no_batch:
         eng.close()
-        batch = batch_decode_sample(args)
-        if mode == "megakernel":   # the default arm: measure the opt-in variant of the same kernel beside it
-            try:
+        try:   # secondary: never lose the line over any of it. Order = cost: the two short experiments, the batched decoder, the timelines
+            if mode == "megakernel":   # the default arm: measure the opt-in variant of the same kernel beside it
                 experiments = experiments_sample(args, int(np.sum(tokens.astype(np.int64)) % 1000003), K, W)
-            except Exception as ex:   # secondary: never lose the line over it
-                experiments = {"error": repr(ex)[:300]}
+            batch = batch_decode_sample(args)
+            if mode == "megakernel":
+                experiments["mega_trace"] = trace_sample(args)
+        except Exception as ex:
+            experiments = dict(experiments or {}, error=repr(ex)[:300])
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only (it costs ~10 s of host time)
         try:
