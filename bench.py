@@ -283,8 +283,9 @@ def _child_text(cmd, timeout, max_lines=60):
         if r.returncode != 0:
             lines.append(f"exit {r.returncode}: {(r.stderr or '').strip()[-300:]}")
         return lines
-    except subprocess.TimeoutExpired:
-        return [f"timed out after {timeout} s"]
+    except subprocess.TimeoutExpired as ex:
+        partial = ex.stdout.decode(errors="replace") if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+        return [ln.rstrip()[:400] for ln in partial.splitlines() if ln.strip()][:max_lines] + [f"timed out after {timeout} s"]
     except Exception as ex:
         return [repr(ex)[:300]]
 
@@ -303,6 +304,10 @@ def experiments_sample(args, main_checksum, K, W):
         out["fused_down"] = lines[-1] if lines else {"error": note or "no output"}
         if lines and note:
             out["fused_down"]["note"] = note
+        if out["fused_down"].get("tokens_match_main_arm") is not True:
+            # something is off with the never-before-run kernel: bring back WHERE (layout of the transposed matrix alone; one forward of a
+            # one-layer model through the verified and the fused kernel, buffer by buffer, for 1 / 2 / 16 stripes; the reference's golden stream)
+            out["fused_down_diagnosis"] = _child_text([sys.executable, os.path.join(ROOT, "tests", "fuse_check.py"), "--quick", "/tmp/sllm_fuse_check.log"], 60, max_lines=40)
     probe = os.path.join(ROOT, "tools", "microbench", "_build", "fusion_probe")
     if os.path.exists(probe):
         lines, note = _child_json_lines([probe, "1000"], 60)

@@ -2,7 +2,8 @@
 progressive log: `python tests/fuse_check.py [logfile]`. First a localisation — one forward at position 0 of a ONE-layer model through
 the verified megakernel and through the fused one on the same weights, buffer by buffer (ffn_input = h after wo, swi_output =
 sigma(gate)*up, emb_output = the residual stream after the down projection, model_pred), for each stripe count — so that a wrong
-stage is named; then every case of tests/test_zzz_mega_fuse_gpu.py in turn. Not collected by pytest (no test_ prefix)."""
+stage is named; then every case of tests/test_zzz_mega_fuse_gpu.py in turn (`--quick`: only those that need no oracle run). Not collected by pytest
+(no test_ prefix)."""
 import dataclasses
 import os
 import sys
@@ -12,7 +13,9 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-LOG = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "fuse_check.log")
+QUICK = "--quick" in sys.argv      # localisation + the cases that need no oracle run (bench.py's diagnostic child: about 20 s)
+_args = [a for a in sys.argv[1:] if a != "--quick"]
+LOG = _args[0] if _args else os.path.join(ROOT, "gpurun_out", "fuse_check.log")
 os.makedirs(os.path.dirname(LOG), exist_ok=True)
 _t0 = time.time()
 _f = open(LOG, "w")
@@ -70,9 +73,10 @@ def main():
              for d, inter, dt in [(128, 384, "f32"), (256, 704, "bf16"), (4096, 11008, "bf16"), (2048, 5632, "f32")]]
     cases += [("golden stream tiny_gqa", T.test_golden_stream_of_the_reference),
              ("fallback shapes", T.test_shapes_it_does_not_take_fall_back_visibly)]
-    for d, heads, kvh, inter, wd in [(256, 4, 2, 704, BF16), (512, 8, 8, 1408, BF16), (1024, 16, 4, 2824, BF16), (256, 4, 4, 516, F32)]:
+    for d, heads, kvh, inter, wd in ([] if QUICK else [(256, 4, 2, 704, BF16), (512, 8, 8, 1408, BF16), (1024, 16, 4, 2824, BF16), (256, 4, 4, 516, F32)]):
         cases.append((f"oracle d={d} inter={inter} wd={wd}", lambda d=d, heads=heads, kvh=kvh, inter=inter, wd=wd: T.test_stripe_counts_against_the_oracle(port, d, heads, kvh, inter, wd)))
-    cases.append(("full width 7B x 2 layers", lambda: T.test_full_width_llama2_7b_two_layers(port)))
+    if not QUICK:
+        cases.append(("full width 7B x 2 layers", lambda: T.test_full_width_llama2_7b_two_layers(port)))
     ok = 0
     for name, fn in cases:
         try:
