@@ -506,6 +506,9 @@ def run_ours(args):
             if mode == "megakernel":   # the default arm: measure the opt-in variant of the same kernel beside it
                 experiments = experiments_sample(args, int(np.sum(tokens.astype(np.int64)) % 1000003), K, W)
             batch = batch_decode_sample(args)
+            # the parity cases of the batched decoder that no GPU has run yet (pytest reports them as xfail / xpass only): PASS / FAIL per
+            # case with the traceback of a failure — tests/batch_check.py --quick
+            batch["never_run_parity_cases"] = _child_text([sys.executable, os.path.join(ROOT, "tests", "batch_check.py"), "--quick", "/tmp/sllm_batch_check.log"], 90, max_lines=60)
             if mode == "megakernel":
                 experiments["mega_trace"] = trace_sample(args)
         except Exception as ex:
