@@ -107,8 +107,13 @@ def main():
             fn()
             ok += 1
             log(f"PASS {name}")
-        except Exception:
-            log(f"FAIL {name}:\n" + traceback.format_exc(limit=6))
+        except Exception as ex:
+            if QUICK:   # one line per failure: the exception and the innermost frame of this repository
+                tb = [f for f in traceback.extract_tb(ex.__traceback__) if ROOT in f.filename]
+                where = f"{os.path.relpath(tb[-1].filename, ROOT)}:{tb[-1].lineno}" if tb else "?"
+                log(f"FAIL {name}: {type(ex).__name__}: {str(ex)[:300]} (at {where})")
+            else:
+                log(f"FAIL {name}:\n" + traceback.format_exc(limit=6))
     log(f"done: {ok}/{len(cases)} passed")
 
 

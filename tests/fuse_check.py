@@ -64,8 +64,8 @@ def main():
             b = fused.greedy([1, 2, 3], 20)
             log(f"{name}: 19 greedy tokens {'IDENTICAL' if np.array_equal(a, b) else 'DIFFER at ' + str(int(np.flatnonzero(a != b)[0]))}")
             plain.close(); fused.close()
-        except Exception:
-            log(f"{name}: localisation FAILED:\n" + traceback.format_exc(limit=6))
+        except Exception as ex:
+            log(f"{name}: localisation FAILED: {type(ex).__name__}: {str(ex)[:300]}" + ("" if QUICK else "\n" + traceback.format_exc(limit=6)))
 
     # ---- 2. the test functions
     import test_zzz_mega_fuse_gpu as T
@@ -83,8 +83,13 @@ def main():
             fn()
             ok += 1
             log(f"PASS {name}")
-        except Exception:
-            log(f"FAIL {name}:\n" + traceback.format_exc(limit=6))
+        except Exception as ex:
+            if QUICK:   # one line per failure: the exception and the innermost frame of this repository
+                tb = [f for f in traceback.extract_tb(ex.__traceback__) if ROOT in f.filename]
+                where = f"{os.path.relpath(tb[-1].filename, ROOT)}:{tb[-1].lineno}" if tb else "?"
+                log(f"FAIL {name}: {type(ex).__name__}: {str(ex)[:300]} (at {where})")
+            else:
+                log(f"FAIL {name}:\n" + traceback.format_exc(limit=6))
     log(f"done: {ok}/{len(cases)} passed")
 
 
