@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <functional>
 #include <initializer_list>
 #include <vector>
@@ -34,7 +35,7 @@ constexpr int kThreads = 512;
 constexpr unsigned kSpinLimit = 1u << 26;
 
 // the megakernel's barrier (csrc/mega_common.cuh grid_barrier, poll-the-counter form)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, unsigned limit = kSpinLimit) {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned v;
@@ -43,7 +44,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
         unsigned spins = 0;
         while ((int)(v - target) < 0) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (++spins > kSpinLimit) __trap();
+            if (++spins > limit) __trap();
         }
     }
     __syncthreads();
@@ -68,6 +69,28 @@ __global__ void __launch_bounds__(kThreads, 1) red_probe_kernel(float* x, float*
         }
         if (mode != 4) grid_barrier(counter, base + (++idx) * gridDim.x);
     }
+}
+
+// ---- clusters + cooperative launch: does a grid of clusters really co-reside (every CTA passes one grid barrier) and can a CTA
+// add into its neighbour's shared memory (DSMEM) — the two things the attention -> wo fusion would lean on
+__global__ void __launch_bounds__(kThreads, 1) cluster_probe_kernel(unsigned* counter, unsigned base, unsigned* ok_count) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    float* mine = reinterpret_cast<float*>(dyn_smem);
+    unsigned rank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    if (threadIdx.x == 0) mine[0] = 0.f;
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x == 0) {   // every CTA adds 1 into slot 0 of cluster rank 0's shared memory
+        uint32_t local = (uint32_t)__cvta_generic_to_shared(mine), remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0u));
+        asm volatile("red.shared::cluster.add.f32 [%0], %1;" ::"r"(remote), "f"(1.0f) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    grid_barrier(counter, base + gridDim.x, 1u << 21);   // co-residency of the whole grid (a grid that is not co-resident traps within seconds)
+    if (threadIdx.x == 0 && rank == 0 && mine[0] == (float)csize) atomicAdd(ok_count, 1u);
 }
 
 // ---- TMA ingest probe ----------------------------------------------------------------------------------------------------
@@ -166,6 +189,7 @@ static void coop_launch(const void* kernel, int grid, size_t smem, cudaStream_t 
 }
 
 int main(int argc, char** argv) {
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);   // a line is out as soon as it is printed, whatever happens later
     const int iters = argc > 1 ? std::atoi(argv[1]) : 2000;
     int dev = 0, sms = 0, smem_optin = 0;
     CK(cudaGetDevice(&dev));
@@ -268,5 +292,56 @@ int main(int argc, char** argv) {
         }
         cudaFree(src); cudaFree(sink);
     }
+    // ---- 4. clusters for real (last: a launch that cannot co-reside would end this process): a cooperative launch of clusters at the megakernel's shared-memory size; every CTA passes a grid
+    // barrier and the cluster's CTAs add into rank 0's shared memory. ok = clusters whose sum came out right.
+    for (int cs : {2, 4}) {
+        unsigned *counter = nullptr, *okc = nullptr;
+        CK(cudaMalloc(&counter, 256));
+        CK(cudaMalloc(&okc, 256));
+        CK(cudaMemset(counter, 0, 256));
+        CK(cudaMemset(okc, 0, 256));
+        const size_t smem = (size_t)200 * 1024;
+        cudaError_t e = cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nclusters = 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((sms / cs) * cs);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclusters, cluster_probe_kernel, &cfg);
+        int grid = (e == cudaSuccess && nclusters > 0) ? std::min(nclusters, sms / cs) * cs : 0;
+        unsigned okh = 0;
+        const char* how = "not launched";
+        if (grid > 0) {
+            cfg.gridDim = dim3(grid);
+            cfg.numAttrs = 2;
+            unsigned base = 0;
+            void* args[] = {&counter, &base, &okc};
+            e = cudaLaunchKernelExC(&cfg, (const void*)cluster_probe_kernel, args);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            how = cudaGetErrorString(e);
+            if (e == cudaSuccess) CK(cudaMemcpy(&okh, okc, 4, cudaMemcpyDeviceToHost));
+        } else {
+            how = cudaGetErrorString(e);
+        }
+        std::printf("{\"probe\": \"cluster_cooperative_launch\", \"cluster_size\": %d, \"grid\": %d, \"of_sms\": %d, \"status\": \"%s\", "
+                    "\"clusters_with_correct_dsmem_sum\": %u, \"clusters\": %d}\n", cs, grid, sms, how, okh, grid / cs);
+        cudaGetLastError();
+        if (e != cudaSuccess) {   // a failed cooperative launch can leave a sticky error: stop here rather than report nonsense below
+            std::printf("{\"probe\": \"aborted\", \"after\": \"cluster_cooperative_launch\"}\n");
+            return 0;
+        }
+        cudaFree(counter); cudaFree(okc);
+    }
+
     return 0;
 }
