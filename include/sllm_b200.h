@@ -56,7 +56,8 @@ int sllm_abi_version(void);
  * dependent launch (1 default), key 4 = K split of the residual-epilogue GEMMs (0 never, n up to n ranges, -1 cost model); batched decode:
  * key 5 = replay one CUDA graph per live-slot count instead of the launch sequence, key 6 = GEMV body with four weight rows per warp at
  * a time when 3 or more sequences share a launch, key 7 (with key 6) = down projection with K cut in two over grid.y when more sequences
- * are live than whole rows fit shared memory, so that Wdown is read once (all 0 by default: experimental until measured) */
+ * are live than whole rows fit shared memory, so that Wdown is read once (all 0 by default: experimental until measured); key 8 = decode
+ * megakernel MEASUREMENT aid, results are garbage: bit 0 = skip the grid barriers, bit 1 = skip the dot products (tools/mega_debug.py) */
 int sllm_tune(int32_t key, int32_t value);
 /* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
 int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);

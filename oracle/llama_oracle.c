@@ -285,3 +285,15 @@ void orc_read(orc_model* m, int32_t buffer_id, int64_t offset, int64_t n, float*
     }
     if (src) memcpy(out, src + offset, sizeof(float) * (size_t)n);
 }
+
+/* test aid: overwrite part of a buffer (same ids as orc_read) — used to inject a synthetic KV history so that a full-depth
+ * model can be checked at a late position without running every earlier position through the CPU path */
+void orc_write(orc_model* m, int32_t buffer_id, int64_t offset, int64_t n, const float* src) {
+    float* dst = 0;
+    switch (buffer_id) {
+        case 2: dst = m->key_cache; break;
+        case 3: dst = m->value_cache; break;
+        default: break;
+    }
+    if (dst) memcpy(dst + offset, src, sizeof(float) * (size_t)n);
+}

@@ -51,6 +51,8 @@ int32_t orc_greedy(orc_model* m, const int32_t* prompt, int32_t n_prompt, int32_
                    float* last_logits);
 /* buffer ids follow the reference's ModelBufferType (include/model/model.h:14-34) */
 void orc_read(orc_model* m, int32_t buffer_id, int64_t offset, int64_t n, float* out);
+/* test aid: overwrite floats [offset, offset+n) of the key (2) or value (3) cache, layout [L][S][kv] (model.cpp:264-265) */
+void orc_write(orc_model* m, int32_t buffer_id, int64_t offset, int64_t n, const float* src);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,7 @@ class Port:
         L.orc_greedy.restype = C.c_int32
         L.orc_greedy.argtypes = [C.c_void_p, _i32p, C.c_int32, C.c_int32, _i32p, C.c_void_p]
         L.orc_read.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _f32p]
+        L.orc_write.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _f32p]
 
     # -- synthetic weights --
     def blob_floats(self, shape: Shape) -> int:
@@ -223,6 +224,11 @@ class PortModel:
         out = np.empty(n, np.float32)
         self.lib.orc_read(self.h, buffer_id, offset, n, out)
         return out
+
+    def write(self, buffer_id: int, offset: int, values: np.ndarray) -> None:
+        """Overwrite part of the key (2) / value (3) cache, layout [L][S][kv] — injects a synthetic history."""
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        self.lib.orc_write(self.h, buffer_id, offset, values.size, values)
 
     def close(self):
         if self.h:

@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                     mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
                     const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (WD == SLLM_INT8) {
+                    if (p.debug & 2) {
+                        a0 = __uint_as_float(*reinterpret_cast<const uint32_t*>(sp));   // measurement aid: touch the slot, skip the arithmetic
+                    } else if (WD == SLLM_INT8) {
                         // 16 int8 weights per chunk, exact int8 -> fp32 by byte permute (gemv_core.cuh s8f); the group scale of
                         // the chunk (one fp32 per 4 chunks, stored behind the tile's weights) multiplies the chunk's partial sum
                         const uint8_t* sc_base = sp - lane * 16 + (size_t)ph.R * sbytes;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             MEGA_STAMP(ev, 5);
             continue;
         }
-        grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        if (p.debug & 1) { ++bar_idx; __syncthreads(); } else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
         MEGA_STAMP(ev, 5);   // barrier passed
         if (ph.kind != PH_QKV) continue;
         MEGA_STAMP(ev + 1, 0);
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             fence_async_smem();
         }
         MEGA_STAMP(ev + 1, 4);
-        grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        if (p.debug & 1) { ++bar_idx; __syncthreads(); } else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
         MEGA_STAMP(ev + 1, 5);
     }
 }
@@ -957,7 +959,10 @@ static int mega_launch_t(const MegaParams& p, int grid, size_t smem, cudaStream_
     return SLLM_OK;
 }
 
-int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down) {
+extern int g_tune_mega_debug;
+int mega_launch(const MegaParams& p_in, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down) {
+    MegaParams p = p_in;
+    p.debug = g_tune_mega_debug;
     if (fuse_down) {   // experimental kernel: fp32 / bf16 weights only (mega_fuse_down_ok)
 #define MEGA_F(GG)                                                                                                      \
     case GG:                                                                                                            \

@@ -49,6 +49,7 @@ struct MegaParams {
     int32_t* history;
     unsigned* bar_counter;
     unsigned long long* trace;  // optional [grid][512][8] %globaltimer stamps (nullptr = off)
+    int32_t debug;              // measurement aid (sllm_tune key 8; results are garbage): bit 0 = skip the grid barriers, bit 1 = skip the dot products
 };
 
 // ---- barrier-free {value, epoch}-word version (megakernel_ll.cu), single GPU and tensor parallel -------------

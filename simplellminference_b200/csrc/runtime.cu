@@ -15,6 +15,7 @@ int g_tune_pf_ksplit = -1;  // prefill GEMM, residual epilogue: 0 = never split 
 int g_tune_batch_graph = 0;   // batched decode: 1 = replay one CUDA graph per live-slot count instead of the launch sequence (experimental)
 int g_tune_batch_rows4 = 0;   // batched decode GEMV: 1 = four weight rows per warp at a time for >= 3 vectors (experimental)
 int g_tune_batch_ksplit = 0;  // batched decode, with rows4: down projection with K cut in two over grid.y when more vectors are live than fit whole rows (experimental)
+int g_tune_mega_debug = 0;   // decode megakernel measurement aid (MegaParams::debug): bit 0 = no grid barriers, bit 1 = no dot products; results are garbage
 int g_tune_pf_pair = -1;   // prefill GEMM: 1 / 0 = force / forbid the two-SM (cta_group::2) kernel, -1 = heuristic
 
 void set_error(const char* fmt, ...) {
@@ -68,6 +69,7 @@ int sllm_tune(int32_t key, int32_t value) {
         case 5: sllm::g_tune_batch_graph = value; return SLLM_OK;
         case 6: sllm::g_tune_batch_rows4 = value; return SLLM_OK;
         case 7: sllm::g_tune_batch_ksplit = value; return SLLM_OK;
+        case 8: sllm::g_tune_mega_debug = value; return SLLM_OK;
         default: sllm::set_error("unknown tunable %d", key); return SLLM_EINVAL;
     }
 }

@@ -183,13 +183,10 @@ def test_step_bytes_share_the_weights(port):
     bd.close(); eng.close()
 
 
-# ---- written after the round's GPU budget was spent (the tests above ran on a B200): the round-end run is the FIRST execution
-# of everything below. Until a run has confirmed them they are non-strict xfail: an XPASS in the report is the confirmation, an
-# xfail names what to fix, and neither hides the verified part of the suite. Remove the mark once they have passed on a GPU.
-first_run = pytest.mark.xfail(strict=False, reason="never executed on a GPU yet (written after the round's GPU budget was spent)")
+# ---- the cases below first ran at the end of round 1 on the driver's B200 (all passed): plain tests since then, so a regression
+# of the batched decoder turns the suite red.
 
 
-@first_run
 def test_full_width_llama2_7b_two_layers_batch_of_eight(port):
     """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers and eight sequences: the shapes
     where the staged activations need opt-in shared memory (8 x 4096 floats = 128 KB per CTA) and where the down projection
@@ -246,7 +243,6 @@ def run_teacher_forced(port, ms, wd, kvd, seed, firsts, joins, n_steps, checkpoi
     return eng, bd
 
 
-@first_run
 @pytest.mark.parametrize("heads,kv_heads", [(8, 8), (8, 2)])
 def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     """Contexts of up to 300 positions in 20 slots: the attention kernel runs with several KV splits per (slot, head) and
@@ -262,7 +258,6 @@ def test_long_context_many_slots_split_kv(port, heads, kv_heads):
     bd.close(); eng.close()
 
 
-@first_run
 @pytest.mark.parametrize("name", ["cfg1_stories15M", "cfg2_stories110M", "tiny_gqa", "tiny_gqa_bf16w", "tiny_gqa_int8w", "tiny_mha_hd48"])
 def test_golden_streams_of_the_reference_inside_a_batch(golden_models, name):
     """The token streams and final logits recorded from the UNMODIFIED reference (tests/golden/models_ref.npz, the fixtures
@@ -290,7 +285,6 @@ def test_golden_streams_of_the_reference_inside_a_batch(golden_models, name):
     bd.close(); eng.close()
 
 
-@first_run
 def test_continuous_batching_matches_oracle_per_request(port):
     """scheduler.ContinuousBatcher over the real decoder: nine requests through three slots and a pool that cannot hold
     three full-length requests at once (admissions are deferred), chunks of 5 steps; every request = the oracle alone.
@@ -321,7 +315,6 @@ def test_continuous_batching_matches_oracle_per_request(port):
     bd.close(); eng.close()
 
 
-@first_run
 def test_cpp_mirror_predict_batch(tmp_path):
     """model::LlamaModel::predict_batch of the C++ host mirror (waves of prompts through sllm_batch_*) against the oracle per prompt."""
     import os
@@ -337,7 +330,6 @@ def test_cpp_mirror_predict_batch(tmp_path):
     assert "PASS" in r.stdout
 
 
-@first_run
 def test_graph_replay_matches_direct_launches():
     """Opt-in development knob sllm_tune(5, 1): the step's launch sequence depends on the live-slot count alone (tokens,
     positions and block tables are device memory), so it is captured into one CUDA graph per count and replayed. Same
@@ -371,7 +363,6 @@ def test_graph_replay_matches_direct_launches():
     eng.close()
 
 
-@first_run
 @pytest.mark.parametrize("preset,wd", [("tiny_gqa", F32), ("tiny_gqa", BF16), ("tiny_gqa", INT8), ("tiny_mha_hd48", F32)])
 def test_four_row_gemv_body_is_bit_identical(preset, wd):
     """Opt-in development knob sllm_tune(6, 1): the GEMV body that takes two units (four weight rows) per warp at a time,
@@ -401,7 +392,6 @@ def test_four_row_gemv_body_is_bit_identical(preset, wd):
     eng.close()
 
 
-@first_run
 def test_sampling_per_slot_matches_the_single_sequence_sampler(port):
     """sllm_batch_set_sampling: a slot that samples draws exactly what predict.sample_ids draws for that sequence alone (same
     logits, same (seed, position) key), and its neighbours — greedy or sampling with other parameters — are not disturbed."""
@@ -439,7 +429,6 @@ def test_sampling_per_slot_matches_the_single_sequence_sampler(port):
     bd.close(); eng.close()
 
 
-@first_run
 @pytest.mark.parametrize("wd", [F32, BF16, INT8])
 def test_split_down_projection_matches_oracle(port, wd):
     """Opt-in development knobs sllm_tune(6, 1) + (7, 1): with an intermediate size whose rows do not fit shared memory eight

@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# tools/r2_session.sh <steps...> — round-2 GPU sessions: each named step under its own timeout, its output in gpurun_out/<name>.log
+# as soon as it is done. Nothing here is a bench value taken under a profiler.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out
+mkdir -p "$OUT"
+step() { local secs=$1 name=$2; shift 2; local t0=$SECONDS
+    timeout --signal=TERM --kill-after=20 "$secs" "$@" > "$OUT/$name.log" 2>&1
+    echo "$name rc=$? $((SECONDS - t0))s" | tee -a "$OUT/session_steps.txt"; return 0; }
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > "$OUT/gpu.txt" 2>&1
+free -g > "$OUT/host.txt"; nproc >> "$OUT/host.txt"
+for s in "$@"; do
+  case "$s" in
+    fullcfg)   step 900 fullcfg python -m pytest tests/test_full_config_gpu.py -q -x -s -rs ;;
+    probe)     step 120 fusion_probe tools/microbench/_build/fusion_probe 1000 ;;
+    trace)     step 120 mega_trace python tools/mega_trace.py ;;
+    trace_ll)  step 120 mega_trace_ll python tools/mega_trace.py --ll ;;
+    debug)     step 240 mega_debug python tools/mega_debug.py ;;
+    pytest)    step 1200 pytest_gpu python -m pytest tests -q -m gpu -rxXs --deselect tests/test_full_config_gpu.py ;;
+    pytest_all) step 1500 pytest_gpu python -m pytest tests -q -m gpu -rxXs ;;
+    bench)     step 600 bench python bench.py --no-batch; grep -h '^{' "$OUT/bench.log" | tail -1 > "$OUT/bench.json" ;;
+    bench_full) step 900 bench python bench.py; grep -h '^{' "$OUT/bench.log" | tail -1 > "$OUT/bench.json" ;;
+    *) step 900 "custom_$(echo "$s" | tr -c 'a-zA-Z0-9' '_' | cut -c1-40)" bash -c "$s" ;;
+  esac
+done
+echo "session done" | tee -a "$OUT/session_steps.txt"
