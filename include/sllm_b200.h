@@ -180,6 +180,12 @@ typedef struct {
                                     per layer instead of five, but a summation order that is not fixed (logits vary in the last bits
                                     from run to run). Costs a second, transposed copy of the down matrices. Off until measured;
                                     sllm_engine_mode() says "megakernel(fused-down)" when it is in effect */
+#define SLLM_ENGINE_MEGA_V2 128u /* with MEGAKERNEL on one GPU (fp32 / bf16 weights): the megakernel with two grid-wide dependency points
+                                   * per layer instead of five (csrc/megakernel2.cu): qkv -> attention -> wo chained through per-kv-head
+                                   * counters, wo as a K split by kv head group adding into h with red.global.add.f32. With
+                                   * MEGA_FUSE_DOWN the down projection is fused into the gate_up phase as well. Summation order of wo
+                                   * (and of a fused down) is not fixed: logits differ in the last bits from run to run (inside the
+                                   * decode tolerance). Shapes it cannot take fall back to the grid-barrier kernel (sllm_engine_mode). */
 #define SLLM_ENGINE_P2P_ALLREDUCE 8u /* TP: one-shot all-reduce over NVLink peer memory instead of NCCL */
 
 typedef struct sllm_engine sllm_engine;

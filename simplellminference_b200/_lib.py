@@ -31,6 +31,7 @@ class EngineConfig(C.Structure):
 
 ENGINE_UNFUSED, ENGINE_NO_GRAPH, ENGINE_PDL, ENGINE_P2P_ALLREDUCE, ENGINE_MEGAKERNEL, ENGINE_MEGA_LL = 1, 2, 4, 8, 16, 32
 ENGINE_MEGA_FUSE_DOWN = 64
+ENGINE_MEGA_V2 = 128
 EINVAL, ENOTSUP, ENOMEM, ESTATE, ECOMM = -1, -2, -3, -4, -5   # SLLM_E* of include/sllm_b200.h
 
 _P = C.c_void_p

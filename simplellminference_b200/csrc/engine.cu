@@ -55,6 +55,11 @@ struct sllm_engine {
     bool mega = false;            // persistent one-launch-per-token kernel (megakernel.cu / megakernel_ll.cu)
     bool mega_ll = false;         // barrier-free {value, epoch}-word version (also the tensor-parallel one)
     bool mega_fuse = false;       // experimental: down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN)
+    bool mega2 = false;           // megakernel2.cu: two grid-wide dependency points per layer (SLLM_ENGINE_MEGA_V2)
+    void* wo_t = nullptr;         // its column-block copy of every layer's Wo (megakernel.cuh "PH_WO_T"); wo stays for the batched prefill
+    float* v2_bufs = nullptr;     // xbuf[2], hbuf[2]: d floats each, touched by that kernel only (zero-on-entry invariants)
+    unsigned* v2_flags = nullptr; // per-kv-head dependency counters
+    Mega2Params mega2_params{};
     void* wdown_t = nullptr;      // its transposed per-layer matrices (megakernel.cuh "PH_DOWN_T"); wdown stays for the batched prefill
     MegaLLPlan ll_plan{};
     MegaLLParams ll_params{};
@@ -180,6 +185,9 @@ static void layout(sllm_engine* e) {
     e->prompt_dev = carve<int32_t>(e, 4 * (size_t)S);
     e->history_dev = carve<int32_t>(e, 4 * (size_t)S);
     e->wdown_t = e->mega_fuse ? carve<void>(e, (size_t)L * mega_down_t_bytes(e->d, e->I_loc, e->cfg.w_dtype)) : nullptr;
+    e->wo_t = e->mega2 ? carve<void>(e, (size_t)L * mega2_wot_bytes(e->d, e->hd, e->H_loc, e->KVH_loc, e->cfg.w_dtype)) : nullptr;
+    e->v2_bufs = e->mega2 ? carve<float>(e, 4 * (size_t)4 * d) : nullptr;
+    e->v2_flags = e->mega2 ? carve<unsigned>(e, (size_t)2 * e->KVH_loc * 128) : nullptr;
 }
 
 static int count_launch(sllm_engine* e) {
@@ -483,6 +491,7 @@ static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
         SLLM_REQUIRE(!e->mega_ll || e->ll_ready, SLLM_ESTATE, "tensor-parallel megakernel: peer areas not exchanged yet (sllm_engine_p2p_import)");
         for (int i = 0; i < n; ++i) {
             const int rc = e->mega_ll ? mega_ll_launch(e->ll_params, e->H_loc / e->KVH_loc, e->ll_plan.grid, e->ll_plan.smem, e->stream)
+                           : e->mega2 ? mega2_launch(e->mega2_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream, e->mega_fuse)
                                       : mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream, e->mega_fuse);
             if (rc) return rc;
             e->total_launches++;
@@ -593,6 +602,12 @@ static int mega_stage_end(sllm_engine* e) {
             rc = mega_repack_down_t(reinterpret_cast<uint8_t*>(e->wdown.rm) + wbytes(e->cfg.w_dtype, l * e->wdown.rows * e->wdown.cols),
                                     reinterpret_cast<uint8_t*>(e->wdown_t) + (size_t)l * per_layer, e->d, e->I_loc, e->cfg.w_dtype, e->stream);
     }
+    if (e->mega2) {   // the column-block copy of every layer's Wo, from the same row-major staging copy
+        const size_t per_layer = mega2_wot_bytes(e->d, e->hd, e->H_loc, e->KVH_loc, e->cfg.w_dtype);
+        for (int64_t l = 0; l < e->wo.layers && rc == SLLM_OK; ++l)
+            rc = mega2_repack_wot(reinterpret_cast<uint8_t*>(e->wo.rm) + wbytes(e->cfg.w_dtype, l * e->wo.rows * e->wo.cols),
+                                  reinterpret_cast<uint8_t*>(e->wo_t) + (size_t)l * per_layer, e->d, e->hd, e->H_loc, e->KVH_loc, e->cfg.w_dtype, e->stream);
+    }
     cudaError_t ce = cudaStreamSynchronize(e->stream);
     cudaFree(e->emb.rm);
     for (Matrix* m : ms) m->rm = nullptr;
@@ -621,6 +636,10 @@ static int setup_mega(sllm_engine* e) {
         for (int l = 0; l < e->L; ++l)
             mega_fill_down_t(host[(size_t)4 * l + 3], reinterpret_cast<const uint8_t*>(e->wdown_t) + (size_t)l * mega_down_t_bytes(e->d, e->I_loc, e->cfg.w_dtype),
                              e->d, e->I_loc, l, e->cfg.w_dtype);
+    if (e->mega2)
+        for (int l = 0; l < e->L; ++l)
+            mega2_fill_wot(host[(size_t)4 * l + 1], reinterpret_cast<const uint8_t*>(e->wo_t) + (size_t)l * mega2_wot_bytes(e->d, e->hd, e->H_loc, e->KVH_loc, e->cfg.w_dtype),
+                           e->d, e->hd, e->H_loc, e->KVH_loc, l, e->cfg.w_dtype);
     if (e->mega_ll) {
         MegaLLParams& q = e->ll_params;
         q.phases = e->phases_dev;
@@ -647,6 +666,12 @@ static int setup_mega(sllm_engine* e) {
     p.sin_t = e->sin_t; p.cos_t = e->cos_t; p.x = e->x; p.h = e->h; p.q = e->q; p.swi = e->swi; p.logits = e->logits;
     p.att_part = e->mega_att; p.blk_val = e->blk_val; p.blk_idx = e->blk_idx; p.st = e->state; p.prompt = e->prompt_dev;
     p.history = e->history_dev; p.bar_counter = e->bar_counter; p.trace = nullptr;
+    if (e->mega2) {
+        Mega2Params& P = e->mega2_params;
+        P.m = p;
+        P.xbuf[0] = e->v2_bufs; P.xbuf[1] = e->v2_bufs + e->d; P.hbuf[0] = e->v2_bufs + 2 * (size_t)e->d; P.hbuf[1] = e->v2_bufs + 3 * (size_t)e->d;
+        P.x_copy = e->x; P.h_copy = e->h; P.flags = e->v2_flags;
+    }
     return SLLM_OK;
 }
 
@@ -745,6 +770,8 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
         const int g_q = e->H_loc / e->KVH_loc;
         e->mega_fuse = e->mega && !e->mega_ll && (cfg->flags & SLLM_ENGINE_MEGA_FUSE_DOWN) && mega_fuse_down_ok(cfg->w_dtype, e->d, e->I_loc) &&
                        (g_q == 1 || g_q == 2 || g_q == 4 || g_q == 8);
+        e->mega2 = e->mega && !e->mega_ll && (cfg->flags & SLLM_ENGINE_MEGA_V2) && (g_q == 1 || g_q == 2 || g_q == 4 || g_q == 8) &&
+                   mega2_ok(cfg->w_dtype, e->d, e->hd, e->H_loc, e->KVH_loc, e->mega_plan_.nsplit, e->mega_plan_.grid, nullptr);
     }
     layout(e);  // measure
     e->arena_bytes = align_up(e->arena_used, 1 << 20);
@@ -1118,7 +1145,7 @@ int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32
         case 200: {   // megakernel timeline: allocate on first request, stamps are written from the next step on
             SLLM_REQUIRE(e->mega, SLLM_ESTATE, "trace needs megakernel mode");
             const size_t nb = (size_t)(e->mega_ll ? e->ll_plan.grid : e->mega_plan_.grid) * 512 * 8 * 8;
-            if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; e->ll_params.trace = e->trace; }
+            if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; e->mega2_params.m.trace = e->trace; e->ll_params.trace = e->trace; }
             *ptr = e->trace; *n = (int64_t)(nb / 4); *dtype = SLLM_F32; break;
         }
         case 110: *ptr = e->emb.sc; *n = e->emb.sc ? (int64_t)e->V * e->d / e->cfg.group : 0; break;
@@ -1172,6 +1199,7 @@ int64_t sllm_engine_kernel_bytes(const sllm_engine* e, int32_t kind, int32_t pos
 
 const char* sllm_engine_mode(const sllm_engine* e) {
     if (!e) return "null";
+    if (e->mega && e->mega2) return e->mega_fuse ? "megakernel(v2,fused-down)" : "megakernel(v2)";
     if (e->mega) return e->mega_ll ? "megakernel(ll)" : e->mega_fuse ? "megakernel(fused-down)" : "megakernel";
     if (!e->fused) return "unfused";
     return e->use_graph ? (e->pdl ? "fused+graph+pdl" : "fused+graph") : (e->pdl ? "fused+pdl" : "fused");

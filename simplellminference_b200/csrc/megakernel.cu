@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             MEGA_STAMP(ev, 5);
             continue;
         }
-        if (p.debug & 1) { ++bar_idx; __syncthreads(); } else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        if (p.debug & 1) __syncthreads(); else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
         MEGA_STAMP(ev, 5);   // barrier passed
         if (ph.kind != PH_QKV) continue;
         MEGA_STAMP(ev + 1, 0);
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             fence_async_smem();
         }
         MEGA_STAMP(ev + 1, 4);
-        if (p.debug & 1) { ++bar_idx; __syncthreads(); } else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
+        if (p.debug & 1) __syncthreads(); else grid_barrier(p.bar_counter, bar_base + (++bar_idx) * (unsigned)ncta);
         MEGA_STAMP(ev + 1, 5);
     }
 }

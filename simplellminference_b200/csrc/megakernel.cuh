@@ -106,7 +106,7 @@ void mega_fill_phases(PhaseDesc* host, int L, int w_dtype, const void* wqkv, con
 // scales_rowmajor: int8 only, fp32 [rows][cols/64] (the tiled layout carries each tile's scales behind its weights)
 int mega_repack(const void* src_rowmajor, const float* scales_rowmajor, void* dst_tiled, int rows, int cols, int kind, int w_dtype, int hd,
                 int q_loc, int kv_loc, int I_loc, cudaStream_t st);
-enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4, PH_DOWN_T = 5 };
+enum { PH_QKV = 0, PH_WO = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_CLS = 4, PH_DOWN_T = 5, PH_WO_T = 6 };
 int mega_launch(const MegaParams& p, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down = false);
 
 // ---- experimental: down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN) ---------------------------------
@@ -123,5 +123,26 @@ bool mega_fuse_down_ok(int w_dtype, int d, int I_loc);
 size_t mega_down_t_bytes(int d, int I_loc, int w_dtype);
 void mega_fill_down_t(PhaseDesc& ds, const void* Wt, int d, int I_loc, int layer, int w_dtype);
 int mega_repack_down_t(const void* src_rowmajor /* [d][I_loc] */, void* dst, int d, int I_loc, int w_dtype, cudaStream_t st);
+
+
+// ---- megakernel2.cu: two (or three) grid-wide dependency points per layer instead of five (SLLM_ENGINE_MEGA_V2) -------------------
+// qkv -> attention and attention -> wo go through per-kv-head counters instead of grid barriers; wo is a K split by kv head group
+// over the CTAs that hold the group's attention items, reading a column-block copy of Wo ("WoT", PH_WO_T: for group g the block
+// Wo[:, g*G*hd:(g+1)*G*hd] as [d rows][CRP chunks], 4 KB tiles of 256 / CRP whole rows) and adding into h with red.global.add.f32.
+struct Mega2Params {
+    MegaParams m;          // phases[4l + 1] is the PH_WO_T descriptor; m.x / m.h are not used
+    float* xbuf[2];        // residual stream entering layer gl (global layer index = launches * L + l): xbuf[gl & 1]
+    float* hbuf[2];        // h of layer gl: hbuf[gl & 1], zeroed during layer gl - 1
+    float* x_copy;         // introspection: final residual stream (emb_output)
+    float* h_copy;         // introspection: h of the last layer (ffn_input)
+    unsigned* flags;       // [2][KVH_loc] monotonic counters, one per 128-byte line: units of q/k/v finished, attention splits finished
+};
+struct WotGeom { int nchunks, crp, nr, ntr; size_t group_bytes, bytes; };
+WotGeom mega2_wot_geom(int d, int ghd, int kvh, int w_dtype);
+bool mega2_ok(int w_dtype, int d, int hd, int H_loc, int KVH_loc, int nsplit, int grid, const char** why);
+size_t mega2_wot_bytes(int d, int hd, int H_loc, int KVH_loc, int w_dtype);
+void mega2_fill_wot(PhaseDesc& ds, const void* W, int d, int hd, int H_loc, int KVH_loc, int layer, int w_dtype);
+int mega2_repack_wot(const void* src_rowmajor /* [d][H_loc*hd] */, void* dst, int d, int hd, int H_loc, int KVH_loc, int w_dtype, cudaStream_t st);
+int mega2_launch(const Mega2Params& P, int g, int grid, size_t smem, cudaStream_t st, bool fuse_down);
 
 }  // namespace sllm

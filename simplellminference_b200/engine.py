@@ -19,13 +19,13 @@ BUF = dict(key_cache=2, value_cache=3, emb_output=4, rms_output=5, query=6, mha_
 class Engine:
     def __init__(self, shape: ModelShape, w_dtype: int = BF16, kv_dtype: int = BF16, group: int = 64, tp_rank: int = 0,
                  tp_size: int = 1, fused: bool = True, graph: bool = True, pdl: bool = False, mega: bool = False, mega_ll: bool = False, p2p_allreduce: bool = False,
-                 stream: torch.cuda.Stream | None = None, mega_fuse_down: bool = False):
+                 stream: torch.cuda.Stream | None = None, mega_fuse_down: bool = False, mega_v2: bool = False):
         self.lib = _lib.load()
         self.shape, self.w_dtype, self.kv_dtype, self.group = shape, w_dtype, kv_dtype, group
         self.tp_rank, self.tp_size = tp_rank, tp_size
         flags = (0 if fused else _lib.ENGINE_UNFUSED) | (0 if graph else _lib.ENGINE_NO_GRAPH) | \
                 (_lib.ENGINE_PDL if pdl else 0) | (_lib.ENGINE_MEGAKERNEL if mega else 0) | (_lib.ENGINE_MEGA_LL if mega_ll else 0) | (_lib.ENGINE_P2P_ALLREDUCE if p2p_allreduce else 0) | \
-                (_lib.ENGINE_MEGA_FUSE_DOWN if mega_fuse_down else 0)   # experimental: see SLLM_ENGINE_MEGA_FUSE_DOWN in include/sllm_b200.h
+                (_lib.ENGINE_MEGA_FUSE_DOWN if mega_fuse_down else 0) | (_lib.ENGINE_MEGA_V2 if mega_v2 else 0)   # see SLLM_ENGINE_MEGA_* in include/sllm_b200.h
         cfg = _lib.EngineConfig(_lib.Shape(shape.vocab, shape.head_dim, shape.hidden, shape.kv_hidden, shape.inter, shape.max_len,
                                            shape.layers, shape.heads, shape.kv_heads, shape.eps, shape.theta),
                                 w_dtype, kv_dtype, group, tp_rank, tp_size, flags)

@@ -35,16 +35,22 @@ def logit_tol(want):
 
 
 @pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
-@pytest.mark.parametrize("mode", ["mega", "mega_ll", "fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
+@pytest.mark.parametrize("mode", ["mega", "mega_v2", "mega_v2_fuse", "mega_ll", "fused_graph", "fused_graph_pdl", "fused_nograph", "unfused"])
 def test_golden_models(golden_models, name, mode):
     """Token streams and final logits recorded from the reference itself (tests/golden/models_ref.npz)."""
     prompt, n_total, wd = mg.MODEL_RUNS[name]
     ms = PRESETS[PRESET_OF[name]]
-    kw = dict(mega=dict(mega=True), mega_ll=dict(mega=True, mega_ll=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
+    kw = dict(mega=dict(mega=True), mega_v2=dict(mega=True, mega_v2=True), mega_v2_fuse=dict(mega=True, mega_v2=True, mega_fuse_down=True),
+              mega_ll=dict(mega=True, mega_ll=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
     if mode.startswith("mega"):
-        # int8 group-64 tiles are streamed by the grid-barrier megakernel only: asking for the word-based one falls back to it, visibly
-        want_mode = "megakernel" if (mode == "mega" or wd == INT8) else "megakernel(ll)"
+        # int8 group-64 tiles are streamed by the grid-barrier megakernel only: asking for another one falls back to it, visibly
+        rb = ms.hidden * (4 if wd == F32 else 2)   # mega_fuse_down_ok: a row of outputs = 2^k stripes of 512 bytes
+        fuse_ok = wd != INT8 and rb % 512 == 0 and (rb // 512) & (rb // 512 - 1) == 0 and rb // 512 <= 16 and ms.inter % 4 == 0
+        want_mode = {"mega": "megakernel", "mega_ll": "megakernel(ll)", "mega_v2": "megakernel(v2)",
+                     "mega_v2_fuse": "megakernel(v2,fused-down)" if fuse_ok else "megakernel(v2)"}[mode]
+        if wd == INT8:
+            want_mode = "megakernel"
         assert eng.mode == want_mode, eng.mode
     toks = eng.greedy(prompt, n_total)
     want = golden_models[name + "/tokens"]
@@ -77,13 +83,14 @@ def test_blob_loader_equals_synthetic(port):
         a.close(); b.close()
 
 
-@pytest.mark.parametrize("mega", [True, False])
+@pytest.mark.parametrize("mega", [True, False, "v2"])
 def test_forward_api_matches_oracle_per_position(port, mega):
     """LlamaModel::forward semantics: explicit (token, pos), logits back on the host, every position checked."""
     ms = PRESETS["tiny_mha_hd48"]
     blob = port.fill_blob(oracle_shape(ms), 42)
     om = port.model(oracle_shape(ms), blob)
-    eng = Engine(ms, w_dtype=F32, kv_dtype=F32, mega=mega).load_blob(blob)
+    eng = Engine(ms, w_dtype=F32, kv_dtype=F32, mega=bool(mega), mega_v2=(mega == "v2")).load_blob(blob)
+    assert mega != "v2" or eng.mode == "megakernel(v2)", eng.mode
     tok = 5
     for pos in range(ms.max_len):
         want = om.forward(tok, pos)
@@ -94,7 +101,7 @@ def test_forward_api_matches_oracle_per_position(port, mega):
     eng.close()
 
 
-@pytest.mark.parametrize("mega", [True, False])
+@pytest.mark.parametrize("mega", [True, False, "v2", "v2fuse"])
 @pytest.mark.parametrize("wd,kvd", [(BF16, BF16), (INT8, BF16), (F32, BF16)])
 def test_bf16_kv_cache_variant(port, wd, kvd, mega):
     """bf16 KV cache has no reference implementation: its definition is the oracle with cache rows rounded to
@@ -103,7 +110,7 @@ def test_bf16_kv_cache_variant(port, wd, kvd, mega):
     blob = port.fill_blob(oracle_shape(ms), 7, wd, 64)
     om = port.model(oracle_shape(ms), blob, kv_bf16=True)
     want, want_l = om.greedy([1, 9], 46)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, mega=mega).load_synthetic(7)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(7)
     got = eng.greedy([1, 9], 46)
     logits = eng.buffer("model_pred").cpu().numpy()
     err = float(np.abs(logits - want_l).max())
@@ -129,13 +136,15 @@ def test_full_context_and_state_api(port):
     eng.close()
 
 
-@pytest.mark.parametrize("mega", [True, False])
+@pytest.mark.parametrize("mega", [True, False, "v2", "v2fuse"])
 def test_medium_shape_tokens(port, mega):
     """A GQA shape with the production head_dim (128) and a long-ish context, bf16 weights, fp32 KV."""
     ms = ModelShape(4096, 128, 1024, 256, 2816, 160, 4, 8, 2)
     blob = port.fill_blob(oracle_shape(ms), 3, BF16)
     want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1).greedy(list(range(1, 33)), 150)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=mega).load_synthetic(3)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(3)
+    if str(mega).startswith("v2"):
+        assert eng.mode == ("megakernel(v2,fused-down)" if mega == "v2fuse" else "megakernel(v2)"), eng.mode
     got = eng.greedy(list(range(1, 33)), 150)
     assert np.array_equal(got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
@@ -144,15 +153,16 @@ def test_medium_shape_tokens(port, mega):
 
 
 @pytest.mark.parametrize("kvd", [F32, BF16])
-@pytest.mark.parametrize("mega_ll", [False, True])
+@pytest.mark.parametrize("mega_ll", [False, True, "v2", "v2fuse"])
 def test_gqa8_hd64_megakernel(port, kvd, mega_ll):
     """TinyLlama's head geometry (8 query heads per KV head, head_dim 64): the cross-stripe attention buffer spans both K/V
     stages. Must run in megakernel mode (it used to fall back) and match the oracle."""
     ms = ModelShape(2048, 64, 512, 64, 1408, 200, 3, 8, 1)
     blob = port.fill_blob(oracle_shape(ms), 5, BF16)
     want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=(kvd == BF16)).greedy([1, 5, 9], 190)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=kvd, mega=True, mega_ll=mega_ll).load_synthetic(5)
-    assert eng.mode == ("megakernel(ll)" if mega_ll else "megakernel"), eng.mode
+    v2 = str(mega_ll).startswith("v2")
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=kvd, mega=True, mega_ll=(mega_ll is True), mega_v2=v2, mega_fuse_down=(mega_ll == "v2fuse")).load_synthetic(5)
+    assert eng.mode == {False: "megakernel", True: "megakernel(ll)", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega_ll], eng.mode
     got = eng.greedy([1, 5, 9], 190)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
     if kvd == F32:
@@ -181,7 +191,7 @@ def test_int8_megakernel_shapes(port):
         eng.close(); ref.close()
 
 
-@pytest.mark.parametrize("wd,mega", [(BF16, True), (INT8, True), (BF16, False)])
+@pytest.mark.parametrize("wd,mega", [(BF16, True), (INT8, True), (BF16, False), (BF16, "v2"), (BF16, "v2fuse")])
 def test_full_width_llama2_7b_two_layers(port, wd, mega):
     """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers: the tile geometry the bench runs on
     (K = 11008 -> 16 K slices of 86 chunks, 2-row tiles; int8: 88 chunks) checked against the oracle, which the small shapes cannot
@@ -191,13 +201,13 @@ def test_full_width_llama2_7b_two_layers(port, wd, mega):
     blob = port.fill_blob(oracle_shape(ms), 9, wd, 64, threads=os.cpu_count() or 1)
     om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
     want, want_l = om.greedy([1, 2, 3], 14)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=mega).load_synthetic(9)
-    assert eng.mode == ("megakernel" if mega else "fused+graph"), eng.mode
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(9)
+    assert eng.mode == {True: "megakernel", False: "fused+graph", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega], eng.mode
     got = eng.greedy([1, 2, 3], 14)
     assert np.array_equal(got, want), (got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
     assert err <= 5e-3 * max(1.0, float(np.abs(want_l).max())), err
-    if wd == BF16 and mega:   # the same prompt as ONE batched tensor-core pass: K = 11008 with its ragged k-block tail per K slice
+    if wd == BF16 and mega is True:   # the same prompt as ONE batched tensor-core pass: K = 11008 with its ragged k-block tail per K slice
         ids = np.concatenate([[1, 2, 3], want[:9]]).astype(np.int32)
         om2 = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
         for p in range(ids.size - 1):
@@ -213,7 +223,7 @@ def test_full_width_llama2_7b_two_layers(port, wd, mega):
     eng.close()
 
 
-@pytest.mark.parametrize("mega_ll", [False, True])
+@pytest.mark.parametrize("mega_ll", [False, True, "v2", "v2fuse"])
 def test_full_width_llama3_8b_one_layer(port, mega_ll):
     """Llama-3-8B widths (GQA 4 query heads per KV head, inter 14336 -> 112-chunk K slices, 128 256-row tied classifier) with one
     layer, both megakernels, against the oracle (bf16 KV on both sides)."""
@@ -221,8 +231,8 @@ def test_full_width_llama3_8b_one_layer(port, mega_ll):
     ms = dataclasses.replace(PRESETS["llama3-8b"], layers=1, max_len=48)
     blob = port.fill_blob(oracle_shape(ms), 13, BF16, 64, threads=os.cpu_count() or 1)
     want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True).greedy([1, 2, 3, 4, 5], 14)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, mega=True, mega_ll=mega_ll).load_synthetic(13)
-    assert eng.mode == ("megakernel(ll)" if mega_ll else "megakernel"), eng.mode
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, mega=True, mega_ll=(mega_ll is True), mega_v2=str(mega_ll).startswith("v2"), mega_fuse_down=(mega_ll == "v2fuse")).load_synthetic(13)
+    assert eng.mode == {False: "megakernel", True: "megakernel(ll)", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega_ll], eng.mode
     got = eng.greedy([1, 2, 3, 4, 5], 14)
     assert np.array_equal(got, want), (got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())

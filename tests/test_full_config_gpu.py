@@ -1,20 +1,25 @@
 """GPU parity at the BASELINE.json configurations THEMSELVES (full depth, full width, late positions) — VERDICT r1 "next" item 1.
 
-The small-shape tests cannot reach what decides correctness at depth: the 129-entry phase table, the barrier / flag epochs over
+The small-shape tests cannot reach what decides correctness at depth: the 129-entry phase table, the barrier / counter epochs over
 hundreds of dependency points per step, ring run-ahead across 32 layers, split-KV attention past position 512 with 32 KV heads
 (cfg4), past 4096 with GQA-4 (cfg5), int8 group-64 tiles at 22 layers near position 2000 (cfg3). A full-depth CPU forward costs
-0.3-0.5 s on the box's cores, so two kinds of check are affordable:
+0.3-0.7 s on the box's cores, so two kinds of check are affordable:
 
-  * greedy:   a short prompt + 16 greedy tokens against the oracle (LlamaModel::predict semantics, model.cpp:148-185);
-  * late:     a synthetic KV history INJECTED into both sides (same bf16-exact values in the oracle's [L][S][kv] cache and in the
-              engine's cache, whatever its layout), then teacher-forced forwards at the late positions: logits per position and
-              the arg-max. Same inputs -> same outputs is the whole parity contract; producing the history with 500-4000 CPU
-              forwards would only burn GPU-box minutes.
+  * head:  a short prompt, then TEACHER-FORCED along the oracle's own greedy stream (LlamaModel::predict, model.cpp:148-185): logits
+           at every position, arg-max where the oracle's margin allows it, and the length of the identical greedy prefix is reported;
+  * late:  a synthetic KV history INJECTED into both sides (the same bf16-exact values in the oracle's [L][S][kv] cache and in the
+           engine's cache, whatever its layout), then teacher-forced forwards at the late positions. Same inputs -> same outputs is
+           the whole parity contract; producing the history with 500-4000 CPU forwards would only burn GPU-box minutes.
 
-Every engine mode that serves the configuration is checked: the default megakernel, the word-based megakernel (the kernel behind
-every N > 1 number) and the per-kernel CUDA-graph path. bf16 KV on both sides (orc_set_kv_bf16), tolerance 5e-3 * max|logit|
-(DESIGN.md "Tolerances": a cache value on a bf16 rounding boundary may round the other way under another summation order), and the
-arg-max must agree wherever the oracle's top-1/top-2 margin exceeds 20x the observed error.
+Why teacher-forced and not "token stream identical": at 32 layers the synthetic gain-4 model amplifies fp32 rounding noise chaotically,
+and the bf16 cache turns it into rounding-boundary flips. The REFERENCE ALGORITHM AGAINST ITSELF shows it: the C restatement built with
+FMA contraction (oracle/_build/liboracle_port_fma.so = what `-O3 -march=x86-64-v3` does to the reference) leaves the strict build's
+greedy stream at the 5th generated token on cfg4 (measured in the dev container: tokens 28505 vs 2143, margin 0.52). So the tolerance
+of these tests is CALIBRATED per position by that yardstick — yard_i = |logits_fma_i - logits_strict_i| / max|logits_strict_i|, both
+teacher-forced on the same tokens and the same injected history: the CUDA path must stay within max(5e-3, 4 * yard_i) of the strict
+oracle, i.e. no further from the reference than a legal re-association of the reference's own arithmetic is (times 4: the statistic is
+one sample per position). Every engine mode that serves the configuration is checked: the default megakernel(s), the word-based
+megakernel (the kernel behind every N > 1 number) and the per-kernel CUDA-graph path. bf16 KV on both sides (orc_set_kv_bf16).
 """
 import os
 
@@ -23,13 +28,17 @@ import pytest
 import torch
 
 from conftest import oracle_shape
-from simplellminference_b200.config import BF16, F32, INT8, PRESETS
+from oracle import loader
+from simplellminference_b200.config import BF16, INT8, PRESETS
 from simplellminference_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
 
 NT = os.cpu_count() or 1
-MODES = {"mega": dict(mega=True), "mega_ll": dict(mega=True, mega_ll=True), "fused_graph": {}}
+MODES = {"mega": dict(mega=True), "mega_v2": dict(mega=True, mega_v2=True), "mega_v2_fuse": dict(mega=True, mega_v2=True, mega_fuse_down=True),
+         "mega_ll": dict(mega=True, mega_ll=True), "fused_graph": {}}
+ALL = ["mega", "mega_v2", "mega_v2_fuse", "mega_ll", "fused_graph"]
+FLOOR, K_YARD = 5e-3, 4.0
 
 
 def _need_ram(gib):
@@ -64,82 +73,110 @@ def _inject_engine(eng, ms, l, k, v):
     torch.cuda.synchronize()
 
 
-def _check_logits(got, want, what):
-    scale = max(1.0, float(np.abs(want).max()))
-    err = float(np.abs(got - want).max())
-    assert err <= 5e-3 * scale, (what, err, scale)
-    srt = np.partition(want, -2)[-2:]
-    if srt[1] - srt[0] >= 20 * err:
-        assert int(np.argmax(got)) == int(np.argmax(want)), (what, "arg-max", err, float(srt[1] - srt[0]))
-    return err / scale
-
-
-def _late_positions(port, ms, wd, n_hist, tokens, modes, seed, group=64):
-    """Inject n_hist positions of history, then teacher-force `tokens` at positions n_hist, n_hist+1, ...; returns {mode: max rel err}."""
+def _oracle_runs(port, ms, wd, seed, group, n_hist, feed):
+    """Strict oracle (and the FMA-contracted yardstick build when the CPU can run it) teacher-forced on `feed(i, strict_logits_so_far)`.
+    Returns (tokens fed, strict logits per position, yardstick per position or None)."""
     blob = port.fill_blob(oracle_shape(ms), seed, wd, group, threads=NT)
-    om = port.model(oracle_shape(ms), blob, threads=NT, kv_bf16=True)
     S, kv = ms.max_len, ms.kv_hidden
-    for l, k, v in _history(ms, n_hist, seed + 1):
-        om.write(2, l * S * kv, k)
-        om.write(3, l * S * kv, v)
-    want = [om.forward(int(t), n_hist + i) for i, t in enumerate(tokens)]
-    om.close()
+    libs = [port]
+    if loader.cpu_supports_v3() and os.path.exists(loader.PORT_FMA_SO):
+        libs.append(loader.Port(loader.PORT_FMA_SO))
+    toks, logits = None, []
+    for lib in libs:
+        om = lib.model(oracle_shape(ms), blob, threads=NT, kv_bf16=True)
+        if n_hist:
+            for l, k, v in _history(ms, n_hist, seed + 1):
+                om.write(2, l * S * kv, k)
+                om.write(3, l * S * kv, v)
+        if toks is None:        # the strict run decides the tokens
+            toks, out, i = [], [], 0
+            while True:
+                t = feed(i, out)
+                if t is None:
+                    break
+                toks.append(int(t))
+                out.append(om.forward(int(t), n_hist + i))
+                i += 1
+            logits.append(out)
+        else:
+            logits.append([om.forward(t, n_hist + i) for i, t in enumerate(toks)])
+        om.close()
     del blob
-    out = {}
+    strict = logits[0]
+    yard = None
+    if len(logits) == 2:
+        yard = [float(np.abs(a - b).max()) / max(1.0, float(np.abs(a).max())) for a, b in zip(strict, logits[1])]
+    return toks, strict, yard
+
+
+def _check_engines(ms, wd, seed, group, n_hist, toks, strict, yard, modes, what):
+    report = {}
     for mode in modes:
         eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=group, **MODES[mode]).load_synthetic(seed)
-        for l, k, v in _history(ms, n_hist, seed + 1):
-            _inject_engine(eng, ms, l, k, v)
-        worst = 0.0
-        for i, t in enumerate(tokens):
+        if n_hist:
+            for l, k, v in _history(ms, n_hist, seed + 1):
+                _inject_engine(eng, ms, l, k, v)
+        errs, same_prefix, still_same = [], 0, True
+        for i, t in enumerate(toks):
             got, nxt = eng.forward(int(t), n_hist + i)
-            worst = max(worst, _check_logits(got, want[i], (mode, eng.mode, n_hist + i)))
+            want = strict[i]
+            scale = max(1.0, float(np.abs(want).max()))
+            err = float(np.abs(got - want).max())
+            errs.append(err / scale)
+            tol = max(FLOOR, K_YARD * yard[i]) if yard is not None else 2e-2
+            assert err <= tol * scale, (what, mode, eng.mode, "position", n_hist + i, "rel err", err / scale, "tol", tol, "yardstick", yard[i] if yard else None)
             assert nxt == int(np.argmax(got))
-        out[mode + ":" + eng.mode] = worst
+            srt = np.partition(want, -2)[-2:]
+            if srt[1] - srt[0] > 2.5 * err:
+                assert nxt == int(np.argmax(want)), (what, mode, "arg-max at position", n_hist + i, err, float(srt[1] - srt[0]))
+            still_same = still_same and nxt == int(np.argmax(want))
+            same_prefix += int(still_same)
+        report[f"{mode}:{eng.mode}"] = dict(max_rel_err=f"{max(errs):.2e}", first=f"{errs[0]:.2e}", argmax_same_prefix=f"{same_prefix}/{len(toks)}")
         eng.close()
-    print("late-position parity", {k: f"{v:.2e}" for k, v in out.items()})
-    return out
+    print(f"\n[{what}] yardstick (reference vs its FMA-contracted build), per position:", None if yard is None else [f"{y:.1e}" for y in yard])
+    for k, v in report.items():
+        print(f"[{what}] {k}: {v}")
+    return report
 
 
-def _greedy(port, ms, wd, prompt, n_total, modes, seed, group=64):
-    blob = port.fill_blob(oracle_shape(ms), seed, wd, group, threads=NT)
-    om = port.model(oracle_shape(ms), blob, threads=NT, kv_bf16=True)
-    want, want_l = om.greedy(prompt, n_total)
-    om.close()
-    del blob
-    for mode in modes:
-        eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=group, **MODES[mode]).load_synthetic(seed)
-        got = eng.greedy(prompt, n_total)
-        assert np.array_equal(got, want), (mode, eng.mode, got, want)
-        _check_logits(eng.buffer("model_pred").cpu().numpy(), want_l, (mode, eng.mode, "last logits"))
-        eng.close()
+def _late(port, ms, wd, n_hist, tokens, modes, seed, what, group=64):
+    toks, strict, yard = _oracle_runs(port, ms, wd, seed, group, n_hist, lambda i, out: tokens[i] if i < len(tokens) else None)
+    return _check_engines(ms, wd, seed, group, n_hist, toks, strict, yard, modes, what)
+
+
+def _head(port, ms, wd, prompt, n_total, modes, seed, what, group=64):
+    def feed(i, out):   # predict's loop: prompt tokens verbatim, then the strict oracle's own arg-max
+        if i >= n_total - 1:
+            return None
+        return prompt[i] if i < len(prompt) else int(np.argmax(out[i - 1]))
+    toks, strict, yard = _oracle_runs(port, ms, wd, seed, group, 0, feed)
+    return _check_engines(ms, wd, seed, group, 0, toks, strict, yard, modes, what)
 
 
 # ---- cfg4: Llama-2-7B-shaped, 32 layers, bf16 weights + bf16 KV (the configuration the metric is quoted on) ---------------------------
-def test_cfg4_llama2_7b_full_depth_greedy(port):
+def test_cfg4_llama2_7b_full_depth_head(port):
     _need_ram(34)
-    _greedy(port, PRESETS["llama2-7b"], BF16, [1, 2, 3], 19, ["mega", "mega_ll", "fused_graph"], 1234)
+    _head(port, PRESETS["llama2-7b"], BF16, [1, 2, 3], 13, ALL, 1234, "cfg4 head")
 
 
 def test_cfg4_llama2_7b_full_depth_positions_512_520(port):
     """Positions 512-520 after a 512-position history: the bench's position range (split-KV over > 512 positions, 32 KV heads)."""
     _need_ram(34)
-    toks = [11, 2222, 13000, 31999, 5, 777, 20481, 9, 1500]
-    _late_positions(port, PRESETS["llama2-7b"], BF16, 512, toks, ["mega", "mega_ll", "fused_graph"], 1234)
+    _late(port, PRESETS["llama2-7b"], BF16, 512, [11, 2222, 13000, 31999, 5, 777, 20481, 9, 1500], ALL, 1234, "cfg4 pos 512-520")
 
 
 # ---- cfg5: Llama-3-8B-shaped, 32 layers, GQA-4, 128K vocabulary, position > 4096 --------------------------------------------------------
 def test_cfg5_llama3_8b_full_depth_past_4096(port):
     _need_ram(38)
-    _late_positions(port, PRESETS["llama3-8b"], BF16, 4200, [7, 100000, 64000, 128255], ["mega", "mega_ll", "fused_graph"], 77)
+    _late(port, PRESETS["llama3-8b"], BF16, 4200, [7, 100000, 64000, 128255], ALL, 77, "cfg5 pos 4200-4203")
 
 
 # ---- cfg3: TinyLlama-1.1B-shaped, 22 layers, int8 group-64 weights (and bf16), bf16 KV, near position 2000 ------------------------------
 @pytest.mark.parametrize("wd", [INT8, BF16])
 def test_cfg3_tinyllama_full_depth_near_2000(port, wd):
-    modes = ["mega", "fused_graph"] if wd == INT8 else ["mega", "mega_ll", "fused_graph"]
-    _late_positions(port, PRESETS["tinyllama-1.1b"], wd, 2000, [3, 31000, 15000, 42, 8191, 2], modes, 5)
+    modes = ["mega", "fused_graph"] if wd == INT8 else ALL
+    _late(port, PRESETS["tinyllama-1.1b"], wd, 2000, [3, 31000, 15000, 42, 8191, 2], modes, 5, f"cfg3 wd={wd} pos 2000-2005")
 
 
-def test_cfg3_tinyllama_full_depth_greedy_int8(port):
-    _greedy(port, PRESETS["tinyllama-1.1b"], INT8, [1, 5, 9], 24, ["mega", "fused_graph"], 5)
+def test_cfg3_tinyllama_full_depth_head_int8(port):
+    _head(port, PRESETS["tinyllama-1.1b"], INT8, [1, 5, 9], 20, ["mega", "fused_graph"], 5, "cfg3 int8 head")
