@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-mega", action="store_true", help="use the per-kernel fused CUDA-graph path instead of the persistent megakernel")
     ap.add_argument("--mega-ll", action="store_true", help="single GPU: the barrier-free {value,epoch}-word megakernel instead of the grid-barrier one")
     ap.add_argument("--mega-fuse-down", action="store_true", help="single GPU, experimental: the megakernel variant with the down projection fused into the gate_up phase (SLLM_ENGINE_MEGA_FUSE_DOWN)")
+    ap.add_argument("--mega-v2", action="store_true", help="single GPU: the megakernel with two grid-wide dependency points per layer (SLLM_ENGINE_MEGA_V2, csrc/megakernel2.cu)")
     ap.add_argument("--nccl", action="store_true", help="tensor parallel: NCCL all-reduce instead of the fused peer-memory one")
     ap.add_argument("--kernel-only", default=None, help="profiling aid: loop one fused kernel kind and exit")
     ap.add_argument("--no-batch", action="store_true", help="skip the secondary figures measured in child processes after the timed regions (batched multi-sequence decode: "
@@ -350,7 +351,7 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
                  graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused), mega_ll=args.mega_ll,
-                 p2p_allreduce=(world > 1 and not args.nccl), mega_fuse_down=(args.mega_fuse_down and world == 1))
+                 p2p_allreduce=(world > 1 and not args.nccl), mega_fuse_down=(args.mega_fuse_down and world == 1), mega_v2=(args.mega_v2 and world == 1))
     eng.load_synthetic(1234)
     if world > 1:
         eng.init_comm(dist) if args.nccl else eng.init_p2p(dist)

@@ -337,6 +337,15 @@ int64_t sllm_batch_total_launches(const sllm_batch* b);
  * host arithmetic only, so that a host sizes n_pages against sllm_device_info's free HBM first; -1 = bad argument. */
 int64_t sllm_batch_arena_bytes(const sllm_shape* shape, int32_t max_seqs, int32_t page_len, int32_t n_pages, int32_t kv_dtype);
 
+/* Calibrated partition of the persistent decode kernels (SLLM_ENGINE_MEGAKERNEL, one GPU, not MEGA_LL). The SMs of a B200 do not all
+ * stream from HBM at the same rate (a stable pattern of about +-5 % per GPU) and every phase of the kernel ends with its slowest CTA.
+ * This call runs `rounds` x 9 decode steps from (token 1, position 0) with the kernel's timeline on, measures every CTA's time per
+ * byte over the big weight phases, and from then on gives each CTA a share of every phase's tile rows in inverse proportion. It
+ * changes WHICH CTA computes a row, never how a row is computed: results are unchanged (bit for bit in the deterministic kernel).
+ * Call it after loading weights and before use: it overwrites the first positions of the KV cache and resets the step state to
+ * (token 0, position 0). sllm_engine_calibration(cta) = the measured relative time per byte (1.0 = mean, 0 = never calibrated). */
+int sllm_engine_calibrate(sllm_engine* e, int32_t rounds);
+float sllm_engine_calibration(const sllm_engine* e, int32_t cta);
 /* Introspection for parity tests and the roofline: named buffers follow the reference's ModelBufferType
  * numbering (include/model/model.h:14-34); returns a device pointer and its element count/dtype. */
 int sllm_engine_buffer(sllm_engine* e, int32_t buffer_id, void** dev_ptr, int64_t* n_elems, int32_t* dtype);

@@ -107,6 +107,8 @@ SIGNATURES = {
     "sllm_engine_kernel_bytes": (_L, [_P, _I, _I]),
     "sllm_engine_kv_layout": (_I, [_P]),
     "sllm_engine_mode": (C.c_char_p, [_P]),
+    "sllm_engine_calibrate": (C.c_int, [_P, _I]),
+    "sllm_engine_calibration": (C.c_float, [_P, _I]),
     "sllm_engine_step_launches": (_I, [_P]),
     "sllm_engine_total_launches": (_L, [_P]),
 }

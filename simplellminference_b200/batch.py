@@ -98,6 +98,7 @@ class BatchDecoder:
         _lib.check(self.lib.sllm_batch_create(engine.h, max_seqs, page_len, n_pages, kv_dtype, C.byref(h)))
         self.h = h
         self.max_seqs, self.page_len, self.n_pages, self.kv_dtype = max_seqs, page_len, n_pages, kv_dtype
+        self.max_len = engine.shape.max_len   # positions one sequence can reach (sllm_batch_step refuses to go past it)
 
     def add(self, prompt) -> int:
         prompt = np.ascontiguousarray(prompt, dtype=np.int32)

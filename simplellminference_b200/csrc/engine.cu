@@ -13,7 +13,9 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "engine_view.cuh"
@@ -60,6 +62,9 @@ struct sllm_engine {
     float* v2_bufs = nullptr;     // xbuf[2], hbuf[2]: d floats each, touched by that kernel only (zero-on-entry invariants)
     unsigned* v2_flags = nullptr; // per-kv-head dependency counters
     Mega2Params mega2_params{};
+    std::vector<PhaseDesc> phases_host;   // what phases_dev holds (sllm_engine_calibrate rewrites the share tables in it)
+    uint32_t* cum_dev = nullptr;           // share tables of the calibrated partition: up to kCumTables x (grid + 1) words
+    std::vector<double> calib_tau;         // measured relative time per byte of every CTA (empty = never calibrated)
     void* wdown_t = nullptr;      // its transposed per-layer matrices (megakernel.cuh "PH_DOWN_T"); wdown stays for the batched prefill
     MegaLLPlan ll_plan{};
     MegaLLParams ll_params{};
@@ -122,6 +127,7 @@ struct sllm_engine {
     int64_t pf_gemm_launches = 0;
 };
 
+constexpr int kCumTables = 8;
 // ------------------------------------------------------------------------------------------- helpers ---
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static size_t wbytes(int dtype, int64_t n) { return dtype == SLLM_F32 ? 4 * (size_t)n : dtype == SLLM_BF16 ? 2 * (size_t)n : (size_t)n; }
@@ -188,6 +194,7 @@ static void layout(sllm_engine* e) {
     e->wo_t = e->mega2 ? carve<void>(e, (size_t)L * mega2_wot_bytes(e->d, e->hd, e->H_loc, e->KVH_loc, e->cfg.w_dtype)) : nullptr;
     e->v2_bufs = e->mega2 ? carve<float>(e, 4 * (size_t)4 * d) : nullptr;
     e->v2_flags = e->mega2 ? carve<unsigned>(e, (size_t)2 * e->KVH_loc * 128) : nullptr;
+    e->cum_dev = (e->mega && !e->mega_ll) ? carve<uint32_t>(e, sizeof(uint32_t) * (size_t)kCumTables * (size_t)(e->mega_plan_.grid + 1)) : nullptr;
 }
 
 static int count_launch(sllm_engine* e) {
@@ -480,11 +487,15 @@ static int build_graph(sllm_engine* e) {
     return SLLM_OK;
 }
 
-static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
+// *done = steps actually enqueued (the host shadow of the position must follow the device, also when a launch fails half way)
+static int enqueue_steps(sllm_engine* e, int n, int host_pos, int* done) {
+    *done = 0;
     SLLM_REQUIRE(e->weights_loaded, SLLM_ESTATE, "weights not loaded");
     if (!e->fused) {
-        for (int i = 0; i < n; ++i)
+        for (int i = 0; i < n; ++i) {
             if (int rc = enqueue_unfused_step(e, host_pos + i)) return rc;
+            ++*done;
+        }
         return SLLM_OK;
     }
     if (e->mega) {
@@ -495,20 +506,25 @@ static int enqueue_steps(sllm_engine* e, int n, int host_pos) {
                                       : mega_launch(e->mega_params, e->H_loc / e->KVH_loc, e->mega_plan_.grid, e->mega_plan_.smem, e->stream, e->mega_fuse);
             if (rc) return rc;
             e->total_launches++;
+            ++*done;
         }
         return SLLM_OK;
     }
     if (e->use_graph) {
         SLLM_REQUIRE(e->graph_exec, SLLM_ESTATE, "decode graph not built (weights or communicator missing)");
-        for (int i = 0; i < n; ++i) SLLM_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
-        e->total_launches += (int64_t)n * e->step_launches;
-        g_launches += (int64_t)n * e->step_launches;
+        for (int i = 0; i < n; ++i) {
+            SLLM_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+            e->total_launches += e->step_launches;
+            g_launches += e->step_launches;
+            ++*done;
+        }
         return SLLM_OK;
     }
     for (int i = 0; i < n; ++i) {
         const int64_t t0 = e->total_launches;
-        if (int rc = enqueue_fused_dispatch(e)) return rc;
+        if (int rc = enqueue_fused_dispatch(e)) return rc;   // a step that failed between its kernels leaves the device state undefined: the caller must set_state again
         e->step_launches = (int)(e->total_launches - t0);
+        ++*done;
     }
     return SLLM_OK;
 }
@@ -656,6 +672,7 @@ static int setup_mega(sllm_engine* e) {
     }
     SLLM_CUDA(cudaMemcpyAsync(e->phases_dev, host.data(), sizeof(PhaseDesc) * host.size(), cudaMemcpyHostToDevice, e->stream));
     SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    e->phases_host = host;
     MegaParams& p = e->mega_params;
     p.phases = e->phases_dev;
     p.d = e->d; p.hd = e->hd; p.L = e->L; p.S = e->S; p.V = e->V; p.V_loc = e->V_loc; p.v0 = e->v0; p.q_loc = e->q_loc; p.kv_loc = e->kv_loc;
@@ -943,8 +960,9 @@ int sllm_engine_enqueue_steps(sllm_engine* e, int32_t n_steps) {
     SLLM_REQUIRE(e && n_steps >= 0, SLLM_EINVAL, "bad argument");
     SLLM_REQUIRE(e->tp == 1 || e->comm || e->p2p_ready, SLLM_ESTATE, "tensor-parallel engine without a communicator");
     SLLM_REQUIRE(e->h_state[7] + n_steps <= e->S, SLLM_EINVAL, "%d steps from position %d overrun max_len %d", n_steps, e->h_state[7], e->S);
-    int rc = enqueue_steps(e, n_steps, e->h_state[7]);
-    e->h_state[7] += n_steps;
+    int done = 0;
+    const int rc = enqueue_steps(e, n_steps, e->h_state[7], &done);
+    e->h_state[7] += done;   // the host shadow follows what was really enqueued, also when a launch failed half way
     return rc;
 }
 
@@ -966,7 +984,8 @@ int sllm_engine_forward(sllm_engine* e, int32_t token, int32_t pos, float* logit
     SLLM_REQUIRE(token >= 0 && token < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", token, e->V);
     SLLM_CUDA(cudaMemcpyAsync(e->state, e->h_state, 16, cudaMemcpyHostToDevice, e->stream));
     e->h_state[7] = pos;
-    if (int rc = enqueue_steps(e, 1, pos)) return rc;
+    int done = 0;
+    if (int rc = enqueue_steps(e, 1, pos, &done)) return rc;
     e->h_state[7] = pos + 1;
     if (logits_host) SLLM_CUDA(cudaMemcpyAsync(logits_host, e->logits, sizeof(float) * (size_t)e->V_loc, cudaMemcpyDeviceToHost, e->stream));
     if (next_token_host) SLLM_CUDA(cudaMemcpyAsync(e->h_state + 4, &e->state->next, 4, cudaMemcpyDeviceToHost, e->stream));
@@ -984,6 +1003,119 @@ int sllm_engine_greedy(sllm_engine* e, const int32_t* prompt, int32_t n_prompt, 
     e->h_state[7] = 0;
     if (int rc = sllm_engine_enqueue_steps(e, n_total - 1)) return rc;
     return sllm_engine_read_tokens(e, tokens_out, n_total - 1);
+}
+
+// ---- calibrated partition ---------------------------------------------------------------------------------------
+// SMs do not stream from HBM at the same rate: a stable pattern of about +-5 % per GPU (position on the dies / distance to the memory
+// partitions), and every phase of the persistent kernel ends with the slowest CTA. sllm_engine_calibrate times a few real steps with
+// the kernel's own %globaltimer stamps, takes every CTA's time per byte over the big weight phases, and gives each CTA a share of
+// every phase's tile rows in inverse proportion — an integer allocation that minimises the latest finisher, contiguous per CTA.
+static int items_of(const sllm_engine* e, const PhaseDesc& ph) {   // the n the kernels pass to cta_cut for this phase (0 = not partitioned by it)
+    if (ph.kind == PH_WO_T) return 0;
+    if (e->mega_fuse && ph.kind == PH_GATEUP) return ph.nunits / kFuseJT;
+    return ph.ntr;
+}
+static std::vector<int> host_cuts(const std::vector<uint32_t>* cum, int n, int ncta) {   // boundaries b[0..ncta] exactly as cta_cut computes them
+    std::vector<int> b((size_t)ncta + 1);
+    for (int c = 0; c <= ncta; ++c) b[c] = cum ? (int)(((uint64_t)n * (*cum)[c]) >> 24) : (int)(((int64_t)n * c) / ncta);
+    return b;
+}
+static std::vector<uint32_t> build_cum(int n, const std::vector<double>& tau) {
+    const int ncta = (int)tau.size();
+    double lo = 0.0, hi = 0.0;
+    for (double t : tau) hi = std::max(hi, t);
+    hi *= (double)n + 1.0;
+    auto total = [&](double T) { int64_t s = 0; for (double t : tau) s += (int64_t)std::floor(T / t); return s; };
+    for (int it = 0; it < 80; ++it) { const double mid = 0.5 * (lo + hi); (total(mid) >= n ? hi : lo) = mid; }
+    std::vector<int> cnt((size_t)ncta);
+    int64_t sum = 0;
+    for (int c = 0; c < ncta; ++c) { cnt[c] = (int)std::floor(hi / tau[c]); sum += cnt[c]; }
+    while (sum > n) {   // give back the surplus where it hurts most
+        int worst = 0;
+        for (int c = 1; c < ncta; ++c) if (cnt[c] * tau[c] > cnt[worst] * tau[worst]) worst = c;
+        cnt[worst]--; sum--;
+    }
+    std::vector<uint32_t> cum((size_t)ncta + 1);
+    int64_t b = 0;
+    for (int c = 0; c < ncta; ++c) { cum[c] = (uint32_t)((b * (1ll << 24) + n - 1) / n); b += cnt[c]; }
+    cum[ncta] = 1u << 24;
+    return cum;
+}
+
+extern "C" int sllm_engine_calibrate(sllm_engine* e, int32_t rounds) {
+    SLLM_REQUIRE(e && e->weights_loaded, SLLM_ESTATE, "calibrate: engine without weights");
+    SLLM_REQUIRE(e->mega && !e->mega_ll && e->tp == 1, SLLM_ENOTSUP, "calibrate: only the single-GPU grid-barrier megakernels partition their phases by a share table");
+    if (rounds < 1) rounds = 2;
+    const int ncta = e->mega_plan_.grid, L = e->L, nev = 5 * L + 1;
+    SLLM_REQUIRE(nev <= 512 && e->S >= 24, SLLM_ENOTSUP, "calibrate: needs at most 102 layers and max_len >= 24");
+    const size_t tb = (size_t)ncta * 512 * 8 * 8;
+    if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, tb)); SLLM_CUDA(cudaMemset(e->trace, 0, tb)); }
+    e->mega_params.trace = e->trace; e->mega2_params.m.trace = e->trace;
+    std::vector<unsigned long long> tr(tb / 8);
+    std::map<int, std::vector<uint32_t>> tables;   // by item count
+    int rc = SLLM_OK;
+    for (int round = 0; round < rounds && rc == SLLM_OK; ++round) {
+        std::vector<double> T((size_t)ncta, 0.0), B((size_t)ncta, 0.0);
+        if ((rc = set_state(e, 1, 0, 0))) break;
+        e->h_state[7] = 0;
+        int done = 0;
+        if ((rc = enqueue_steps(e, 3, 0, &done))) break;
+        for (int step = 0; step < 6 && rc == SLLM_OK; ++step) {
+            if ((rc = enqueue_steps(e, 1, 3 + step, &done))) break;
+            SLLM_CUDA(cudaMemcpyAsync(tr.data(), e->trace, tb, cudaMemcpyDeviceToHost, e->stream));
+            SLLM_CUDA(cudaStreamSynchronize(e->stream));
+            for (size_t wp = 0; wp < e->phases_host.size(); ++wp) {
+                const PhaseDesc& ph = e->phases_host[wp];
+                const int n = items_of(e, ph);
+                if (n <= 0 || ph.kind == PH_WO) continue;          // the big streams: qkv, gate_up, down, classifier
+                const int ev = (int)wp + ph.layer + ((ph.kind != PH_QKV && ph.kind != PH_CLS) ? 1 : 0);
+                const auto it = tables.find(n);
+                const std::vector<int> cut = host_cuts(it == tables.end() ? nullptr : &it->second, n, ncta);
+                for (int c = 0; c < ncta; ++c) {
+                    const unsigned long long t1 = tr[((size_t)c * 512 + ev) * 8 + 1], t3 = tr[((size_t)c * 512 + ev) * 8 + 3];
+                    if (t3 > t1 && cut[c + 1] > cut[c]) { T[c] += (double)(t3 - t1); B[c] += (double)(cut[c + 1] - cut[c]) / (double)n * (double)ph.ntr * ph.KS * ph.tile_bytes; }
+                }
+            }
+        }
+        if (rc) break;
+        std::vector<double> tau((size_t)ncta, 1.0);
+        double mean = 0.0;
+        int cnt = 0;
+        for (int c = 0; c < ncta; ++c) if (B[c] > 0.0) { tau[c] = T[c] / B[c]; mean += tau[c]; cnt++; }
+        SLLM_REQUIRE(cnt == ncta && mean > 0.0, SLLM_ESTATE, "calibrate: the timeline of %d of %d CTAs is empty", ncta - cnt, ncta);
+        mean /= cnt;
+        for (double& t : tau) t = std::min(1.25, std::max(0.8, t / mean));
+        e->calib_tau = tau;
+        // one table per distinct item count, then every phase points at its table
+        tables.clear();
+        std::vector<uint32_t> flat;
+        std::map<int, size_t> slot;
+        for (const PhaseDesc& ph : e->phases_host) {
+            const int n = items_of(e, ph);
+            if (n <= 0 || slot.count(n) || (int)slot.size() >= kCumTables) continue;
+            slot[n] = slot.size();
+            tables[n] = build_cum(n, tau);
+            flat.insert(flat.end(), tables[n].begin(), tables[n].end());
+        }
+        SLLM_CUDA(cudaMemcpyAsync(e->cum_dev, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        for (PhaseDesc& ph : e->phases_host) {
+            const int n = items_of(e, ph);
+            ph.cum = (n > 0 && slot.count(n)) ? e->cum_dev + slot[n] * (size_t)(ncta + 1) : nullptr;
+        }
+        SLLM_CUDA(cudaMemcpyAsync(e->phases_dev, e->phases_host.data(), sizeof(PhaseDesc) * e->phases_host.size(), cudaMemcpyHostToDevice, e->stream));
+        SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    e->mega_params.trace = nullptr; e->mega2_params.m.trace = nullptr;
+    SLLM_CUDA(cudaMemsetAsync(e->history_dev, 0, sizeof(int32_t) * (size_t)e->S, e->stream));
+    if (int rc2 = set_state(e, 0, 0, 0)) return rc2;
+    e->h_state[7] = 0;
+    SLLM_CUDA(cudaStreamSynchronize(e->stream));
+    return rc;
+}
+
+/* the measured relative time per byte of CTA `cta` (1.0 = the mean; 0 when the engine was never calibrated) */
+extern "C" float sllm_engine_calibration(const sllm_engine* e, int32_t cta) {
+    return (e && cta >= 0 && (size_t)cta < e->calib_tau.size()) ? (float)e->calib_tau[(size_t)cta] : 0.0f;
 }
 
 // ---- batched prefill ------------------------------------------------------------------------------------------

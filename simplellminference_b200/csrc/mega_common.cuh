@@ -134,9 +134,12 @@ __device__ __forceinline__ void unit_rows(const MegaParams& p, const PhaseDesc& 
 }
 
 // balanced split of a phase's tile rows over the CTAs
+__device__ __forceinline__ int cta_cut(const uint32_t* cum, int n, int cta, int ncta) {   // first of CTA `cta`'s share of n items
+    return cum ? (int)(((uint64_t)n * cum[cta]) >> 24) : (int)(((int64_t)n * cta) / ncta);
+}
 __device__ __forceinline__ void cta_tiles(const PhaseDesc& ph, int cta, int ncta, int& g0, int& g1) {
-    g0 = (int)(((int64_t)ph.ntr * cta) / ncta);
-    g1 = (int)(((int64_t)ph.ntr * (cta + 1)) / ncta);
+    g0 = cta_cut(ph.cum, ph.ntr, cta, ncta);
+    g1 = cta_cut(ph.cum, ph.ntr, cta + 1, ncta);
 }
 
 // the split a phase's tile rows get in the kernel that fuses the down projection into the gate_up phase: gate_up follows the split
@@ -146,8 +149,8 @@ __device__ __forceinline__ void phase_tiles(const PhaseDesc& ph, int cta, int nc
     if (FUSE && ph.kind == PH_GATEUP) {
         const int per = kFuseJT / (ph.R >> 1);        // gate_up tile rows (R / 2 units each) per down tile row
         const int ntr_e = ph.nunits / kFuseJT;
-        g0 = (int)(((int64_t)ntr_e * cta) / ncta) * per;
-        g1 = (int)(((int64_t)ntr_e * (cta + 1)) / ncta) * per;
+        g0 = cta_cut(ph.cum, ntr_e, cta, ncta) * per;
+        g1 = cta_cut(ph.cum, ntr_e, cta + 1, ncta) * per;
     } else {
         cta_tiles(ph, cta, ncta, g0, g1);
     }
@@ -159,6 +162,11 @@ __device__ __forceinline__ void down_t_rows(int g0, int g1, int rg, int RG, int&
     a = g0 + (cnt * rg) / RG;
     b = g0 + (cnt * (rg + 1)) / RG;
 }
+
+// (An L2 look-ahead of the weight stream — a second cursor per warp issuing cp.async.bulk.prefetch.L2 for the tiles 2-16 slots ahead of
+// the ring, so that HBM keeps streaming through a dependency stall — was built and measured in round 2 and removed: it is SLOWER at
+// every depth (2 tiles / 18 MB ahead: -5 %, 8 tiles / 74 MB: -30 %; profiles/r02_l2_lookahead_sweep.jsonl), as the round-1 attempts
+// at phase boundaries were. The bulk prefetches compete with the demand copies of the two-slot rings instead of running under them.)
 
 // acc[e] += w_e * s for the E weights of one 16-byte chunk (fp32 / bf16 storage)
 template <int WD>

@@ -736,6 +736,7 @@ static void fill_desc(PhaseDesc& ds, const void* W, int rows, int cols, int kind
     ds.ntr = g.ntr;
     ds.tile_bytes = g.tile_bytes;
     ds.srow = g.srow;
+    ds.cum = nullptr;
 }
 
 // can the megakernel run this shape? (everything else keeps using the per-kernel fused path)
@@ -906,6 +907,7 @@ void mega_fill_down_t(PhaseDesc& ds, const void* Wt, int d, int I_loc, int layer
     ds.ntr = I_loc / kFuseJT;
     ds.tile_bytes = kFuseJT * 512;
     ds.srow = 0;
+    ds.cum = nullptr;
 }
 
 template <class T>

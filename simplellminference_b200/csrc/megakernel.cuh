@@ -23,6 +23,10 @@ struct PhaseDesc {       // one weight phase, built on the host
     int32_t ntr;         // tile rows = ceil(2*nunits / R)
     int32_t tile_bytes;  // R * (SC * 16 + srow)
     int32_t srow;        // int8 only: bytes of one row's group scales inside a tile (SC/4 fp32 scales padded to 16 bytes), else 0
+    const uint32_t* cum; // optional [grid + 1] cumulative shares of the CTAs in 2^-24 units (cum[0] = 0, cum[grid] = 2^24): CTA c takes tile
+                         // rows [ntr * cum[c], ntr * cum[c + 1]) instead of an equal cut. SMs do not all stream from HBM at the same rate
+                         // (a stable +-5 % pattern per GPU, profiles/r02_mega_trace_v1.txt) and every phase ends with the slowest one:
+                         // sllm_engine_calibrate measures the pattern and sizes the shares by it. nullptr = equal shares.
 };
 
 // geometry of a [rows][cols] matrix in the tiled layout

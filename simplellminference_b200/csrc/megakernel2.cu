@@ -532,6 +532,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
         const int cpl = (nsc + 31) >> 5;
         float best_v = -INFINITY;
         int best_i = 0x7fffffff;
+        // what the epilogue of this thread's unit (first round: unit u0 + tid) needs from global memory, requested BEFORE the stream so
+        // that its latency is not exposed between the last tile and the dependency point: RoPE table entries / the residual h
+        float pre0 = 0.f, pre1 = 0.f;
+        if (tid < min(n, kRoundUnits)) {
+            const int u = u0 + tid;
+            if (ph.kind == PH_QKV) {
+                if (u < ((p.q_loc + p.kv_loc) >> 1)) {
+                    const int j = u % half;
+                    pre0 = __ldg(p.sin_t + (size_t)pos * half + j);
+                    pre1 = __ldg(p.cos_t + (size_t)pos * half + j);
+                }
+            } else if (ph.kind == PH_DOWN) {
+                pre0 = __ldcg(hb + 2 * u);
+                if (2 * u + 1 < ph.nrows) pre1 = __ldcg(hb + 2 * u + 1);
+            }
+        }
 
 #pragma unroll 1
         for (int rbase = 0; rbase < n || rbase == 0; rbase += kRoundUnits) {
@@ -613,7 +629,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                     };
                     if (u < rope_units) {
                         const int head = u / half, j = u - head * half;
-                        const float fci = p.sin_t[(size_t)pos * half + j], fcr = p.cos_t[(size_t)pos * half + j];
+                        const float fci = rbase == 0 ? pre0 : p.sin_t[(size_t)pos * half + j], fcr = rbase == 0 ? pre1 : p.cos_t[(size_t)pos * half + j];
                         const float o0 = s0 * fcr - s1 * fci, o1 = s1 * fcr + s0 * fci;   // rope_kernel.cpp:36-37
                         const int r0 = head * p.hd + j;
                         if (r0 < p.q_loc) { p.q[r0] = o0; p.q[r0 + half] = o1; }
@@ -629,8 +645,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                     if constexpr (FUSE) xs[rbase + t] = sv;
                 } else if (ph.kind == PH_DOWN) {
                     const int r = 2 * u;
-                    x_out[r] = s0 + __ldcg(hb + r);                           // add_kernel.cpp:10-13
-                    if (r + 1 < ph.nrows) x_out[r + 1] = s1 + __ldcg(hb + r + 1);
+                    x_out[r] = s0 + (rbase == 0 ? pre0 : __ldcg(hb + r));     // add_kernel.cpp:10-13
+                    if (r + 1 < ph.nrows) x_out[r + 1] = s1 + (rbase == 0 ? pre1 : __ldcg(hb + r + 1));
                 } else {
                     const int r = 2 * u;
                     p.logits[r] = s0;
@@ -901,6 +917,7 @@ void mega2_fill_wot(PhaseDesc& ds, const void* W, int d, int hd, int H_loc, int 
     ds.ntr = g.ntr;
     ds.tile_bytes = kSlotBytes;
     ds.srow = 0;
+    ds.cum = nullptr;
 }
 
 // one thread per 16-byte chunk of the destination

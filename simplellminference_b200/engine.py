@@ -48,6 +48,22 @@ class Engine:
         _lib.check(self.lib.sllm_engine_load_blob_f32(self.h, blob.ctypes.data, blob.size))
         return self
 
+    def calibrate(self, rounds: int = 2) -> "Engine":
+        """Size every CTA's share of the persistent kernel's phases by its measured HBM streaming rate (sllm_engine_calibrate).
+        Call after loading weights and before use (it runs a few decode steps from position 0 and resets the step state)."""
+        _lib.check(self.lib.sllm_engine_calibrate(self.h, rounds))
+        return self
+
+    def calibration(self) -> np.ndarray:
+        """Relative time per byte of every CTA as last measured (1.0 = mean); empty if never calibrated."""
+        out = []
+        while True:
+            v = float(self.lib.sllm_engine_calibration(self.h, len(out)))
+            if v == 0.0:
+                break
+            out.append(v)
+        return np.asarray(out, dtype=np.float32)
+
     # -- tensor parallel bootstrap (torch.distributed is only the messenger of the 128-byte NCCL id) --
     def init_comm(self, dist=None) -> "Engine":
         import torch.distributed as td

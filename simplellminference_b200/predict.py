@@ -5,10 +5,14 @@ token by token, then feeds back the arg-max and prints each piece — and never 
 Here:
   * `SPELayer` keeps the reference's three calls (encode / decode / GetVocabularySize) over the SAME third-party library
     (the `sentencepiece` Python package instead of the C++ one); nothing of the tokenizer is re-implemented;
-  * `predict` runs the prompt through the engine — one batched tensor-core pass where the engine supports it, else token by token —
-    and generates in chunks of device-resident steps (one host synchronisation per chunk), optionally STOPPING at an EOS id
-    (additive: `eos_id=None` is the reference's behaviour) and streaming decoded text to a callback like the reference's std::cout.
-Token ids, not text, are what the parity tests compare; this module adds no arithmetic to the path.
+  * `predict` feeds the prompt token by token through the decode step, exactly as the reference does (model.cpp:157-166: fp32
+    activations, the parity path), and generates in chunks of device-resident steps (one host synchronisation per chunk), optionally
+    STOPPING at an EOS id (additive: `eos_id=None` is the reference's behaviour) and streaming decoded text to a callback like the
+    reference's std::cout. `batched_prefill=True` (opt-in) runs the prompt as ONE tensor-core pass instead (sllm_engine_prefill):
+    ~200x faster on a 512-token prompt, but the operands of its GEMMs are rounded to bf16, so its KV rows and logits agree with the
+    reference within the prefill tolerance (DESIGN.md "Tolerances"), not bit for bit — token identity with the reference is only
+    contracted for the default.
+Token ids, not text, are what the parity tests compare; with the default arguments this module adds no arithmetic to the path.
 """
 from __future__ import annotations
 
@@ -67,7 +71,7 @@ def sample_ids(engine, prompt_ids, max_length: int, temperature: float = 1.0, to
     return np.asarray(out, dtype=np.int32)
 
 
-def predict_ids(engine, prompt_ids, max_length: int, eos_id: Optional[int] = None, chunk: int = 16, batched_prefill: bool = True,
+def predict_ids(engine, prompt_ids, max_length: int, eos_id: Optional[int] = None, chunk: int = 16, batched_prefill: bool = False,
                 on_tokens: Optional[Callable[[np.ndarray], None]] = None) -> np.ndarray:
     """Greedy loop of LlamaModel::predict on token ids. Returns the tokens that follow prompt[0] (prompt echo, then generated
     tokens) — at most max_length of them, like the reference; fewer if eos_id is given and generated (the EOS is the last token).

@@ -40,7 +40,7 @@ class SchedulerStats:
 
 class ContinuousBatcher:
     """``decoder``: a ``BatchDecoder`` (or anything with its add / step / tokens / remove / position / free_pages /
-    max_seqs / page_len interface). Not thread-safe: one host thread drives a decoder, like the reference's model."""
+    max_seqs / page_len / n_pages / max_len interface). Not thread-safe: one host thread drives a decoder, like the reference's model."""
 
     def __init__(self, decoder, eos_id: int | None = None, chunk: int = 8):
         if chunk < 1:
@@ -62,6 +62,11 @@ class ContinuousBatcher:
         total = int(prompt.size) + int(max_new_tokens) - 1   # steps: positions 0 .. total-1 (the last prompt token's step yields the first new one)
         if self._pages_for(total) > self._pool_pages():
             raise ValueError(f"request of {total} positions can never fit the page pool")
+        max_len = getattr(self.dec, "max_len", None)
+        if max_len is not None and total > max_len:
+            # refused HERE: admitted, it would make sllm_batch_step fail in the middle of a chunk ("cannot take N more steps") and
+            # strand every other live request with its slots and pages held
+            raise ValueError(f"request of {total} positions exceeds the decoder's max_len {max_len}")
         r = _Request(self._next_id, prompt, total, sampling)
         self._next_id += 1
         self.waiting.append(r)

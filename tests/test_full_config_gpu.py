@@ -14,11 +14,13 @@ hundreds of dependency points per step, ring run-ahead across 32 layers, split-K
 Why teacher-forced and not "token stream identical": at 32 layers the synthetic gain-4 model amplifies fp32 rounding noise chaotically,
 and the bf16 cache turns it into rounding-boundary flips. The REFERENCE ALGORITHM AGAINST ITSELF shows it: the C restatement built with
 FMA contraction (oracle/_build/liboracle_port_fma.so = what `-O3 -march=x86-64-v3` does to the reference) leaves the strict build's
-greedy stream at the 5th generated token on cfg4 (measured in the dev container: tokens 28505 vs 2143, margin 0.52). So the tolerance
-of these tests is CALIBRATED per position by that yardstick — yard_i = |logits_fma_i - logits_strict_i| / max|logits_strict_i|, both
-teacher-forced on the same tokens and the same injected history: the CUDA path must stay within max(5e-3, 4 * yard_i) of the strict
-oracle, i.e. no further from the reference than a legal re-association of the reference's own arithmetic is (times 4: the statistic is
-one sample per position). Every engine mode that serves the configuration is checked: the default megakernel(s), the word-based
+greedy stream at the 5th generated token on cfg4 (measured in the dev container: tokens 28505 vs 2143, margin 0.52). So (1) every position
+is checked on IDENTICAL inputs: tokens are teacher-forced and so is the cache — after each forward the strict oracle's K/V rows of that
+position replace the ones the engine (or the yardstick build) wrote, so nothing compounds from position to position; and (2) the
+tolerance is CALIBRATED per position by the yardstick yard_i = |logits_fma_i - logits_strict_i| / max|logits_strict_i|: the CUDA path
+must stay within max(5e-3, 4 * yard_i) of the strict oracle, i.e. no further from the reference than a legal re-association of the
+reference's own arithmetic is (times 4: the statistic is one sample per position; measured yard_i ~ 1e-2 at 32 layers). The K row
+the engine writes for layer 0 (no depth amplification) must match the oracle's to a bf16 ulp. Every engine mode that serves the configuration is checked: the default megakernel(s), the word-based
 megakernel (the kernel behind every N > 1 number) and the per-kernel CUDA-graph path. bf16 KV on both sides (orc_set_kv_bf16).
 """
 import os
@@ -73,75 +75,108 @@ def _inject_engine(eng, ms, l, k, v):
     torch.cuda.synchronize()
 
 
+def _rows_at(om, ms, pos):
+    """The oracle's K and V cache rows of every layer at one position: ([L][kv], [L][kv])."""
+    S, kv = ms.max_len, ms.kv_hidden
+    k = np.stack([om.read(2, (l * S + pos) * kv, kv) for l in range(ms.layers)])
+    v = np.stack([om.read(3, (l * S + pos) * kv, kv) for l in range(ms.layers)])
+    return k, v
+
+
+def _put_rows_oracle(om, ms, pos, k, v):
+    S, kv = ms.max_len, ms.kv_hidden
+    for l in range(ms.layers):
+        om.write(2, (l * S + pos) * kv, k[l])
+        om.write(3, (l * S + pos) * kv, v[l])
+
+
+def _put_rows_engine(eng, ms, pos, k, v):
+    for name, rows in (("key_cache", k), ("value_cache", v)):
+        buf = eng.buffer(name)
+        src = torch.from_numpy(rows).cuda().to(buf.dtype)
+        if eng.lib.sllm_engine_kv_layout(eng.h) == 1:   # head-major [L][KVH][S][hd]
+            buf.view(ms.layers, ms.kv_heads, ms.max_len, ms.head_dim)[:, :, pos, :] = src.view(ms.layers, ms.kv_heads, ms.head_dim)
+        else:
+            buf.view(ms.layers, ms.max_len, ms.kv_hidden)[:, pos, :] = src
+    torch.cuda.synchronize()
+
+
 def _oracle_runs(port, ms, wd, seed, group, n_hist, feed):
-    """Strict oracle (and the FMA-contracted yardstick build when the CPU can run it) teacher-forced on `feed(i, strict_logits_so_far)`.
-    Returns (tokens fed, strict logits per position, yardstick per position or None)."""
+    """Strict oracle teacher-forced on `feed(i, strict_logits_so_far)`; then the FMA-contracted yardstick build (when the CPU can run
+    it) on the same tokens AND the strict run's cache rows (so every position sees identical inputs on both sides).
+    Returns (tokens fed, strict logits per position, strict K/V rows per position, yardstick per position or None)."""
     blob = port.fill_blob(oracle_shape(ms), seed, wd, group, threads=NT)
     S, kv = ms.max_len, ms.kv_hidden
-    libs = [port]
-    if loader.cpu_supports_v3() and os.path.exists(loader.PORT_FMA_SO):
-        libs.append(loader.Port(loader.PORT_FMA_SO))
-    toks, logits = None, []
-    for lib in libs:
+
+    def model(lib):
         om = lib.model(oracle_shape(ms), blob, threads=NT, kv_bf16=True)
         if n_hist:
             for l, k, v in _history(ms, n_hist, seed + 1):
                 om.write(2, l * S * kv, k)
                 om.write(3, l * S * kv, v)
-        if toks is None:        # the strict run decides the tokens
-            toks, out, i = [], [], 0
-            while True:
-                t = feed(i, out)
-                if t is None:
-                    break
-                toks.append(int(t))
-                out.append(om.forward(int(t), n_hist + i))
-                i += 1
-            logits.append(out)
-        else:
-            logits.append([om.forward(t, n_hist + i) for i, t in enumerate(toks)])
+        return om
+
+    om = model(port)
+    toks, strict, rows, i = [], [], [], 0
+    while True:
+        t = feed(i, strict)
+        if t is None:
+            break
+        toks.append(int(t))
+        strict.append(om.forward(int(t), n_hist + i))
+        rows.append(_rows_at(om, ms, n_hist + i))
+        i += 1
+    om.close()
+    yard = None
+    if loader.cpu_supports_v3() and os.path.exists(loader.PORT_FMA_SO):
+        om = model(loader.Port(loader.PORT_FMA_SO))
+        yard = []
+        for i, t in enumerate(toks):
+            if i:
+                _put_rows_oracle(om, ms, n_hist + i - 1, *rows[i - 1])
+            lg = om.forward(t, n_hist + i)
+            yard.append(float(np.abs(lg - strict[i]).max()) / max(1.0, float(np.abs(strict[i]).max())))
         om.close()
     del blob
-    strict = logits[0]
-    yard = None
-    if len(logits) == 2:
-        yard = [float(np.abs(a - b).max()) / max(1.0, float(np.abs(a).max())) for a, b in zip(strict, logits[1])]
-    return toks, strict, yard
+    return toks, strict, rows, yard
 
 
-def _check_engines(ms, wd, seed, group, n_hist, toks, strict, yard, modes, what):
+def _check_engines(ms, wd, seed, group, n_hist, toks, strict, rows, yard, modes, what):
     report = {}
     for mode in modes:
         eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=group, **MODES[mode]).load_synthetic(seed)
         if n_hist:
             for l, k, v in _history(ms, n_hist, seed + 1):
                 _inject_engine(eng, ms, l, k, v)
-        errs, same_prefix, still_same = [], 0, True
+        errs, kerrs = [], []
         for i, t in enumerate(toks):
             got, nxt = eng.forward(int(t), n_hist + i)
             want = strict[i]
             scale = max(1.0, float(np.abs(want).max()))
             err = float(np.abs(got - want).max())
             errs.append(err / scale)
-            tol = max(FLOOR, K_YARD * yard[i]) if yard is not None else 2e-2
+            tol = max(FLOOR, K_YARD * yard[i]) if yard is not None else 5e-2
             assert err <= tol * scale, (what, mode, eng.mode, "position", n_hist + i, "rel err", err / scale, "tol", tol, "yardstick", yard[i] if yard else None)
             assert nxt == int(np.argmax(got))
             srt = np.partition(want, -2)[-2:]
             if srt[1] - srt[0] > 2.5 * err:
                 assert nxt == int(np.argmax(want)), (what, mode, "arg-max at position", n_hist + i, err, float(srt[1] - srt[0]))
-            still_same = still_same and nxt == int(np.argmax(want))
-            same_prefix += int(still_same)
-        report[f"{mode}:{eng.mode}"] = dict(max_rel_err=f"{max(errs):.2e}", first=f"{errs[0]:.2e}", argmax_same_prefix=f"{same_prefix}/{len(toks)}")
+            # the K row the engine wrote for layer 0 at this position sees no depth amplification: one bf16 ulp at most
+            k0 = eng.kv_row("k", 0, n_hist + i).float().cpu().numpy()
+            kerrs.append(float(np.abs(k0 - rows[i][0][0]).max()) / max(1e-6, float(np.abs(rows[i][0][0]).max())))
+            assert kerrs[-1] <= 1e-2, (what, mode, "layer-0 K row", n_hist + i, kerrs[-1])
+            _put_rows_engine(eng, ms, n_hist + i, *rows[i])   # teacher-force the cache too: the next position sees the oracle's rows
+        report[f"{mode}:{eng.mode}"] = dict(max_rel_err=f"{max(errs):.2e}", per_position=[f"{e:.1e}" for e in errs], layer0_k_row=f"{max(kerrs):.1e}")
         eng.close()
-    print(f"\n[{what}] yardstick (reference vs its FMA-contracted build), per position:", None if yard is None else [f"{y:.1e}" for y in yard])
+    print(f"\n[{what}] yardstick (reference vs its FMA-contracted build, identical inputs), per position:", None if yard is None else [f"{y:.1e}" for y in yard])
     for k, v in report.items():
         print(f"[{what}] {k}: {v}")
     return report
 
 
 def _late(port, ms, wd, n_hist, tokens, modes, seed, what, group=64):
-    toks, strict, yard = _oracle_runs(port, ms, wd, seed, group, n_hist, lambda i, out: tokens[i] if i < len(tokens) else None)
-    return _check_engines(ms, wd, seed, group, n_hist, toks, strict, yard, modes, what)
+    toks, strict, rows, yard = _oracle_runs(port, ms, wd, seed, group, n_hist, lambda i, out: tokens[i] if i < len(tokens) else None)
+    return _check_engines(ms, wd, seed, group, n_hist, toks, strict, rows, yard, modes, what)
 
 
 def _head(port, ms, wd, prompt, n_total, modes, seed, what, group=64):
@@ -149,8 +184,8 @@ def _head(port, ms, wd, prompt, n_total, modes, seed, what, group=64):
         if i >= n_total - 1:
             return None
         return prompt[i] if i < len(prompt) else int(np.argmax(out[i - 1]))
-    toks, strict, yard = _oracle_runs(port, ms, wd, seed, group, 0, feed)
-    return _check_engines(ms, wd, seed, group, 0, toks, strict, yard, modes, what)
+    toks, strict, rows, yard = _oracle_runs(port, ms, wd, seed, group, 0, feed)
+    return _check_engines(ms, wd, seed, group, 0, toks, strict, rows, yard, modes, what)
 
 
 # ---- cfg4: Llama-2-7B-shaped, 32 layers, bf16 weights + bf16 KV (the configuration the metric is quoted on) ---------------------------

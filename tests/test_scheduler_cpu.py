@@ -148,3 +148,17 @@ def test_requests_submitted_while_running_join_the_batch():
     out = cb.run()
     assert np.array_equal(out[a], alone([1], 30)) and np.array_equal(out[b], alone([2, 3], 11))
     assert predict_many(FakeDecoder(2, 4, 20), [[1], [2, 3]], 5)[1].tolist() == alone([2, 3], 6).tolist()
+
+
+def test_request_longer_than_max_len_is_refused_at_submit():
+    """A request whose prompt + new tokens exceed the engine's max_len must be refused by submit(): admitted, it would fail inside
+    a chunk of steps and leave every other live request un-retired."""
+    dec = FakeDecoder(max_seqs=2, page_len=4, n_pages=100, max_len=32)
+    cb = ContinuousBatcher(dec)
+    ok = cb.submit([1, 2, 3], 10)
+    with pytest.raises(ValueError, match="max_len"):
+        cb.submit(list(range(1, 21)), 14)          # 20 + 14 - 1 = 33 positions > 32
+    cb.submit(list(range(1, 21)), 13)              # 32 positions: exactly fits
+    out = cb.run()
+    assert ok in out and len(out) == 2
+    assert dec.free_pages == dec.n_pages

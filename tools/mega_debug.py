@@ -7,11 +7,12 @@ import torch
 from simplellminference_b200 import _lib
 from simplellminference_b200.config import PRESETS, BF16
 from simplellminference_b200.engine import Engine
-ap = argparse.ArgumentParser(); ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--steps", type=int, default=20)
+ap = argparse.ArgumentParser(); ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--steps", type=int, default=20); ap.add_argument("--v2", action="store_true"); ap.add_argument("--fuse-down", action="store_true")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True).load_synthetic(1234)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True, mega_v2=a.v2, mega_fuse_down=a.fuse_down).load_synthetic(1234)
+print(json.dumps({"mode": eng.mode}), flush=True)
 lib = _lib.load()
 for dbg, what in ((0, "normal"), (1, "no grid barriers"), (2, "no dot products"), (3, "no barriers, no dot products"), (0, "normal again")):
     lib.sllm_tune(8, dbg)

@@ -16,6 +16,17 @@ for s in "$@"; do
     probe)     step 120 fusion_probe tools/microbench/_build/fusion_probe 1000 ;;
     trace)     step 120 mega_trace python tools/mega_trace.py ;;
     trace_ll)  step 120 mega_trace_ll python tools/mega_trace.py --ll ;;
+    trace_v2)  step 120 mega_trace_v2 python tools/mega_trace.py --v2 ;;
+    trace_v2f) step 120 mega_trace_v2f python tools/mega_trace.py --v2 --fuse-down ;;
+    trace_v2fc) step 120 mega_trace_v2fc python tools/mega_trace.py --v2 --fuse-down --calibrate ;;
+    caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
+    debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
+    sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
+    cprobe)    step 120 consumer_probe tools/microbench/_build/consumer_probe ;;
+    v2tests)   step 900 v2tests python -m pytest tests/test_engine_gpu.py -q -k "v2" ;;
+    v2check)   step 300 v2check python tools/v2_check.py ;;
+    bench_v2)  step 600 bench_v2 python bench.py --no-batch --no-cpu-baseline --mega-v2; grep -h '^{' "$OUT/bench_v2.log" | tail -1 > "$OUT/bench_v2.json" ;;
+    bench_v2f) step 600 bench_v2f python bench.py --no-batch --no-cpu-baseline --mega-v2 --mega-fuse-down; grep -h '^{' "$OUT/bench_v2f.log" | tail -1 > "$OUT/bench_v2f.json" ;;
     debug)     step 240 mega_debug python tools/mega_debug.py ;;
     pytest)    step 1200 pytest_gpu python -m pytest tests -q -m gpu -rxXs --deselect tests/test_full_config_gpu.py ;;
     pytest_all) step 1500 pytest_gpu python -m pytest tests -q -m gpu -rxXs ;;
