@@ -21,6 +21,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "_build", "liboracle_port.so")
 PORT_FMA_SO = os.path.join(HERE, "_build", "liboracle_port_fma.so")   # yardstick build (FMA contraction), see oracle/Makefile
+PORT_FAST_SO = os.path.join(HERE, "_build", "liboracle_port_fast.so")  # yardstick build (-Ofast: re-associated sums)
 REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
 REF_FAST_SO = os.path.join(HERE, "_ref", "libref_oracle_fast.so")
 

@@ -12,6 +12,7 @@ constexpr int kSlots = 2;
 constexpr int kCplMax = 4;        // max 16-byte chunks per lane per row slice (slice <= 2 KB)
 constexpr int kRoundUnits = 128;  // units per partial-table round
 constexpr int kAttTile = 64;
+constexpr int kAttP = 3 * kAttTile;   // scores per query head the single-pass attention of megakernel2.cu keeps (two K/V stages + a tail of <= 64 rows)
 constexpr unsigned kSpinLimit = 1u << 26;
 #ifndef SLLM_BARRIER_POLL_COUNTER
 #define SLLM_BARRIER_POLL_COUNTER 1   // measured on B200 (llama2-7b bf16): 350.4 tok/s vs 338.1 with the separate release flag
@@ -39,7 +40,7 @@ __host__ __device__ inline MegaSmem mega_smem_layout(int hd, int g, int kv_esz) 
     L.ring = off; off += (size_t)kMegaWarps * kSlots * kSlotBytes;
     L.att = off;
     L.att_q = off; off += (size_t)g * hd * 4;
-    L.att_p = off; off += (size_t)g * kAttTile * 4;
+    L.att_p = off; off += (size_t)g * kAttP * 4;
     L.att_misc = off; off += 256;
     off = (off + 127) & ~(size_t)127;
     L.kv_stride = hd * kv_esz;   // dense rows: a tile is one contiguous bulk copy
@@ -163,10 +164,17 @@ __device__ __forceinline__ void down_t_rows(int g0, int g1, int rg, int RG, int&
     b = g0 + (cnt * (rg + 1)) / RG;
 }
 
-// (An L2 look-ahead of the weight stream — a second cursor per warp issuing cp.async.bulk.prefetch.L2 for the tiles 2-16 slots ahead of
-// the ring, so that HBM keeps streaming through a dependency stall — was built and measured in round 2 and removed: it is SLOWER at
-// every depth (2 tiles / 18 MB ahead: -5 %, 8 tiles / 74 MB: -30 %; profiles/r02_l2_lookahead_sweep.jsonl), as the round-1 attempts
-// at phase boundaries were. The bulk prefetches compete with the demand copies of the two-slot rings instead of running under them.)
+// ---- L2 prefetch of the weight stream: built twice in round 2, measured, removed ------------------------------------------------------
+// The rings hold 128 KB per SM; at a dependency point (grid barrier, attention, per-head counters) the consumers stall and HBM runs dry
+// (with the dot products removed the step takes exactly as long, with the barriers removed it is 20 % shorter: r02_mega_debug_v1.jsonl).
+// Asking the L2 for the tiles beyond the ring with cp.async.bulk.prefetch.L2 works IN ISOLATION (r02_prefetch_probe.jsonl: 39 MB asked
+// for, 10 us of idling, then streamed through the rings in 2.1 us instead of 4.2 us = 120-130 GB/s per SM against 49-63 from HBM), and
+// loses in the kernel in both forms tried: (1) a continuous look-ahead of 2-16 tiles per warp during streaming: -5 % to -30 %
+// (r02_l2_lookahead_sweep.jsonl); (2) 2-12 tiles per warp asked for right before a grid barrier and / or before the attention chain:
+// -4 % to -13 % (r02_l2_prefetch_at_stalls_sweep.jsonl). A CTA's "stall" is the time the slowest CTAs still stream (the bulk prefetches
+// of the early ones take HBM bandwidth from exactly the copies the barrier is waiting for), and the attention / counter chain is a
+// sequence of small latency-critical L2 round trips that queue behind 40 MB of prefetch traffic. HBM is the shared resource: anything
+// that is not on the critical path and uses it lengthens the critical path.
 
 // acc[e] += w_e * s for the E weights of one 16-byte chunk (fp32 / bf16 storage)
 template <int WD>

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
     uint8_t* const smem = mega_smem;
     const MegaSmem SL = mega_smem_layout(p.hd, G, KESZ);
     uint64_t* ring_bar = reinterpret_cast<uint64_t*>(smem + SL.bars);            // [16][kSlots]
-    uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;                          // [2]
+    uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;                          // [3]: K/V stages 0, 1 and the tail stage of the single-pass attention
     float* red = reinterpret_cast<float*>(smem + SL.red);
     float* part = reinterpret_cast<float*>(smem + SL.part);                      // [kRoundUnits][2][16]
     uint8_t* ring = smem + SL.ring;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int nwp = 4 * p.L + 1;
 
-    if (tid < kMegaWarps * kSlots + 2) mb_init(ring_bar + tid, 1);
+    if (tid < kMegaWarps * kSlots + 3) mb_init(ring_bar + tid, 1);
     if (tid == 0) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_npub = 0;
@@ -236,8 +236,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
         for (int s = 0; s < kSlots; ++s) produce_one();
     }
     unsigned cons_count = 0;
-    unsigned kv_use0 = 0, kv_use1 = 0;
-
+    unsigned kv_use0 = 0, kv_use1 = 0, kv_use2 = 0;
     // value r of the token's embedding row (layer 0's residual): the tiled classifier / embedding matrix
     auto emb_elem = [&](int r) -> float {
         const PhaseDesc em = p.phases[nwp - 1];
@@ -267,6 +266,36 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                 // merge the group's attention splits: weights of the splits per head first, then the columns
                 const int rec = p.hd + kAttRecPad;
                 float* wgt = part;                              // [G][nsplit + 1] (the partial table is idle here)
+                if (p.nsplit <= 8) {   // every record word a thread needs, requested at once: ONE L2 round trip, the weights recomputed per thread
+                    for (int c4 = tid; c4 < ghd / 4; c4 += kMegaThreads) {
+                        const int col = c4 * 4;
+                        const int gi = col / p.hd, j = col - gi * p.hd;
+                        const float* base = p.att_part + (size_t)(my_kvh * G + gi) * p.nsplit * rec;
+                        float m[8], ls[8];
+                        float4 v[8];
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            m[s] = -INFINITY; ls[s] = 0.f; v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (s < p.nsplit) {
+                                m[s] = __ldcg(base + (size_t)s * rec + p.hd);
+                                ls[s] = __ldcg(base + (size_t)s * rec + p.hd + 1);
+                                v[s] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * rec + j));
+                            }
+                        }
+                        float M = -INFINITY;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) M = fmaxf(M, m[s]);
+                        float Ls = 0.f;
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const float w = (m[s] == -INFINITY) ? 0.f : expf(m[s] - M);
+                            Ls = fmaf(ls[s], w, Ls);
+                            o.x = fmaf(v[s].x, w, o.x); o.y = fmaf(v[s].y, w, o.y); o.z = fmaf(v[s].z, w, o.z); o.w = fmaf(v[s].w, w, o.w);
+                        }
+                        reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+                    }
+                } else {
                 if (tid < G) {
                     const float* base = p.att_part + (size_t)(my_kvh * G + tid) * p.nsplit * rec + p.hd;
                     float M = -INFINITY;
@@ -293,6 +322,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                     }
                     const float Ls = wgt[gi * (p.nsplit + 1) + p.nsplit];
                     reinterpret_cast<float4*>(xs)[c4] = make_float4(o.x / Ls, o.y / Ls, o.z / Ls, o.w / Ls);
+                }
                 }
                 __syncthreads();
                 // this lane's chunk(s) of the merged vector -> registers
@@ -713,6 +743,33 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
         // ---- publish this CTA's q / k / v units to the kv head groups they belong to (all stores above precede the round's
         //      trailing __syncthreads; red.release orders them before the counter)
         if (tid < s_npub) flag_add_release(qkv_cnt + (size_t)s_pub_g[tid] * 32, (unsigned)s_pub_n[tid]);
+        // Single-pass attention: when the item's rows all fit on chip — the two K/V stages (128 rows, prefetched while the qkv weights
+        // streamed) plus a tail of up to 64 rows in the partial table, which is idle from here to the next weight phase — scores, softmax
+        // and P.V run ONCE over all of them instead of tile by tile (4 block-wide syncs per tile and an exposed copy for the third tile).
+        // The tail is requested now, so that it lands under the wait for the group's q / k / v.
+        const int att_row_bytes = p.hd * KESZ;
+        const int tail_cap = min(kAttTile, (kRoundUnits * 2 * kMegaWarps * 4) / (2 * att_row_bytes));
+        int att_t0 = 0, att_rows = 0;
+        if (has_item) {
+            const int npos_ = pos + 1, per_ = (npos_ + p.nsplit - 1) / p.nsplit;
+            att_t0 = my_part * per_;
+            att_rows = max(0, min(npos_, att_t0 + per_) - att_t0);
+        }
+        const bool att_single = att_rows <= 2 * kAttTile + tail_cap;
+        const int att_tail = att_single ? max(0, att_rows - 2 * kAttTile) : 0;
+        uint8_t* const tail_k = reinterpret_cast<uint8_t*>(part);
+        uint8_t* const tail_v = tail_k + (size_t)tail_cap * att_row_bytes;
+        if (att_tail > 0 && warp == 0 && lane == 0) {
+            fence_async_smem();   // the epilogue's generic reads of the partial table precede the async writes
+            const int ts = att_t0 + 2 * kAttTile;
+            const int bulk_rows = max(0, min(att_tail, pos - ts));
+            const size_t head_off = ((size_t)l * p.KVH_loc + my_kvh) * p.S * att_row_bytes;
+            mb_expect(att_bar + 2, (uint32_t)(2 * bulk_rows * att_row_bytes));
+            if (bulk_rows > 0) {
+                tma_g2s(tail_k, p.kc + head_off + (size_t)ts * att_row_bytes, bulk_rows * att_row_bytes, att_bar + 2);
+                tma_g2s(tail_v, p.vc + head_off + (size_t)ts * att_row_bytes, bulk_rows * att_row_bytes, att_bar + 2);
+            }
+        }
         M2_STAMP(ev, 5);
         M2_STAMP(ev + 1, 0);
         if (!has_item) { M2_STAMP(ev + 1, 4); M2_STAMP(ev + 1, 5); continue; }
@@ -766,6 +823,78 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
 #pragma unroll
                 for (int e = 0; e < KVEC; ++e) acc[gi][e] = 0.f;
 
+            if (att_single) {
+                const int nrows = att_rows;
+                auto krow = [&](int r) -> const uint8_t* { return r < 2 * kAttTile ? k_s + (size_t)r * stride : tail_k + (size_t)(r - 2 * kAttTile) * row_bytes; };
+                auto vrow = [&](int r) -> const uint8_t* { return r < 2 * kAttTile ? v_s + (size_t)r * stride : tail_v + (size_t)(r - 2 * kAttTile) * row_bytes; };
+                if (pos >= t0 && pos < t1 && warp == 1) {   // the newest row (generic stores of this launch) bypasses the async proxy
+                    const size_t g_off = head_off + (size_t)pos * row_bytes;
+                    for (int c = lane; c < cpr; c += 32) {
+                        *reinterpret_cast<uint4*>(const_cast<uint8_t*>(krow(pos - t0)) + c * 16) = __ldcg(reinterpret_cast<const uint4*>(p.kc + g_off + c * 16));
+                        *reinterpret_cast<uint4*>(const_cast<uint8_t*>(vrow(pos - t0)) + c * 16) = __ldcg(reinterpret_cast<const uint4*>(p.vc + g_off + c * 16));
+                    }
+                }
+                if (nrows > 0) { mb_wait_fast(att_bar, kv_use0 & 1); kv_use0++; }
+                if (nrows > kAttTile) { mb_wait_fast(att_bar + 1, kv_use1 & 1); kv_use1++; }
+                if (att_tail > 0) { mb_wait_fast(att_bar + 2, kv_use2 & 1); kv_use2++; }
+                __syncthreads();
+#pragma unroll 1
+                for (int kb = 0; kb < nrows; kb += kAttTile) {        // scores of all rows, 8 threads per key
+                    const int r = kb + key;
+                    float s[G];
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi) s[gi] = 0.f;
+                    if (r < nrows) {
+                        const uint8_t* kr = krow(r);
+                        for (int c = kpart; c < cpr; c += 8) {
+                            float kf[KVEC];
+                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(kr + c * 16), kf);
+#pragma unroll
+                            for (int gi = 0; gi < G; ++gi) {
+                                const float* qv = q_s + gi * p.hd + c * KVEC;
+#pragma unroll
+                                for (int e = 0; e < KVEC; ++e) s[gi] = fmaf(qv[e], kf[e], s[gi]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi) {
+                        s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 1);
+                        s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 2);
+                        s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], 4);
+                        if (kpart == 0 && r < nrows) p_s[gi * kAttP + r] = s[gi] * scale;
+                    }
+                }
+                __syncthreads();
+                for (int gi = warp; gi < G; gi += kMegaWarps) {        // softmax over the split's rows (mha_kernel.cpp:7-20 per split)
+                    float mx = -INFINITY;
+                    for (int i = lane; i < nrows; i += 32) mx = fmaxf(mx, p_s[gi * kAttP + i]);
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+                    for (int i = lane; i < nrows; i += 32) {
+                        const float e = expf(p_s[gi * kAttP + i] - mx);
+                        p_s[gi * kAttP + i] = e;
+                        sum += e;
+                    }
+                    sum = warp_sum(sum);
+                    if (lane == 0) { ml_s[2 * gi] = mx; ml_s[2 * gi + 1] = sum; }
+                }
+                __syncthreads();
+                if (pv_active) {
+                    for (int r = pv_stripe; r < nrows; r += kStripes) {
+                        float vf[KVEC];
+                        kv_unpack<KVD>(*reinterpret_cast<const uint4*>(vrow(r) + pv_chunk * 16), vf);
+#pragma unroll
+                        for (int gi = 0; gi < G; ++gi) {
+                            const float pr = p_s[gi * kAttP + r];
+#pragma unroll
+                            for (int e = 0; e < KVEC; ++e) acc[gi][e] = fmaf(pr, vf[e], acc[gi][e]);
+                        }
+                    }
+                }
+                fence_async_smem();
+                __syncthreads();
+            } else {
 #pragma unroll 1
             for (int tile = 0; tile < ntiles; ++tile) {
                 const int stage = tile & 1;
@@ -842,6 +971,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                 fence_async_smem();
                 __syncthreads();
                 if (warp == 0 && tile + 2 < ntiles) issue_tile(tile + 2);
+            }
             }
             float* o_s = reinterpret_cast<float*>(k_s);   // [kStripes][G][hd]
             if (pv_active) {

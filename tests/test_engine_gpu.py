@@ -197,10 +197,13 @@ def test_full_width_llama2_7b_two_layers(port, wd, mega):
     do. bf16 KV cache (fp32 K/V tiles of 128-wide heads do not fit the megakernel), so the oracle rounds its cache rows too."""
     import dataclasses
     ms = dataclasses.replace(PRESETS["llama2-7b"], layers=2, max_len=64)
-    blob = port.fill_blob(oracle_shape(ms), 9, wd, 64, threads=os.cpu_count() or 1)
+    # seed 10: the oracle's top-1/top-2 margins along this stream are >= 5.8 (on logits of ~280). Seed 9, used until round 2, has a
+    # 0.0018 margin at the first generated token: the grid-barrier kernel itself lands on either side of it depending on max_len
+    # (the number of attention splits), so a token-identity assertion there tested luck, not parity
+    blob = port.fill_blob(oracle_shape(ms), 10, wd, 64, threads=os.cpu_count() or 1)
     om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
     want, want_l = om.greedy([1, 2, 3], 14)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(9)
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(10)
     assert eng.mode == {True: "megakernel", False: "fused+graph", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega], eng.mode
     got = eng.greedy([1, 2, 3], 14)
     assert np.array_equal(got, want), (got, want)

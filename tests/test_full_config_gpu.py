@@ -14,10 +14,14 @@ hundreds of dependency points per step, ring run-ahead across 32 layers, split-K
 Why teacher-forced and not "token stream identical": at 32 layers the synthetic gain-4 model amplifies fp32 rounding noise chaotically,
 and the bf16 cache turns it into rounding-boundary flips. The REFERENCE ALGORITHM AGAINST ITSELF shows it: the C restatement built with
 FMA contraction (oracle/_build/liboracle_port_fma.so = what `-O3 -march=x86-64-v3` does to the reference) leaves the strict build's
-greedy stream at the 5th generated token on cfg4 (measured in the dev container: tokens 28505 vs 2143, margin 0.52). So (1) every position
+greedy stream at the 5th generated token on cfg4 (measured in the dev container: tokens 28505 vs 2143, margin 0.52); built with -Ofast
+(liboracle_port_fast.so: serial sums re-associated into 8-lane partial sums, what every parallel implementation must do) its logits
+move by up to 12 % of max|logit| on single positions of cfg4 with IDENTICAL inputs (position 517 of the test below). So (1) every position
 is checked on IDENTICAL inputs: tokens are teacher-forced and so is the cache — after each forward the strict oracle's K/V rows of that
 position replace the ones the engine (or the yardstick build) wrote, so nothing compounds from position to position; and (2) the
-tolerance is CALIBRATED per position by the yardstick yard_i = |logits_fma_i - logits_strict_i| / max|logits_strict_i|: the CUDA path
+tolerance is CALIBRATED per position by the yardstick yard_i = max over the two builds of |logits_build_i - logits_strict_i| /
+max|logits_strict_i| (the sensitivity is a property of the state at that position: both builds and the CUDA path peak at the same
+positions): the CUDA path
 must stay within max(5e-3, 4 * yard_i) of the strict oracle, i.e. no further from the reference than a legal re-association of the
 reference's own arithmetic is (times 4: the statistic is one sample per position; measured yard_i ~ 1e-2 at 32 layers). The K row
 the engine writes for layer 0 (no depth amplification) must match the oracle's to a bf16 ulp. Every engine mode that serves the configuration is checked: the default megakernel(s), the word-based
@@ -128,15 +132,19 @@ def _oracle_runs(port, ms, wd, seed, group, n_hist, feed):
         i += 1
     om.close()
     yard = None
-    if loader.cpu_supports_v3() and os.path.exists(loader.PORT_FMA_SO):
-        om = model(loader.Port(loader.PORT_FMA_SO))
-        yard = []
-        for i, t in enumerate(toks):
-            if i:
-                _put_rows_oracle(om, ms, n_hist + i - 1, *rows[i - 1])
-            lg = om.forward(t, n_hist + i)
-            yard.append(float(np.abs(lg - strict[i]).max()) / max(1.0, float(np.abs(strict[i]).max())))
-        om.close()
+    if loader.cpu_supports_v3():
+        for so in (loader.PORT_FMA_SO, loader.PORT_FAST_SO):
+            if not os.path.exists(so):
+                continue
+            om = model(loader.Port(so))
+            y = []
+            for i, t in enumerate(toks):
+                if i:
+                    _put_rows_oracle(om, ms, n_hist + i - 1, *rows[i - 1])
+                lg = om.forward(t, n_hist + i)
+                y.append(float(np.abs(lg - strict[i]).max()) / max(1.0, float(np.abs(strict[i]).max())))
+            om.close()
+            yard = y if yard is None else [max(a, b) for a, b in zip(yard, y)]
     del blob
     return toks, strict, rows, yard
 

@@ -9,7 +9,7 @@ from simplellminference_b200.config import PRESETS, BF16
 from simplellminference_b200.engine import Engine
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--steps", type=int, default=24)
-ap.add_argument("--variants", default="v1,v1+cal,v1f,v1f+cal,v2f,v2f+cal")
+ap.add_argument("--variants", default="v1,v2f,v2f+cal")
 a = ap.parse_args()
 ms = PRESETS[a.config]
 lib = _lib.load()

@@ -12,6 +12,8 @@ ap.add_argument("--mode", default="mega", choices=["mega", "fused"])
 ap.add_argument("--pos", type=int, default=512)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--fuse-down", action="store_true", help="mega mode: the experimental kernel with the down projection fused into the gate_up phase")
+ap.add_argument("--v2", action="store_true", help="mega mode: csrc/megakernel2.cu (two grid-wide dependency points per layer)")
+ap.add_argument("--calibrate", action="store_true", help="mega mode: sllm_engine_calibrate before the steps")
 ap.add_argument("--batch", type=int, default=0, help="> 0: that many sequences through the batched decoder (sllm_batch_*) instead of the engine's own step")
 a = ap.parse_args()
 ms = PRESETS[a.config]
@@ -33,7 +35,9 @@ if a.batch:   # every sequence decodes a.pos tokens first (untimed), then a.step
     print(json.dumps({"mode": f"batch of {a.batch}", "layers": ms.layers, "step_ms": round(msec, 4), "tokens_per_sec": round(a.batch / msec * 1e3, 1),
                       "GBps": round(nbytes / msec / 1e6, 0)}))
     sys.exit(0)
-eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega"), mega_fuse_down=a.fuse_down).load_synthetic(1)
+eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=(a.mode == "mega"), mega_fuse_down=a.fuse_down, mega_v2=a.v2).load_synthetic(1)
+if a.calibrate:
+    eng.calibrate(3)
 eng.set_state(1, a.pos)
 eng.enqueue_steps(2); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

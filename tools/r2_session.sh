@@ -22,6 +22,13 @@ for s in "$@"; do
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
+    san_*)     c=${s#san_}; tool=${c%%:*}; case_=${c#*:}; step 600 "sanitize_${tool}_${case_}" env SLLM_COMPARE=0 compute-sanitizer --tool "$tool" --print-limit 30 python tools/sanitize_case.py "$case_" ;;
+    case_*)    step 300 "case_${s#case_}" python tools/sanitize_case.py "${s#case_}" ;;
+    ncu_v2f)   PS="python tools/profile_step.py --v2 --fuse-down --calibrate --pos 520 --steps 2"
+               step 120 ncu_v2f_plain $PS
+               step 600 ncu_v2f_full ncu --set full --clock-control none --import-source on -k regex:mega2_step -s 30 -c 1 -o "$OUT/r02_mega2_v2f" -f $PS ;;
+    ncu_bench) step 600 ncu_bench_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/r02_bench_launches.csv" python bench.py --steps 20 --warmup 5 --no-cpu-baseline ;;
+    pprobe)    step 120 prefetch_probe tools/microbench/_build/prefetch_probe ;;
     cprobe)    step 120 consumer_probe tools/microbench/_build/consumer_probe ;;
     v2tests)   step 900 v2tests python -m pytest tests/test_engine_gpu.py -q -k "v2" ;;
     v2check)   step 300 v2check python tools/v2_check.py ;;
