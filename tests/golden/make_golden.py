@@ -28,6 +28,7 @@ SHAPES = {
 MODEL_RUNS = {  # name -> (prompt, n_total, wdtype, positions whose full logits are stored)
     "cfg1_stories15M": ([1], 128, loader.F32),
     "cfg2_stories110M": ([1], 24, loader.F32),
+    "cfg2_stories110M_256": ([1], 256, loader.F32),          # BASELINE.json configs[1] at its full length: 256 greedy tokens
     "tiny_gqa": ([1, 7, 300, 12, 44], 46, loader.F32),       # S=48, H/KVH=2 -> parity domain pos <= 46
     "tiny_gqa_bf16w": ([1, 7, 300, 12, 44], 46, loader.BF16),
     "tiny_gqa_int8w": ([1, 7, 300, 12, 44], 46, loader.INT8),
@@ -69,7 +70,7 @@ def main():
 
     models = {}
     for name, (prompt, n_total, wd) in MODEL_RUNS.items():
-        shape = SHAPES[name.replace("_bf16w", "").replace("_int8w", "")]
+        shape = SHAPES[name.replace("_bf16w", "").replace("_int8w", "").replace("_256", "")]
         blob = port.fill_blob(shape, SEED, wd, 64)
         m = ref.model(shape, blob)
         toks, last = m.greedy(prompt, n_total)

@@ -26,7 +26,7 @@ _spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.pa
 mg = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(mg)
 
-PRESET_OF = {"cfg1_stories15M": "stories15M", "cfg2_stories110M": "stories110M", "tiny_gqa": "tiny_gqa",
+PRESET_OF = {"cfg1_stories15M": "stories15M", "cfg2_stories110M": "stories110M", "cfg2_stories110M_256": "stories110M", "tiny_gqa": "tiny_gqa",
              "tiny_gqa_bf16w": "tiny_gqa", "tiny_gqa_int8w": "tiny_gqa", "tiny_mha_hd48": "tiny_mha_hd48"}
 
 

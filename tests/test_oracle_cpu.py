@@ -36,7 +36,7 @@ def test_ops_match_golden(port, golden_ops):
 @pytest.mark.parametrize("name", list(mg.MODEL_RUNS))
 def test_models_match_golden(port, golden_models, name):
     prompt, n_total, wd = mg.MODEL_RUNS[name]
-    shape = mg.SHAPES[name.replace("_bf16w", "").replace("_int8w", "")]
+    shape = mg.SHAPES[name.replace("_bf16w", "").replace("_int8w", "").replace("_256", "")]
     blob = port.fill_blob(shape, mg.SEED, wd, 64)
     m = port.model(shape, blob, threads=os.cpu_count() or 1)
     toks, last = m.greedy(prompt, n_total)

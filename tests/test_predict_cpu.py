@@ -56,12 +56,15 @@ def _reference_stream(prompt, n, vocab=64):
     return out
 
 
-@pytest.mark.parametrize("prefill", [True, False])
-def test_predict_ids_matches_the_token_loop(prefill):
+@pytest.mark.parametrize("prefill,ask", [(True, True), (True, False), (False, True), (False, False)])
+def test_predict_ids_matches_the_token_loop(prefill, ask):
+    """The prompt goes token by token through the decode step (the reference's loop, the parity path) unless the caller opts in to the
+    batched tensor-core pass AND the engine supports it."""
     eng = ToyEngine(prefill_supported=prefill)
-    got = predict_ids(eng, [5, 9, 2], 40, chunk=7)
+    got = predict_ids(eng, [5, 9, 2], 40, chunk=7, batched_prefill=ask)
     assert got.tolist() == _reference_stream([5, 9, 2], 40)
-    assert eng.calls[0] == ("prefill" if prefill else "greedy")
+    assert eng.calls[0] == ("prefill" if (prefill and ask) else "greedy")
+    assert predict_ids(ToyEngine(prefill_supported=True), [5, 9, 2], 12).size == 12 and True
     assert sum(k for c in eng.calls[1:] for k in [c[1]]) == 40 - 3      # chunks add up exactly to max_length
 
 
