@@ -8,8 +8,8 @@ Tolerances (floating point; the tensor-core operands are bf16, accumulation fp32
 * attention alone against a torch fp32 softmax on the same bf16 q/K/V: P and the output are rounded to bf16
   (2^-9 relative each) -> 2e-2 * max|out|;
 * whole prefill against the oracle: activations entering every GEMM are rounded to bf16 (2^-9 relative per operand).
-  On the gain-1 synthetic model (see _blob): KV rows of every layer <= 3e-2 * max|row| (layer 0, where only the RMSNorm
-  output was rounded: 1e-2), last-position logits <= 3e-2 * max|logit|, next token identical whenever the oracle's
+  On the gain-1 synthetic model (see _blob): KV rows of every layer <= 1.2e-2 * max|row| (measured 5e-3), last-position
+  logits <= 3e-3 * max|logit| (measured 2-5e-4), next token identical whenever the oracle's
   top1-top2 margin exceeds twice the logit error. On the repo-wide gain-4 model the same rounding is
   amplified chaotically layer by layer: layer 0 is held to 1e-2, deeper layers and logits are printed, not bounded;
 * prefill against this engine's own token-by-token decode (fp32 activations): same bounds, and the decode that follows a
@@ -148,8 +148,8 @@ def test_prefill_matches_oracle_and_decode_path(port, name, gain):
           f"next token prefill {int(np.argmax(got_l))} oracle {int(np.argmax(want_l))}")
     assert worst[0] <= 1e-2, worst                      # layer 0: only the RMSNorm output was rounded to bf16
     if gain == 1:
-        assert max(worst.values()) <= 3e-2, worst
-        assert err <= 3e-2 * scale and err_dec <= 3e-2 * scale, (err, err_dec, scale)
+        assert max(worst.values()) <= 1.2e-2, worst       # measured 5e-3, flat over the layers (one bf16 rounding of the GEMM operands)
+        assert err <= 3e-3 * scale and err_dec <= 3e-3 * scale, (err, err_dec, scale)   # measured 2-5e-4 of max|logit| (the old 3e-2 was 60x looser)
         if margin > 2 * err:
             assert int(np.argmax(got_l)) == int(np.argmax(want_l))
     else:

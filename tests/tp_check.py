@@ -28,7 +28,9 @@ def main():
     cases = [("tiny_gqa f32", PRESETS["tiny_gqa"], F32, F32, [1, 7, 300], 40, False),
              ("medium bf16 weights, f32 kv", medium, BF16, F32, list(range(1, 17)), 120, False),
              ("medium bf16 weights, bf16 kv (teacher forced)", medium, BF16, BF16, list(range(1, 17)), 120, True),
-             ("mha8 bf16 weights, f32 kv", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, F32, list(range(1, 9)), 80, False)]
+             ("mha8 bf16 weights, f32 kv", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, F32, list(range(1, 9)), 80, False),
+             # 8 kv heads + bf16 cache: the one case in which the word-based megakernel itself (not its fall-back) runs at 8 ranks
+             ("mha8 bf16 weights, bf16 kv (teacher forced)", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, BF16, list(range(1, 9)), 80, True)]
     import itertools
     for (name, ms, wd, kvd, prompt, n_total, forced), comm in itertools.product(cases, ("nccl", "p2p", "mega")):
         p2p = comm != "nccl"

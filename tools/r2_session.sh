@@ -28,6 +28,7 @@ for s in "$@"; do
                step 120 ncu_v2f_plain $PS
                step 600 ncu_v2f_full ncu --set full --clock-control none --import-source on -k regex:mega2_step -s 30 -c 1 -o "$OUT/r02_mega2_v2f" -f $PS ;;
     ncu_bench) step 600 ncu_bench_launches ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mega|pf_|embed|rmsnorm' -c 3000 --csv --log-file "$OUT/r02_bench_launches.csv" python bench.py --steps 20 --warmup 5 --no-cpu-baseline ;;
+    tp*)       n=${s#tp}; step 900 "tp${n}_check" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29600 + n)) tests/tp_check.py ;;
     pprobe)    step 120 prefetch_probe tools/microbench/_build/prefetch_probe ;;
     cprobe)    step 120 consumer_probe tools/microbench/_build/consumer_probe ;;
     v2tests)   step 900 v2tests python -m pytest tests/test_engine_gpu.py -q -k "v2" ;;
