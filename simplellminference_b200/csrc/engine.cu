@@ -788,7 +788,8 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
         e->mega_fuse = e->mega && !e->mega_ll && (cfg->flags & SLLM_ENGINE_MEGA_FUSE_DOWN) && mega_fuse_down_ok(cfg->w_dtype, e->d, e->I_loc) &&
                        (g_q == 1 || g_q == 2 || g_q == 4 || g_q == 8);
         e->mega2 = e->mega && !e->mega_ll && (cfg->flags & SLLM_ENGINE_MEGA_V2) && (g_q == 1 || g_q == 2 || g_q == 4 || g_q == 8) &&
-                   mega2_ok(cfg->w_dtype, e->d, e->hd, e->H_loc, e->KVH_loc, e->mega_plan_.nsplit, e->mega_plan_.grid, nullptr);
+                   mega2_ok(cfg->w_dtype, e->d, e->hd, e->H_loc, e->KVH_loc, e->mega_plan_.nsplit, e->mega_plan_.grid, nullptr) &&
+                   e->mega_plan_.smem + 10 * 1024 <= (size_t)smem_optin_bytes();   // its static shared memory: phase table + publication list
     }
     layout(e);  // measure
     e->arena_bytes = align_up(e->arena_used, 1 << 20);

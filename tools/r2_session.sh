@@ -22,6 +22,8 @@ for s in "$@"; do
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
+    libab)     for v in "" _phsmem _nosp ""; do step 300 "libab${v:-_base}_$RANDOM" env SLLM_LIB=$PWD/simplellminference_b200/lib/libsllm_b200$v.so python tools/mega_sweep.py --variants v2f+cal --debug 0,0; done ;;
+    sweep_ab)  step 400 mega_sweep_ab python tools/mega_sweep.py --variants v2f+cal --debug 0,4,8,12,0 ;;
     san_*)     c=${s#san_}; tool=${c%%:*}; case_=${c#*:}; step 600 "sanitize_${tool}_${case_}" env SLLM_COMPARE=0 compute-sanitizer --tool "$tool" --print-limit 30 python tools/sanitize_case.py "$case_" ;;
     case_*)    step 300 "case_${s#case_}" python tools/sanitize_case.py "${s#case_}" ;;
     ncu_v2f)   PS="python tools/profile_step.py --v2 --fuse-down --calibrate --pos 520 --steps 2"
