@@ -377,9 +377,12 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     v2 = world == 1 and not (args.mega_v1 or args.mega_ll or args.no_mega or args.unfused)
+    # fusing the down projection into the gate_up phase trades a grid barrier for 148 partial vectors added in L2: it pays when the down matrix is
+    # large (Llama-2-7B 90 MB: +7 %, Llama-3-8B 117 MB: +6 %) and costs on small ones (TinyLlama 23 MB: -4 %; profiles/r02_other_configs.md)
+    fuse_pays = ms.inter * ms.hidden * {"f32": 4, "bf16": 2, "int8": 1}[args.wdtype] >= 48e6
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, fused=not args.unfused,
                  graph=not (args.no_graph or args.unfused), pdl=args.pdl, mega=not (args.no_mega or args.unfused), mega_ll=args.mega_ll,
-                 p2p_allreduce=(world > 1 and not args.nccl), mega_fuse_down=((args.mega_fuse_down or v2) and world == 1), mega_v2=v2)
+                 p2p_allreduce=(world > 1 and not args.nccl), mega_fuse_down=((args.mega_fuse_down or (v2 and fuse_pays)) and world == 1), mega_v2=v2)
     eng.load_synthetic(1234)
     calibrated = False
     if world == 1 and not args.no_calibrate and eng.mode.startswith("megakernel") and "ll" not in eng.mode:

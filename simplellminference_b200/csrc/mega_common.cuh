@@ -24,7 +24,10 @@ struct MegaSmem {
     size_t bars, red, part, ring, att, total;
     size_t att_q, att_p, att_misc, att_k, att_v;
     int kv_stride;
+    int att_tile;   // cache positions per K/V stage: 64, or 32 when a row is wider than 256 bytes (fp32 cache with 128-wide heads), so that
+                    // two K and two V stages always fit in 64 KB next to the weight rings
 };
+__host__ __device__ inline int mega_att_tile(int hd, int kv_esz) { return hd * kv_esz > 256 ? kAttTile / 2 : kAttTile; }
 __host__ __device__ inline int mega_kv_stride(int row_bytes) {
     int s = (row_bytes / 128) * 128 + 32;
     if (s < row_bytes) s += 128;
@@ -44,8 +47,9 @@ __host__ __device__ inline MegaSmem mega_smem_layout(int hd, int g, int kv_esz) 
     L.att_misc = off; off += 256;
     off = (off + 127) & ~(size_t)127;
     L.kv_stride = hd * kv_esz;   // dense rows: a tile is one contiguous bulk copy
-    L.att_k = off; off += (size_t)2 * kAttTile * L.kv_stride;
-    L.att_v = off; off += (size_t)2 * kAttTile * L.kv_stride;
+    L.att_tile = mega_att_tile(hd, kv_esz);
+    L.att_k = off; off += (size_t)2 * L.att_tile * L.kv_stride;
+    L.att_v = off; off += (size_t)2 * L.att_tile * L.kv_stride;
     L.total = off;
     return L;
 }

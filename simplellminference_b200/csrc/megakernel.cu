@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
     extern __shared__ __align__(128) uint8_t mega_smem[];
     uint8_t* const smem = mega_smem;
     const MegaSmem SL = mega_smem_layout(p.hd, G, KESZ);
+    const int AT = SL.att_tile;                      // cache positions per K/V stage (mega_common.cuh)
     uint64_t* ring_bar = reinterpret_cast<uint64_t*>(smem + SL.bars);            // [16][kSlots]
     uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;                          // [2]
     float* red = reinterpret_cast<float*>(smem + SL.red);
@@ -318,14 +319,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                 const int t0 = split * per, t1 = min(npos, t0 + per);
                 const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;   // [L][KVH][S][hd]
                 for (int tile = 0; tile < 2; ++tile) {
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     if (rows <= 0) break;
                     const int bulk_rows = max(0, min(rows, pos - ts));
                     mb_expect(att_bar + tile, (uint32_t)(2 * bulk_rows * row_bytes));
                     if (bulk_rows > 0) {
-                        tma_g2s(smem + SL.att_k + (size_t)tile * kAttTile * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
-                        tma_g2s(smem + SL.att_v + (size_t)tile * kAttTile * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_k + (size_t)tile * AT * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_v + (size_t)tile * AT * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
                     }
                 }
             }
@@ -560,20 +561,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
             for (int item = cta; item < nitems; item += ncta) {
                 const int kvh = item / p.nsplit, split = item - kvh * p.nsplit;
                 const int t0 = split * per, t1 = min(npos, t0 + per);
-                const int ntiles = (t1 > t0) ? (t1 - t0 + kAttTile - 1) / kAttTile : 0;
+                const int ntiles = (t1 > t0) ? (t1 - t0 + AT - 1) / AT : 0;
                 for (int i = tid; i < G * p.hd; i += kMegaThreads) q_s[i] = __ldcg(p.q + (size_t)(kvh * G) * p.hd + i);
                 if (tid < G) { ml_s[2 * tid] = -INFINITY; ml_s[2 * tid + 1] = 0.f; }
                 const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;   // [L][KVH][S][hd]
                 auto issue_tile = [&](int tile) {              // warp 0: TMA for rows written by EARLIER launches;
                     const int stage = tile & 1;                // the row written this step (pos) is copied by hand
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     const int bulk_rows = max(0, min(rows, pos - ts));
                     if (lane == 0) {
                         mb_expect(att_bar + stage, (uint32_t)(2 * bulk_rows * row_bytes));
                         if (bulk_rows > 0) {
-                            tma_g2s(k_s + (size_t)stage * kAttTile * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
-                            tma_g2s(v_s + (size_t)stage * kAttTile * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                            tma_g2s(k_s + (size_t)stage * AT * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                            tma_g2s(v_s + (size_t)stage * AT * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
                         }
                     }
                 };
@@ -592,15 +593,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
 #pragma unroll 1
                 for (int tile = 0; tile < ntiles; ++tile) {
                     const int stage = tile & 1;
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     // the newest row (written by phase A of THIS launch with generic stores) bypasses the async proxy
                     if (pos >= ts && pos < ts + rows && warp == 1) {
                         const size_t g_off = head_off + (size_t)pos * row_bytes;
                         for (int c = lane; c < cpr; c += 32) {
-                            *reinterpret_cast<uint4*>(k_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                            *reinterpret_cast<uint4*>(k_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) =
                                 __ldcg(reinterpret_cast<const uint4*>(p.kc + g_off + c * 16));
-                            *reinterpret_cast<uint4*>(v_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                            *reinterpret_cast<uint4*>(v_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) =
                                 __ldcg(reinterpret_cast<const uint4*>(p.vc + g_off + c * 16));
                         }
                     }
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
 #pragma unroll
                         for (int gi = 0; gi < G; ++gi) s[gi] = 0.f;
                         if (key < rows) {
-                            const uint8_t* krow = k_s + ((size_t)stage * kAttTile + key) * stride;
+                            const uint8_t* krow = k_s + ((size_t)stage * AT + key) * stride;
                             for (int c = kpart; c < cpr; c += 8) {
                                 float kf[KVEC];
                                 kv_unpack<KVD>(*reinterpret_cast<const uint4*>(krow + c * 16), kf);
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_step_kernel(const MegaPa
                         }
                         for (int r = pv_stripe; r < rows; r += kStripes) {
                             float vf[KVEC];
-                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * kAttTile + r) * stride + pv_chunk * 16), vf);
+                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * AT + r) * stride + pv_chunk * 16), vf);
 #pragma unroll
                             for (int gi = 0; gi < G; ++gi) {
                                 const float pr = p_s[gi * kAttTile + r];
@@ -764,8 +765,8 @@ MegaPlan mega_plan_for(int sms, int smem_optin, int w_dtype, int group, int kv_d
     if ((hd * kesz / 16) > 32) { pl.why = "head_dim chunking"; return pl; }
     const MegaSmem SL = mega_smem_layout(hd, g, kesz);
     if (SL.total > (size_t)smem_optin) { pl.why = "shared memory"; return pl; }
-    if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
-    if ((size_t)std::max(d, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
+    if ((size_t)16 * g * hd * 4 > (size_t)4 * SL.att_tile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
+    if ((size_t)std::max(d, I_loc) * 4 > (size_t)4 * SL.att_tile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 2 || kv_loc % 2) { pl.why = "odd dims"; return pl; }
     pl.grid = sms;
     pl.smem = SL.total;

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
     extern __shared__ __align__(128) uint8_t mega_smem[];
     uint8_t* const smem = mega_smem;
     const MegaSmem SL = mega_smem_layout(p.hd, G, KESZ);
+    const int AT = SL.att_tile;                      // cache positions per K/V stage (mega_common.cuh)
     uint64_t* ring_bar = reinterpret_cast<uint64_t*>(smem + SL.bars);            // [16][kSlots]
     uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;                          // [3]: K/V stages 0, 1 and the tail stage of the single-pass attention
     float* red = reinterpret_cast<float*>(smem + SL.red);
@@ -548,14 +549,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                 const int t0 = my_part * per, t1 = min(npos, t0 + per);
                 const size_t head_off = ((size_t)l * p.KVH_loc + my_kvh) * p.S * row_bytes;   // [L][KVH][S][hd]
                 for (int tile = 0; tile < 2; ++tile) {
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     if (rows <= 0) break;
                     const int bulk_rows = max(0, min(rows, pos - ts));
                     mb_expect(att_bar + tile, (uint32_t)(2 * bulk_rows * row_bytes));
                     if (bulk_rows > 0) {
-                        tma_g2s(smem + SL.att_k + (size_t)tile * kAttTile * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
-                        tma_g2s(smem + SL.att_v + (size_t)tile * kAttTile * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_k + (size_t)tile * AT * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_v + (size_t)tile * AT * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
                     }
                 }
             }
@@ -765,13 +766,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
             att_t0 = my_part * per_;
             att_rows = max(0, min(npos_, att_t0 + per_) - att_t0);
         }
-        const bool att_single = att_rows <= 2 * kAttTile + tail_cap;   // +0.9 % tokens/s at 512-650 positions (A/B on one box)
-        const int att_tail = att_single ? max(0, att_rows - 2 * kAttTile) : 0;
+        const bool att_single = att_rows <= 2 * AT + tail_cap;   // +0.9 % tokens/s at 512-650 positions (A/B on one box)
+        const int att_tail = att_single ? max(0, att_rows - 2 * AT) : 0;
         uint8_t* const tail_k = reinterpret_cast<uint8_t*>(part);
         uint8_t* const tail_v = tail_k + (size_t)tail_cap * att_row_bytes;
         if (att_tail > 0 && warp == 0 && lane == 0) {
             fence_async_smem();   // the epilogue's generic reads of the partial table precede the async writes
-            const int ts = att_t0 + 2 * kAttTile;
+            const int ts = att_t0 + 2 * AT;
             const int bulk_rows = max(0, min(att_tail, pos - ts));
             const size_t head_off = ((size_t)l * p.KVH_loc + my_kvh) * p.S * att_row_bytes;
             mb_expect(att_bar + 2, (uint32_t)(2 * bulk_rows * att_row_bytes));
@@ -808,20 +809,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
             __syncthreads();
             M2_STAMP(ev + 1, 1);
             const int t0 = split * per, t1 = min(npos, t0 + per);
-            const int ntiles = (t1 > t0) ? (t1 - t0 + kAttTile - 1) / kAttTile : 0;
+            const int ntiles = (t1 > t0) ? (t1 - t0 + AT - 1) / AT : 0;
             for (int i = tid; i < G * p.hd; i += kMegaThreads) q_s[i] = __ldcg(p.q + (size_t)(kvh * G) * p.hd + i);
             if (tid < G) { ml_s[2 * tid] = -INFINITY; ml_s[2 * tid + 1] = 0.f; }
             const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;
             auto issue_tile = [&](int tile) {
                 const int stage = tile & 1;
-                const int ts = t0 + tile * kAttTile;
-                const int rows = min(kAttTile, t1 - ts);
+                const int ts = t0 + tile * AT;
+                const int rows = min(AT, t1 - ts);
                 const int bulk_rows = max(0, min(rows, pos - ts));
                 if (lane == 0) {
                     mb_expect(att_bar + stage, (uint32_t)(2 * bulk_rows * row_bytes));
                     if (bulk_rows > 0) {
-                        tma_g2s(k_s + (size_t)stage * kAttTile * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
-                        tma_g2s(v_s + (size_t)stage * kAttTile * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                        tma_g2s(k_s + (size_t)stage * AT * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                        tma_g2s(v_s + (size_t)stage * AT * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
                     }
                 }
             };
@@ -835,8 +836,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
 
             if (att_single) {
                 const int nrows = att_rows;
-                auto krow = [&](int r) -> const uint8_t* { return r < 2 * kAttTile ? k_s + (size_t)r * stride : tail_k + (size_t)(r - 2 * kAttTile) * row_bytes; };
-                auto vrow = [&](int r) -> const uint8_t* { return r < 2 * kAttTile ? v_s + (size_t)r * stride : tail_v + (size_t)(r - 2 * kAttTile) * row_bytes; };
+                auto krow = [&](int r) -> const uint8_t* { return r < 2 * AT ? k_s + (size_t)r * stride : tail_k + (size_t)(r - 2 * AT) * row_bytes; };
+                auto vrow = [&](int r) -> const uint8_t* { return r < 2 * AT ? v_s + (size_t)r * stride : tail_v + (size_t)(r - 2 * AT) * row_bytes; };
                 if (pos >= t0 && pos < t1 && warp == 1) {   // the newest row (generic stores of this launch) bypasses the async proxy
                     const size_t g_off = head_off + (size_t)pos * row_bytes;
                     for (int c = lane; c < cpr; c += 32) {
@@ -845,7 +846,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                     }
                 }
                 if (nrows > 0) { mb_wait_fast(att_bar, kv_use0 & 1); kv_use0++; }
-                if (nrows > kAttTile) { mb_wait_fast(att_bar + 1, kv_use1 & 1); kv_use1++; }
+                if (nrows > AT) { mb_wait_fast(att_bar + 1, kv_use1 & 1); kv_use1++; }
                 if (att_tail > 0) { mb_wait_fast(att_bar + 2, kv_use2 & 1); kv_use2++; }
                 __syncthreads();
 #pragma unroll 1
@@ -908,14 +909,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
 #pragma unroll 1
             for (int tile = 0; tile < ntiles; ++tile) {
                 const int stage = tile & 1;
-                const int ts = t0 + tile * kAttTile;
-                const int rows = min(kAttTile, t1 - ts);
+                const int ts = t0 + tile * AT;
+                const int rows = min(AT, t1 - ts);
                 if (pos >= ts && pos < ts + rows && warp == 1) {   // the newest row (generic stores of this launch) bypasses the async proxy
                     const size_t g_off = head_off + (size_t)pos * row_bytes;
                     for (int c = lane; c < cpr; c += 32) {
-                        *reinterpret_cast<uint4*>(k_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                        *reinterpret_cast<uint4*>(k_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) =
                             __ldcg(reinterpret_cast<const uint4*>(p.kc + g_off + c * 16));
-                        *reinterpret_cast<uint4*>(v_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) =
+                        *reinterpret_cast<uint4*>(v_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) =
                             __ldcg(reinterpret_cast<const uint4*>(p.vc + g_off + c * 16));
                     }
                 }
@@ -927,7 +928,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
 #pragma unroll
                     for (int gi = 0; gi < G; ++gi) s[gi] = 0.f;
                     if (key < rows) {
-                        const uint8_t* krow = k_s + ((size_t)stage * kAttTile + key) * stride;
+                        const uint8_t* krow = k_s + ((size_t)stage * AT + key) * stride;
                         for (int c = kpart; c < cpr; c += 8) {
                             float kf[KVEC];
                             kv_unpack<KVD>(*reinterpret_cast<const uint4*>(krow + c * 16), kf);
@@ -969,7 +970,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega2_step_kernel(const Mega2
                     }
                     for (int r = pv_stripe; r < rows; r += kStripes) {
                         float vf[KVEC];
-                        kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * kAttTile + r) * stride + pv_chunk * 16), vf);
+                        kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * AT + r) * stride + pv_chunk * 16), vf);
 #pragma unroll
                         for (int gi = 0; gi < G; ++gi) {
                             const float pr = p_s[gi * kAttTile + r];

@@ -158,7 +158,8 @@ def test_medium_shape_tokens(port, mega):
     blob = port.fill_blob(oracle_shape(ms), 3, BF16)
     want, want_l = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1).greedy(list(range(1, 33)), 150)
     eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(3)
-    # fp32 K/V tiles of 128-wide heads do not fit any megakernel's staging area: every mega flavour falls back to the per-kernel path here
+    # fp32 cache rows of 128-wide heads (the parity-mode cache on the production shapes): in the megakernels since round 2 (K/V stages of 32 positions)
+    assert eng.mode == {True: "megakernel", False: "fused+graph", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega], eng.mode
     got = eng.greedy(list(range(1, 33)), 150)
     assert np.array_equal(got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
@@ -312,4 +313,25 @@ def test_calibrated_partition_keeps_results(port, v2):
     if not v2:
         assert np.array_equal(logits_before, logits_after)
     assert float(np.abs(logits_after - want_l).max()) <= logit_tol(want_l)
+    eng.close()
+
+
+@pytest.mark.parametrize("mega", [True, "v2fuse"])
+def test_fp32_kv_wide_heads_long_context(port, mega):
+    """fp32 cache + 128-wide heads (512-byte rows: K/V stages of 32 positions) far enough into the context that a split spans several
+    stages (the tile loop, not the single-pass path): 8 kv heads -> 18 splits of ~100 positions at position 1800. Teacher-forced on a
+    random prompt, then the logits of the last prompt position and 12 greedy tokens against the oracle."""
+    ms = ModelShape(2048, 128, 1024, 1024, 1408, 1900, 2, 8, 8)
+    blob = port.fill_blob(oracle_shape(ms), 17, BF16)
+    prompt = np.random.default_rng(4).integers(1, ms.vocab, size=1800, dtype=np.int32)
+    om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1)
+    want, want_l = om.greedy(prompt, 1812)
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=True, mega_v2=(mega == "v2fuse"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(17)
+    assert eng.mode == ("megakernel" if mega is True else "megakernel(v2,fused-down)"), eng.mode
+    got = eng.greedy(prompt, 1812)
+    err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max()) / max(1.0, float(np.abs(want_l).max()))
+    same = int(np.argmax(got != want)) if (got != want).any() else got.size
+    print(f"\nfp32 KV, hd 128, 1811 positions [{eng.mode}]: identical prefix {same}/{got.size}, final logits within {err:.1e} of max|logit|")
+    assert same >= 1799 + 6, same          # the echo of the prompt and at least the first generated tokens
+    assert err <= 5e-3, err
     eng.close()

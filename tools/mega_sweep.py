@@ -5,13 +5,15 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from simplellminference_b200 import _lib
-from simplellminference_b200.config import PRESETS, BF16
+from simplellminference_b200.config import PRESETS, BF16, F32, INT8
 from simplellminference_b200.engine import Engine
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--steps", type=int, default=24)
+ap.add_argument("--wdtype", default="bf16"); ap.add_argument("--kvdtype", default="bf16")
 ap.add_argument("--variants", default="v1,v2f,v2f+cal"); ap.add_argument("--debug", default="0", help="comma list of sllm_tune(8) values (megakernel2 A/B bits: 4 = scalar wo reductions, 8 = one x replica)")
 a = ap.parse_args()
 ms = PRESETS[a.config]
+WD = {"f32": F32, "bf16": BF16, "int8": INT8}[a.wdtype]; KVD = {"f32": F32, "bf16": BF16}[a.kvdtype]
 lib = _lib.load()
 try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -20,7 +22,7 @@ except Exception:
 KW = {"v1": {}, "v1f": dict(mega_fuse_down=True), "v2": dict(mega_v2=True), "v2f": dict(mega_v2=True, mega_fuse_down=True), "ll": dict(mega_ll=True)}
 for var in a.variants.split(","):
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True, **KW[var.split("+")[0]]).load_synthetic(1234)
+    eng = Engine(ms, w_dtype=WD, kv_dtype=KVD, stream=stream, mega=True, **KW[var.split("+")[0]]).load_synthetic(1234)
     if var.endswith("+cal"):
         eng.calibrate(3)
         tau = eng.calibration()

@@ -23,6 +23,10 @@ for s in "$@"; do
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
     libab)     for v in "" _phsmem _nosp ""; do step 300 "libab${v:-_base}_$RANDOM" env SLLM_LIB=$PWD/simplellminference_b200/lib/libsllm_b200$v.so python tools/mega_sweep.py --variants v2f+cal --debug 0,0; done ;;
+    sweep_small) step 300 sweep_tiny python tools/mega_sweep.py --config tinyllama-1.1b --pos 1700 --variants v1,v1+cal,v1f,v2,v2+cal,v2f,v2f+cal --debug 0
+               step 300 sweep_110m python tools/mega_sweep.py --config stories110M --wdtype f32 --kvdtype f32 --pos 128 --variants v1,v1+cal,v2,v2+cal --debug 0
+               step 300 sweep_8b python tools/mega_sweep.py --config llama3-8b --pos 7800 --variants v1,v2f,v2f+cal --debug 0 ;;
+    enginetests) step 900 enginetests python -m pytest tests/test_engine_gpu.py -q -s ;;
     sweep_ab)  step 400 mega_sweep_ab python tools/mega_sweep.py --variants v2f+cal --debug 0,4,8,12,0 ;;
     san_*)     c=${s#san_}; tool=${c%%:*}; case_=${c#*:}; step 600 "sanitize_${tool}_${case_}" env SLLM_COMPARE=0 compute-sanitizer --tool "$tool" --print-limit 30 python tools/sanitize_case.py "$case_" ;;
     case_*)    step 300 "case_${s#case_}" python tools/sanitize_case.py "${s#case_}" ;;
@@ -31,6 +35,17 @@ for s in "$@"; do
                step 600 ncu_v2f_full ncu --set full --clock-control none --import-source on -k regex:mega2_step -s 30 -c 1 -o "$OUT/r02_mega2_v2f" -f $PS ;;
     ncu_bench) step 600 ncu_bench_launches ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mega|pf_|embed|rmsnorm' -c 3000 --csv --log-file "$OUT/r02_bench_launches.csv" python bench.py --steps 20 --warmup 5 --no-cpu-baseline ;;
     tp*)       n=${s#tp}; step 900 "tp${n}_check" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29600 + n)) tests/tp_check.py ;;
+    cfgs)      step 300 bench_cfg2 python bench.py --config stories110M --wdtype f32 --kvdtype f32 --prompt-len 128 --no-cpu-baseline
+               step 300 bench_cfg3_bf16 python bench.py --config tinyllama-1.1b --prompt-len 1700 --no-cpu-baseline
+               step 300 bench_cfg3_int8 python bench.py --config tinyllama-1.1b --wdtype int8 --prompt-len 1700 --no-cpu-baseline
+               step 400 bench_cfg5 python bench.py --config llama3-8b --prompt-len 7800 --steps 64 --no-cpu-baseline
+               step 300 bench_7b_int8 python bench.py --wdtype int8 --no-cpu-baseline
+               for n in cfg2 cfg3_bf16 cfg3_int8 cfg5 7b_int8; do grep -h '^{' "$OUT/bench_$n.log" | tail -1 > "$OUT/bench_$n.json"; done ;;
+    batchb)    step 400 batch_bench python tools/batch_bench.py --batches 1,4,8,16 --exp-batches 8,16 --variants plain,graph,graph+rows4,graph+rows4+ksplit --json ;;
+    ncu_pf)    PB="python tools/prefill_bench.py --tokens 512 --reps 2"
+               step 120 ncu_pf_plain $PB
+               step 600 ncu_pf_gemm ncu --set full --clock-control none --import-source on -k regex:pf_gemm_kernel -s 300 -c 8 -o "$OUT/r02_pf_gemm" -f $PB
+               step 400 ncu_pf_attn ncu --set full --clock-control none --import-source on -k regex:pf_attn_kernel -s 40 -c 2 -o "$OUT/r02_pf_attn" -f $PB ;;
     pprobe)    step 120 prefetch_probe tools/microbench/_build/prefetch_probe ;;
     cprobe)    step 120 consumer_probe tools/microbench/_build/consumer_probe ;;
     v2tests)   step 900 v2tests python -m pytest tests/test_engine_gpu.py -q -k "v2" ;;
