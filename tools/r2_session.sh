@@ -27,6 +27,10 @@ for s in "$@"; do
                step 300 sweep_110m python tools/mega_sweep.py --config stories110M --wdtype f32 --kvdtype f32 --pos 128 --variants v1,v1+cal,v2,v2+cal --debug 0
                step 300 sweep_8b python tools/mega_sweep.py --config llama3-8b --pos 7800 --variants v1,v2f,v2f+cal --debug 0 ;;
     enginetests) step 900 enginetests python -m pytest tests/test_engine_gpu.py -q -s ;;
+    steal)     step 300 case_v2fs_7b2 python tools/sanitize_case.py v2fs_7b2
+               step 300 case_v2fs_7b2s python tools/sanitize_case.py v2fs_7b2s
+               step 300 sweep_steal python tools/mega_sweep.py --variants v2f+cal,v2fs+cal,v2f+cal,v2fs+cal --debug 0,0
+               step 200 mega_trace_steal python tools/mega_trace.py --v2 --fuse-down --calibrate --steal ;;
     sweep_ab)  step 400 mega_sweep_ab python tools/mega_sweep.py --variants v2f+cal --debug 0,4,8,12,0 ;;
     san_*)     c=${s#san_}; tool=${c%%:*}; case_=${c#*:}; step 600 "sanitize_${tool}_${case_}" env SLLM_COMPARE=0 compute-sanitizer --tool "$tool" --print-limit 30 python tools/sanitize_case.py "$case_" ;;
     case_*)    step 300 "case_${s#case_}" python tools/sanitize_case.py "${s#case_}" ;;
