@@ -100,6 +100,7 @@ const int32_t* sllm_kvpages_table(const sllm_kvpages* kp) { return kp ? kp->tabl
 constexpr int kBatchMaxSeqs = 64;
 
 struct sllm_batch {
+    bool poisoned = false;   // a step failed between its launches (a CUDA error): the device-side positions no longer match the host's; only destroy is allowed
     EngineView ev{};
     cudaStream_t stream = nullptr;
     int max_seqs = 0, kv_dtype = SLLM_BF16, esz_kv = 2;
@@ -551,6 +552,7 @@ int sllm_batch_set_sampling(sllm_batch* b, int32_t slot, float temperature, int3
 
 int sllm_batch_step(sllm_batch* b, int32_t n_steps) {
     SLLM_REQUIRE(b && n_steps >= 0, SLLM_EINVAL, "batch_step: bad argument");
+    SLLM_REQUIRE(!b->poisoned, SLLM_ESTATE, "batch_step: an earlier step of this batch failed between its launches; destroy the batch");
     const int hi = live_hi(b);
     if (hi == 0 || n_steps == 0) return SLLM_OK;
     // pages for every position the n steps will write, for all slots or for none
@@ -573,7 +575,7 @@ int sllm_batch_step(sllm_batch* b, int32_t n_steps) {
                                   cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before the call returns
     }
     for (int i = 0; i < n_steps; ++i) {
-        if (int rc = batch_step_once(b, hi)) return rc;
+        if (int rc = batch_step_once(b, hi)) { b->poisoned = true; return rc; }   // pages already taken stay with their slots (released on remove)
         for (int s = 0; s < hi; ++s)
             if (b->host_pos[s] >= 0) b->host_pos[s] += 1;
     }
