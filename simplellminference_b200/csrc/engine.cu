@@ -777,6 +777,7 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
     if ((cfg->flags & SLLM_ENGINE_MEGAKERNEL) && e->fused) {
         if (tp == 1 ? (cfg->flags & SLLM_ENGINE_MEGA_LL) != 0 : (cfg->flags & SLLM_ENGINE_P2P_ALLREDUCE) != 0) {
             e->ll_plan = mega_ll_plan(cfg->w_dtype, cfg->kv_dtype, e->d, e->hd, e->q_loc, e->kv_loc, e->I_loc, e->V_loc, e->v0, e->H_loc, e->KVH_loc, e->S, tp);
+            if (cfg->w_dtype == SLLM_INT8 && cfg->group != 64) { e->ll_plan.ok = false; e->ll_plan.why = "int8 group size other than 64"; }   // the tile format carries one scale per 4 chunks
             e->mega_ll = e->mega = e->ll_plan.ok;
         }
         if (!e->mega && tp == 1) {
@@ -1079,13 +1080,14 @@ extern "C" int sllm_engine_calibrate(sllm_engine* e, int32_t rounds) {
             }
         }
         if (rc) break;
-        std::vector<double> tau((size_t)ncta, 1.0);
+        // CTAs without a sample (a small model: fewer tile rows in every phase than CTAs) keep the mean share
+        std::vector<double> tau((size_t)ncta, 0.0);
         double mean = 0.0;
         int cnt = 0;
         for (int c = 0; c < ncta; ++c) if (B[c] > 0.0) { tau[c] = T[c] / B[c]; mean += tau[c]; cnt++; }
-        SLLM_REQUIRE(cnt == ncta && mean > 0.0, SLLM_ESTATE, "calibrate: the timeline of %d of %d CTAs is empty", ncta - cnt, ncta);
+        if (cnt == 0 || !(mean > 0.0)) { set_error("calibrate: the kernel's timeline is empty"); rc = SLLM_ESTATE; break; }
         mean /= cnt;
-        for (double& t : tau) t = std::min(1.25, std::max(0.8, t / mean));
+        for (double& t : tau) t = (t > 0.0) ? std::min(1.25, std::max(0.8, t / mean)) : 1.0;
         e->calib_tau = tau;
         // one table per distinct item count, then every phase points at its table
         tables.clear();

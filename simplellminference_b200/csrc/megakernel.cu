@@ -1033,6 +1033,7 @@ int sllm_mega_plan(const sllm_shape* shape, int32_t w_dtype, int32_t group, int3
         const MegaLLPlan ll = mega_ll_plan_for(sms, smem, w_dtype, kv_dtype, shape->hidden, shape->head_dim, H_loc * shape->head_dim,
                                                KVH_loc * shape->head_dim, shape->inter / tp_size, shape->vocab / tp_size, 0, H_loc, KVH_loc,
                                                shape->max_len, tp_size);
+        if (ll.ok && w_dtype == SLLM_INT8 && group != 64) { *ok = 0; set_error("the word-based megakernel cannot take this shape: int8 group size other than 64"); return SLLM_OK; }
         *ok = ll.ok ? 1 : 0;
         if (grid) *grid = ll.grid;
         if (smem_bytes) *smem_bytes = (int64_t)ll.smem;

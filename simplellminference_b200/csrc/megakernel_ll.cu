@@ -29,6 +29,7 @@ namespace sllm {
 struct MegaLLSmem {
     size_t bars, red, part, ring, resid, att_q, att_p, att_misc, att_k, att_v, total;
     int kv_stride;
+    int att_tile;   // cache positions per K/V stage (mega_att_tile: 32 when a row is wider than 256 bytes, else 64)
 };
 __host__ __device__ inline MegaLLSmem mega_ll_smem_layout(int d, int hd, int g, int kv_esz) {
     MegaLLSmem L;
@@ -46,8 +47,9 @@ __host__ __device__ inline MegaLLSmem mega_ll_smem_layout(int d, int hd, int g, 
     L.resid = off; off += (size_t)d * 4;
     off = (off + 127) & ~(size_t)127;
     L.kv_stride = hd * kv_esz;
-    L.att_k = off; off += (size_t)2 * kAttTile * L.kv_stride;
-    L.att_v = off; off += (size_t)2 * kAttTile * L.kv_stride;
+    L.att_tile = mega_att_tile(hd, kv_esz);
+    L.att_k = off; off += (size_t)2 * L.att_tile * L.kv_stride;
+    L.att_v = off; off += (size_t)2 * L.att_tile * L.kv_stride;
     L.total = off;
     return L;
 }
@@ -125,10 +127,12 @@ __device__ __forceinline__ unsigned long long ll_gtime() {
 template <int WD, int KVD, int G>
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLParams p) {
     constexpr int E = WInfo<WD>::E;
+    constexpr int CPL = (WD == SLLM_INT8) ? 2 : kCplMax;   // max chunks per lane per row slice (x of a lane: CPL * E = 32 registers)
     constexpr int KESZ = MKv<KVD>::ESZ, KVEC = MKv<KVD>::VEC;
     extern __shared__ __align__(128) uint8_t mega_ll_smem[];
     uint8_t* const smem = mega_ll_smem;
     const MegaLLSmem SL = mega_ll_smem_layout(p.d, p.hd, G, KESZ);
+    const int AT = SL.att_tile;                      // cache positions per K/V stage
     uint64_t* ring_bar = reinterpret_cast<uint64_t*>(smem + SL.bars);
     uint64_t* att_bar = ring_bar + kMegaWarps * kSlots;
     float* red = reinterpret_cast<float*>(smem + SL.red);
@@ -211,11 +215,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             for (int c = tid; c < ph.nchunks; c += kMegaThreads) {
                 const int eks = c / em.SC, ecc = c - eks * em.SC;
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(trow + (size_t)eks * em.tile_bytes + (size_t)ecc * 16));
-                float f[8];
+                float f[E];
                 if (WD == SLLM_F32) {
                     f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y); f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
-                } else {
+                } else if (WD == SLLM_BF16) {
                     kv_unpack<SLLM_BF16>(raw, f);
+                } else {   // int8: dequantised value = q * group scale (the scales sit behind the tile's weights)
+                    const uint8_t* tile = p.emb + ((size_t)(token / em.R) * em.KS + eks) * em.tile_bytes;
+                    const float sc = __ldg(reinterpret_cast<const float*>(tile + (size_t)em.R * em.SC * 16 + (size_t)(token % em.R) * em.srow) + (ecc >> 2));
+                    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t wf = w4[k] ^ 0x80808080u;
+                        f[4 * k] = s8f<0>(wf) * sc; f[4 * k + 1] = s8f<1>(wf) * sc; f[4 * k + 2] = s8f<2>(wf) * sc; f[4 * k + 3] = s8f<3>(wf) * sc;
+                    }
                 }
 #pragma unroll
                 for (int ee = 0; ee < E; ++ee) { resid_s[c * E + ee] = f[ee]; ss = fmaf(f[ee], f[ee], ss); }
@@ -319,11 +332,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 reinterpret_cast<float4*>(xs)[c4] = ll_recv4(my_area + p.off_swi + 4 * c4, e);
         }
         // norm weights of this lane's columns (requested now so the loads overlap the reduction below)
-        float nwr[kCplMax][E];
+        float nwr[CPL][E];
         if (normed) {
             const float* nw = p.norms + (size_t)(ph.kind == PH_QKV ? 2 * l : ph.kind == PH_GATEUP ? 2 * l + 1 : 2 * p.L) * p.d;
 #pragma unroll
-            for (int i = 0; i < kCplMax; ++i) {
+            for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i;
 #pragma unroll
                 for (int e4 = 0; e4 < E; e4 += 4) {
@@ -346,9 +359,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
         } else {
             __syncthreads();
         }
-        float xr[kCplMax][E];
+        float xr[CPL][E];
 #pragma unroll
-        for (int i = 0; i < kCplMax; ++i) {
+        for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
 #pragma unroll
             for (int ee = 0; ee < E; ++ee) xr[i][ee] = 0.f;
@@ -378,14 +391,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 const int t0 = split * per, t1 = min(npos, t0 + per);
                 const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;
                 for (int tile = 0; tile < 2; ++tile) {
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     if (rows <= 0) break;
                     const int bulk_rows = max(0, min(rows, pos - ts));
                     mb_expect(att_bar + tile, (uint32_t)(2 * bulk_rows * row_bytes));
                     if (bulk_rows > 0) {
-                        tma_g2s(smem + SL.att_k + (size_t)tile * kAttTile * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
-                        tma_g2s(smem + SL.att_v + (size_t)tile * kAttTile * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_k + (size_t)tile * AT * row_bytes, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
+                        tma_g2s(smem + SL.att_v + (size_t)tile * AT * row_bytes, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + tile);
                     }
                 }
             }
@@ -413,9 +426,27 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 mb_wait_fast(my_bar + si, (cons_count / kSlots) & 1);
                 const uint8_t* sp = my_ring + (size_t)si * kSlotBytes + lane * 16;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                if (upp == 2) {
+                if (WD == SLLM_INT8) {
+                    // 16 int8 weights per chunk (exact int8 -> fp32 by byte permute); the chunk's group scale (one fp32 per 4 chunks,
+                    // stored behind the tile's weights) multiplies the chunk's partial sum — the same arithmetic as megakernel.cu
+                    const uint8_t* sc_base = sp - lane * 16 + (size_t)ph.R * sbytes;
 #pragma unroll
-                    for (int i = 0; i < kCplMax; ++i) {
+                    for (int i = 0; i < CPL; ++i) {
+                        const int c = lane + 32 * i;
+                        if (i < cpl && c < nsc) {
+                            const uint8_t* q = sp + i * 512;
+                            const float* scp = reinterpret_cast<const float*>(sc_base) + (c >> 2);
+                            a0 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], 0.f), scp[0], a0);
+                            a1 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + sbytes), xr[i], 0.f), scp[ph.srow >> 2], a1);
+                            if (upp == 2) {
+                                a2 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 2 * sbytes), xr[i], 0.f), scp[2 * (ph.srow >> 2)], a2);
+                                a3 = fmaf(reg_dot<WD>(*reinterpret_cast<const uint4*>(q + 3 * sbytes), xr[i], 0.f), scp[3 * (ph.srow >> 2)], a3);
+                            }
+                        }
+                    }
+                } else if (upp == 2) {
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
                         if (i < cpl && lane + 32 * i < nsc) {
                             const uint8_t* q = sp + i * 512;
                             a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
@@ -426,7 +457,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < kCplMax; ++i) {
+                    for (int i = 0; i < CPL; ++i) {
                         if (i < cpl && lane + 32 * i < nsc) {
                             const uint8_t* q = sp + i * 512;
                             a0 = reg_dot<WD>(*reinterpret_cast<const uint4*>(q), xr[i], a0);
@@ -605,7 +636,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
             for (int item = cta; item < nitems; item += ncta) {
                 const int kvh = item / nsplit, split = item - kvh * nsplit;
                 const int t0 = split * per, t1 = min(npos, t0 + per);
-                const int ntiles = (t1 > t0) ? (t1 - t0 + kAttTile - 1) / kAttTile : 0;
+                const int ntiles = (t1 > t0) ? (t1 - t0 + AT - 1) / AT : 0;
                 // q of this KV head's query heads: words written by phase A's epilogues (any CTA)
                 for (int i = 2 * tid; i < G * p.hd; i += 2 * kMegaThreads) {
                     const float2 v = ll_recv2(my_area + p.off_qv + (int64_t)(kvh * G) * p.hd + i, e);
@@ -615,14 +646,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 const size_t head_off = ((size_t)l * p.KVH_loc + kvh) * p.S * row_bytes;
                 auto issue_tile = [&](int tile) {
                     const int stage = tile & 1;
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     const int bulk_rows = max(0, min(rows, pos - ts));
                     if (lane == 0) {
                         mb_expect(att_bar + stage, (uint32_t)(2 * bulk_rows * row_bytes));
                         if (bulk_rows > 0) {
-                            tma_g2s(k_s + (size_t)stage * kAttTile * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
-                            tma_g2s(v_s + (size_t)stage * kAttTile * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                            tma_g2s(k_s + (size_t)stage * AT * stride, p.kc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
+                            tma_g2s(v_s + (size_t)stage * AT * stride, p.vc + head_off + (size_t)ts * row_bytes, bulk_rows * row_bytes, att_bar + stage);
                         }
                     }
                 };
@@ -641,8 +672,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
 #pragma unroll 1
                 for (int tile = 0; tile < ntiles; ++tile) {
                     const int stage = tile & 1;
-                    const int ts = t0 + tile * kAttTile;
-                    const int rows = min(kAttTile, t1 - ts);
+                    const int ts = t0 + tile * AT;
+                    const int rows = min(AT, t1 - ts);
                     // the newest row arrives as words from phase A's epilogues (values already rounded to the cache type)
                     if (pos >= ts && pos < ts + rows && warp == 1) {
                         for (int c = lane; c < cpr; c += 32) {
@@ -667,8 +698,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                                 kw = make_uint4(pk(kf[0], kf[1]), pk(kf[2], kf[3]), pk(kf[4 % KVEC], kf[5 % KVEC]), pk(kf[6 % KVEC], kf[7 % KVEC]));
                                 vw = make_uint4(pk(vf[0], vf[1]), pk(vf[2], vf[3]), pk(vf[4 % KVEC], vf[5 % KVEC]), pk(vf[6 % KVEC], vf[7 % KVEC]));
                             }
-                            *reinterpret_cast<uint4*>(k_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) = kw;
-                            *reinterpret_cast<uint4*>(v_s + ((size_t)stage * kAttTile + (pos - ts)) * stride + c * 16) = vw;
+                            *reinterpret_cast<uint4*>(k_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) = kw;
+                            *reinterpret_cast<uint4*>(v_s + ((size_t)stage * AT + (pos - ts)) * stride + c * 16) = vw;
                         }
                     }
                     if (stage == 0) { mb_wait_fast(att_bar, kv_use0 & 1); kv_use0++; }
@@ -679,7 +710,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
 #pragma unroll
                         for (int gi = 0; gi < G; ++gi) s[gi] = 0.f;
                         if (key < rows) {
-                            const uint8_t* krow = k_s + ((size_t)stage * kAttTile + key) * stride;
+                            const uint8_t* krow = k_s + ((size_t)stage * AT + key) * stride;
                             for (int c = kpart; c < cpr; c += 8) {
                                 float kf[KVEC];
                                 kv_unpack<KVD>(*reinterpret_cast<const uint4*>(krow + c * 16), kf);
@@ -721,7 +752,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                         }
                         for (int r = pv_stripe; r < rows; r += kStripes) {
                             float vf[KVEC];
-                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * kAttTile + r) * stride + pv_chunk * 16), vf);
+                            kv_unpack<KVD>(*reinterpret_cast<const uint4*>(v_s + ((size_t)stage * AT + r) * stride + pv_chunk * 16), vf);
 #pragma unroll
                             for (int gi = 0; gi < G; ++gi) {
                                 const float pr = p_s[gi * kAttTile + r];
@@ -774,14 +805,16 @@ MegaLLPlan mega_ll_plan(int w_dtype, int kv_dtype, int d, int hd, int q_loc, int
 MegaLLPlan mega_ll_plan_for(int sms, int smem_optin, int w_dtype, int kv_dtype, int d, int hd, int q_loc, int kv_loc, int I_loc, int V_loc, int v0,
                             int H_loc, int KVH_loc, int max_len, int tp) {
     MegaLLPlan pl;
-    if (w_dtype == SLLM_INT8) { pl.why = "int8 weights"; return pl; }
     if (tp > kMaxTp) { pl.why = "more than 8 ranks"; return pl; }
-    const int E = w_dtype == SLLM_F32 ? 4 : 8;
+    const int E = w_dtype == SLLM_F32 ? 4 : w_dtype == SLLM_BF16 ? 8 : 16;
     for (int cols : {d, q_loc, I_loc}) {
-        const int nch = cols / E;
-        const int SC = (nch + 15) / 16;
-        if (cols % E || cols % 4) { pl.why = "row length not a multiple of 16 bytes"; return pl; }
-        if (SC * 16 * 2 > kSlotBytes || SC > 32 * kCplMax) { pl.why = "rows longer than 32 KB"; return pl; }
+        // int8: a rank's slice of a row-parallel matrix (q_loc, I_loc columns) must hold whole quantisation groups of 64
+        if (cols % E || cols % 4 || (w_dtype == SLLM_INT8 && cols % 64)) { pl.why = "row length not a multiple of 16 bytes / of the int8 group"; return pl; }
+        const TileGeom tg = mega_tile_geom(2, cols, w_dtype);
+        if (tg.KS * tg.SC < tg.nchunks || (tg.SC * 16 + tg.srow) * 2 > kSlotBytes || tg.SC > 32 * (w_dtype == SLLM_INT8 ? 2 : kCplMax)) {
+            pl.why = "rows longer than 32 KB";
+            return pl;
+        }
     }
     const int g = H_loc / KVH_loc;
     if ((g != 1 && g != 2 && g != 4 && g != 8) || hd % 16 || hd > 256) { pl.why = "head shape"; return pl; }
@@ -790,8 +823,8 @@ MegaLLPlan mega_ll_plan_for(int sms, int smem_optin, int w_dtype, int kv_dtype, 
     const MegaLLSmem SL = mega_ll_smem_layout(d, hd, g, kesz);
     if (SL.total + 1024 > (size_t)smem_optin) { pl.why = "shared memory"; return pl; }
     if ((size_t)g * hd * 4 + (size_t)g * kAttTile * 4 + 256 > (size_t)kRoundUnits * 2 * kMegaWarps * 4) { pl.why = "attention scratch (q/p)"; return pl; }
-    if ((size_t)16 * g * hd * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
-    if ((size_t)std::max(q_loc, I_loc) * 4 > (size_t)4 * kAttTile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
+    if ((size_t)16 * g * hd * 4 > (size_t)4 * SL.att_tile * SL.kv_stride) { pl.why = "attention scratch"; return pl; }   // the cross-stripe reduction buffer spans the (drained, contiguous) K and V stages
+    if ((size_t)std::max(q_loc, I_loc) * 4 > (size_t)4 * SL.att_tile * SL.kv_stride) { pl.why = "activation staging"; return pl; }
     if (q_loc % 4 || kv_loc % 2 || I_loc % 4 || d % 4) { pl.why = "dims not multiples of 4"; return pl; }
     // every CTA must own >= 1 tile row of every weight phase (see the safety argument at the top of this file)
     int grid = sms;
@@ -803,7 +836,7 @@ MegaLLPlan mega_ll_plan_for(int sms, int smem_optin, int w_dtype, int kv_dtype, 
     pl.grid = grid;
     pl.smem = SL.total;
     int ns = std::max(1, grid / KVH_loc);
-    const int by_len = (max_len + kAttTile - 1) / kAttTile;
+    const int by_len = (max_len + SL.att_tile - 1) / SL.att_tile;
     if (ns > by_len) ns = by_len;
     if (ns > 32) ns = 32;
     pl.nsplit = ns;
@@ -850,6 +883,10 @@ int mega_ll_launch(const MegaLLParams& p, int g, int grid, size_t smem, cudaStre
         if (p.w_dtype == SLLM_F32) {                                                                        \
             return p.kv_dtype == SLLM_F32 ? mega_ll_launch_t<SLLM_F32, SLLM_F32, GG>(p, grid, smem, st)     \
                                           : mega_ll_launch_t<SLLM_F32, SLLM_BF16, GG>(p, grid, smem, st);   \
+        }                                                                                                   \
+        if (p.w_dtype == SLLM_INT8) {                                                                       \
+            return p.kv_dtype == SLLM_F32 ? mega_ll_launch_t<SLLM_INT8, SLLM_F32, GG>(p, grid, smem, st)    \
+                                          : mega_ll_launch_t<SLLM_INT8, SLLM_BF16, GG>(p, grid, smem, st);  \
         }                                                                                                   \
         return p.kv_dtype == SLLM_F32 ? mega_ll_launch_t<SLLM_BF16, SLLM_F32, GG>(p, grid, smem, st)        \
                                       : mega_ll_launch_t<SLLM_BF16, SLLM_BF16, GG>(p, grid, smem, st);

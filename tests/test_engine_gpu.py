@@ -44,13 +44,12 @@ def test_golden_models(golden_models, name, mode):
               mega_ll=dict(mega=True, mega_ll=True), fused_graph={}, fused_graph_pdl=dict(pdl=True), fused_nograph=dict(graph=False), unfused=dict(fused=False))[mode]
     eng = Engine(ms, w_dtype=wd, kv_dtype=F32, group=64, **kw).load_synthetic(mg.SEED)
     if mode.startswith("mega"):
-        # int8 group-64 tiles are streamed by the grid-barrier megakernel only: asking for another one falls back to it, visibly
         rb = ms.hidden * (4 if wd == F32 else 2)   # mega_fuse_down_ok: a row of outputs = 2^k stripes of 512 bytes
         fuse_ok = wd != INT8 and rb % 512 == 0 and (rb // 512) & (rb // 512 - 1) == 0 and rb // 512 <= 16 and ms.inter % 4 == 0
         want_mode = {"mega": "megakernel", "mega_ll": "megakernel(ll)", "mega_v2": "megakernel(v2)",
                      "mega_v2_fuse": "megakernel(v2,fused-down)" if fuse_ok else "megakernel(v2)"}[mode]
-        if wd == INT8:
-            want_mode = "megakernel"
+        if wd == INT8:   # int8 group-64 tiles: the grid-barrier kernel and the word-based one stream them, megakernel2 falls back (visibly)
+            want_mode = "megakernel(ll)" if mode == "mega_ll" else "megakernel"
         assert eng.mode == want_mode, eng.mode
     want = golden_models[name + "/tokens"]
     want_l = golden_models[name + "/last_logits"]
@@ -203,10 +202,15 @@ def test_int8_megakernel_shapes(port):
         assert err <= logit_tol(want_l), err
         ref = Engine(ms, w_dtype=INT8, kv_dtype=F32, group=64, mega=False).load_synthetic(seed)   # per-kernel int8 path: same tokens
         assert np.array_equal(ref.greedy([1, 2, 3, 4], 70), want)
-        eng.close(); ref.close()
+        ll = Engine(ms, w_dtype=INT8, kv_dtype=F32, group=64, mega=True, mega_ll=True).load_synthetic(seed)   # the word-based kernel (the tensor-parallel one)
+        assert ll.mode == "megakernel(ll)", ll.mode
+        got = ll.greedy([1, 2, 3, 4], 70)
+        assert np.array_equal(got, want), (int(np.flatnonzero(got != want)[0]), got[:8], want[:8])
+        assert float(np.abs(ll.buffer("model_pred").cpu().numpy() - want_l).max()) <= logit_tol(want_l)
+        eng.close(); ref.close(); ll.close()
 
 
-@pytest.mark.parametrize("wd,mega", [(BF16, True), (INT8, True), (BF16, False), (BF16, "v2"), (BF16, "v2fuse")])
+@pytest.mark.parametrize("wd,mega", [(BF16, True), (INT8, True), (BF16, False), (BF16, "v2"), (BF16, "v2fuse"), (INT8, "ll")])
 def test_full_width_llama2_7b_two_layers(port, wd, mega):
     """The Llama-2-7B WIDTHS (d 4096, inter 11008, vocab 32000, 32 heads of 128) with 2 layers: the tile geometry the bench runs on
     (K = 11008 -> 16 K slices of 86 chunks, 2-row tiles; int8: 88 chunks) checked against the oracle, which the small shapes cannot
@@ -219,8 +223,9 @@ def test_full_width_llama2_7b_two_layers(port, wd, mega):
     blob = port.fill_blob(oracle_shape(ms), 10, wd, 64, threads=os.cpu_count() or 1)
     om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1, kv_bf16=True)
     want, want_l = om.greedy([1, 2, 3], 14)
-    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(10)
-    assert eng.mode == {True: "megakernel", False: "fused+graph", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)"}[mega], eng.mode
+    eng = Engine(ms, w_dtype=wd, kv_dtype=BF16, group=64, mega=bool(mega), mega_v2=str(mega).startswith("v2"), mega_fuse_down=(mega == "v2fuse"),
+                 mega_ll=(mega == "ll")).load_synthetic(10)
+    assert eng.mode == {True: "megakernel", False: "fused+graph", "v2": "megakernel(v2)", "v2fuse": "megakernel(v2,fused-down)", "ll": "megakernel(ll)"}[mega], eng.mode
     got = eng.greedy([1, 2, 3], 14)
     assert np.array_equal(got, want), (got, want)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max())
@@ -316,7 +321,7 @@ def test_calibrated_partition_keeps_results(port, v2):
     eng.close()
 
 
-@pytest.mark.parametrize("mega", [True, "v2fuse"])
+@pytest.mark.parametrize("mega", [True, "v2fuse", "ll"])
 def test_fp32_kv_wide_heads_long_context(port, mega):
     """fp32 cache + 128-wide heads (512-byte rows: K/V stages of 32 positions) far enough into the context that a split spans several
     stages (the tile loop, not the single-pass path): 8 kv heads -> 18 splits of ~100 positions at position 1800. Teacher-forced on a
@@ -326,8 +331,8 @@ def test_fp32_kv_wide_heads_long_context(port, mega):
     prompt = np.random.default_rng(4).integers(1, ms.vocab, size=1800, dtype=np.int32)
     om = port.model(oracle_shape(ms), blob, threads=os.cpu_count() or 1)
     want, want_l = om.greedy(prompt, 1812)
-    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=True, mega_v2=(mega == "v2fuse"), mega_fuse_down=(mega == "v2fuse")).load_synthetic(17)
-    assert eng.mode == ("megakernel" if mega is True else "megakernel(v2,fused-down)"), eng.mode
+    eng = Engine(ms, w_dtype=BF16, kv_dtype=F32, mega=True, mega_v2=(mega == "v2fuse"), mega_fuse_down=(mega == "v2fuse"), mega_ll=(mega == "ll")).load_synthetic(17)
+    assert eng.mode == {True: "megakernel", "v2fuse": "megakernel(v2,fused-down)", "ll": "megakernel(ll)"}[mega], eng.mode
     got = eng.greedy(prompt, 1812)
     err = float(np.abs(eng.buffer("model_pred").cpu().numpy() - want_l).max()) / max(1.0, float(np.abs(want_l).max()))
     same = int(np.argmax(got != want)) if (got != want).any() else got.size

@@ -89,13 +89,13 @@ def test_query_head_groups_that_are_not_instantiated_fall_back():
 
 
 def test_word_based_kernel_plans():
-    """The barrier-free kernel: no int8 weights; on one GPU it takes the headline shape too (opt-in SLLM_ENGINE_MEGA_LL); its grid
-    shrinks to the smallest phase's tile rows when a shard has fewer of them than SMs."""
+    """The barrier-free kernel: on one GPU it takes the headline shape too (opt-in SLLM_ENGINE_MEGA_LL), with bf16 or int8 group-64
+    tiles; its grid shrinks to the smallest phase's tile rows when a shard has fewer of them than SMs."""
     ms = PRESETS["llama2-7b"]
     ok, grid, nbytes, nsplit, why = plan(ms, BF16, BF16, word_based=1)
     assert ok and grid == B200_SMS and nbytes + 1024 <= B200_SMEM, why
-    ok, *_, why = plan(ms, INT8, BF16, word_based=1)
-    assert not ok and "int8" in why
+    ok, grid, nbytes, nsplit, why = plan(ms, INT8, BF16, word_based=1)
+    assert ok and grid == B200_SMS, why
     tiny = PRESETS["tiny_gqa"]                       # 128 x 128 wo: 64 two-row units in tiles of four rows = 32 tile rows
     ok, grid, *_ = plan(tiny, F32, F32, word_based=1)
     assert ok and 1 <= grid < B200_SMS

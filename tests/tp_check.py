@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import loader  # noqa: E402
-from simplellminference_b200.config import PRESETS, ModelShape, F32, BF16  # noqa: E402
+from simplellminference_b200.config import PRESETS, ModelShape, F32, BF16, INT8  # noqa: E402
 from simplellminference_b200.engine import Engine  # noqa: E402
 
 
@@ -30,7 +30,11 @@ def main():
              ("medium bf16 weights, bf16 kv (teacher forced)", medium, BF16, BF16, list(range(1, 17)), 120, True),
              ("mha8 bf16 weights, f32 kv", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, F32, list(range(1, 9)), 80, False),
              # 8 kv heads + bf16 cache: the one case in which the word-based megakernel itself (not its fall-back) runs at 8 ranks
-             ("mha8 bf16 weights, bf16 kv (teacher forced)", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, BF16, list(range(1, 9)), 80, True)]
+             ("mha8 bf16 weights, bf16 kv (teacher forced)", ModelShape(4096, 128, 1024, 1024, 2816, 96, 3, 8, 8), BF16, BF16, list(range(1, 9)), 80, True),
+             # int8 group-64 weights: a rank's column block of the row-parallel matrices (wo, down) must hold whole groups
+             # (inter 3072 / 8 ranks = 6 groups); 64-wide heads + fp32 cache -> identical tokens, through the megakernel too
+             ("gqa int8 weights, f32 kv", ModelShape(4096, 64, 1024, 512, 3072, 96, 3, 16, 8), INT8, F32, list(range(1, 9)), 80, False),
+             ("mha8 int8 weights, bf16 kv (teacher forced)", ModelShape(4096, 128, 1024, 1024, 3072, 96, 3, 8, 8), INT8, BF16, list(range(1, 9)), 80, True)]
     import itertools
     for (name, ms, wd, kvd, prompt, n_total, forced), comm in itertools.product(cases, ("nccl", "p2p", "mega")):
         p2p = comm != "nccl"
@@ -43,9 +47,8 @@ def main():
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=p2p, mega=(comm == "mega")).load_synthetic(1234)
-        if comm == "mega":   # fp32 K/V tiles of 128-wide heads do not fit next to the weight rings: that case falls back, visibly
-            fits = not (kvd == F32 and ms.head_dim > 64)
-            assert eng.mode == ("megakernel(ll)" if fits else "fused+graph"), eng.mode
+        if comm == "mega":   # every case runs in the word-based megakernel (fp32 cache rows of 128-wide heads: K/V stages of 32 positions)
+            assert eng.mode == "megakernel(ll)", eng.mode
             name += f" -> {eng.mode}"
         eng = eng.init_p2p(dist) if p2p else eng.init_comm(dist)
         if forced:

@@ -5,8 +5,9 @@ import numpy as np, torch
 from simplellminference_b200.config import PRESETS, BF16
 from simplellminference_b200.engine import Engine
 ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--ll", action="store_true"); ap.add_argument("--fuse-down", action="store_true"); ap.add_argument("--v2", action="store_true"); ap.add_argument("--calibrate", action="store_true")
+ap.add_argument("--config", default="llama2-7b")
 a = ap.parse_args()
-ms = dataclasses.replace(PRESETS["llama2-7b"], layers=a.layers)
+ms = dataclasses.replace(PRESETS[a.config], layers=a.layers)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True, mega_ll=a.ll, mega_fuse_down=a.fuse_down, mega_v2=a.v2).load_synthetic(1)
 if a.calibrate: eng.calibrate(3)

@@ -19,6 +19,8 @@ for s in "$@"; do
     trace_v2)  step 120 mega_trace_v2 python tools/mega_trace.py --v2 ;;
     trace_v2f) step 120 mega_trace_v2f python tools/mega_trace.py --v2 --fuse-down ;;
     trace_v2fc) step 120 mega_trace_v2fc python tools/mega_trace.py --v2 --fuse-down --calibrate ;;
+    int8tests) step 600 int8tests python -m pytest tests/test_engine_gpu.py -q -x -k "int8 or INT8 or wd2 or 2-ll or golden" ;;
+    benchtp*)  n=${s#benchtp}; step 600 "bench_tp${n}" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29700 + n)) bench.py --gpus "$n" --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_tp${n}.log" | tail -1 > "$OUT/bench_tp${n}.json" ;;
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
@@ -50,6 +52,9 @@ for s in "$@"; do
                step 120 ncu_pf_plain $PB
                step 600 ncu_pf_gemm ncu --set full --clock-control none --import-source on -k regex:pf_gemm_kernel -s 300 -c 8 -o "$OUT/r02_pf_gemm" -f $PB
                step 400 ncu_pf_attn ncu --set full --clock-control none --import-source on -k regex:pf_attn_kernel -s 40 -c 2 -o "$OUT/r02_pf_attn" -f $PB ;;
+    smoke)     step 600 smoke python -c 'import __graft_entry__ as g; g.smoke(); print("__SMOKE_OK__")' ;;
+    bench_ref) step 600 bench_ref python bench.py --impl reference --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_ref.log" | tail -1 > "$OUT/bench_ref.json" ;;
+    bench_drv) step 600 bench_drv python bench.py --gpus 1 --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_drv.log" | tail -1 > "$OUT/bench_drv.json" ;;
     pprobe)    step 120 prefetch_probe tools/microbench/_build/prefetch_probe ;;
     cprobe)    step 120 consumer_probe tools/microbench/_build/consumer_probe ;;
     v2tests)   step 900 v2tests python -m pytest tests/test_engine_gpu.py -q -k "v2" ;;
