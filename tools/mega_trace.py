@@ -2,14 +2,14 @@
 import argparse, dataclasses, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from simplellminference_b200.config import PRESETS, BF16
+from simplellminference_b200.config import PRESETS, BF16, F32
 from simplellminference_b200.engine import Engine
 ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4); ap.add_argument("--pos", type=int, default=512); ap.add_argument("--ll", action="store_true"); ap.add_argument("--fuse-down", action="store_true"); ap.add_argument("--v2", action="store_true"); ap.add_argument("--calibrate", action="store_true")
-ap.add_argument("--config", default="llama2-7b")
+ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--wdtype", default="bf16"); ap.add_argument("--kvdtype", default="bf16")
 a = ap.parse_args()
 ms = dataclasses.replace(PRESETS[a.config], layers=a.layers)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, stream=stream, mega=True, mega_ll=a.ll, mega_fuse_down=a.fuse_down, mega_v2=a.v2).load_synthetic(1)
+eng = Engine(ms, w_dtype={'bf16': BF16, 'f32': F32}[a.wdtype], kv_dtype={'bf16': BF16, 'f32': F32}[a.kvdtype], stream=stream, mega=True, mega_ll=a.ll, mega_fuse_down=a.fuse_down, mega_v2=a.v2).load_synthetic(1)
 if a.calibrate: eng.calibrate(3)
 print("mode:", eng.mode, "calibrated" if a.calibrate else "")
 eng.set_state(1, a.pos); eng.enqueue_steps(3); torch.cuda.synchronize()

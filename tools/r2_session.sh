@@ -21,6 +21,10 @@ for s in "$@"; do
     trace_v2fc) step 120 mega_trace_v2fc python tools/mega_trace.py --v2 --fuse-down --calibrate ;;
     int8tests) step 600 int8tests python -m pytest tests/test_engine_gpu.py -q -x -k "int8 or INT8 or wd2 or 2-ll or golden" ;;
     benchtp*)  n=${s#benchtp}; step 600 "bench_tp${n}" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29700 + n)) bench.py --gpus "$n" --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_tp${n}.log" | tail -1 > "$OUT/bench_tp${n}.json" ;;
+    trace_tiny) step 200 mega_trace_tiny_v2 python tools/mega_trace.py --config tinyllama-1.1b --layers 22 --pos 1700 --v2 --calibrate
+               step 200 mega_trace_tiny_v1 python tools/mega_trace.py --config tinyllama-1.1b --layers 22 --pos 1700
+               step 200 mega_trace_110m_v2 python tools/mega_trace.py --config stories110M --wdtype f32 --kvdtype f32 --layers 12 --pos 128 --v2 ;;
+    widetests) step 600 widetests python -m pytest tests/test_engine_gpu.py -q -x -k "wide_heads or int8 or medium" ;;
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
