@@ -57,7 +57,8 @@ int sllm_abi_version(void);
  * key 5 = replay one CUDA graph per live-slot count instead of the launch sequence, key 6 = GEMV body with four weight rows per warp at
  * a time when 3 or more sequences share a launch, key 7 (with key 6) = down projection with K cut in two over grid.y when more sequences
  * are live than whole rows fit shared memory, so that Wdown is read once (all 0 by default: experimental until measured); key 8 = decode
- * megakernel MEASUREMENT aid, results are garbage: bit 0 = skip the grid barriers, bit 1 = skip the dot products (tools/mega_debug.py) */
+ * megakernel MEASUREMENT aid, results are garbage: bit 0 = skip the grid barriers, bit 1 = skip the dot products (tools/mega_debug.py),
+ * bit 4 = tensor-parallel prefill without its peer-memory exchanges (the GEMM / attention time alone) */
 int sllm_tune(int32_t key, int32_t value);
 /* device facts the host side sizes things by: sm count, max opt-in shared memory per block, total/free HBM */
 int sllm_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, size_t* hbm_total, size_t* hbm_free);
@@ -208,6 +209,13 @@ int sllm_engine_init_comm(sllm_engine* e, const void* id_bytes_128);
  * all-gathers them, every rank imports all of them. */
 int sllm_engine_p2p_export(sllm_engine* e, void* handle_bytes_64);
 int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles /* tp_size * 64 bytes */);
+/* Batched prefill under tensor parallelism without a collective library: every rank exports the CUDA-IPC handle of its prefill exchange
+   block and imports everybody's (same messenger protocol as above). From then on sllm_engine_prefill sums the row-parallel partial
+   matrices, adds the residual, normalises and distributes the rows in one kernel over NVLink peer memory (csrc/prefill_tp.cu).
+   SLLM_ENOTSUP: the engine has no such block (one rank, no SLLM_ENGINE_P2P_ALLREDUCE, shape not taken by the batched prefill) — prefill
+   then needs the NCCL communicator. Replaces nothing in the reference (it has neither prefill nor a working multi-GPU build). */
+int sllm_engine_prefill_p2p_export(sllm_engine* e, void* handle_bytes_64);
+int sllm_engine_prefill_p2p_import(sllm_engine* e, const void* all_handles /* tp_size * 64 bytes */);
 
 /* One token, one position: the semantics of LlamaModel::forward(). token/pos by value (host), synchronous.
  * logits_host (vocab floats, may be NULL) receives model_pred; next_token_host (may be NULL) the greedy

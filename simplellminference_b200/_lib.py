@@ -67,6 +67,8 @@ SIGNATURES = {
     "sllm_engine_init_comm": (C.c_int, [_P, _P]),
     "sllm_engine_p2p_export": (C.c_int, [_P, _P]),
     "sllm_engine_p2p_import": (C.c_int, [_P, _P]),
+    "sllm_engine_prefill_p2p_export": (C.c_int, [_P, _P]),
+    "sllm_engine_prefill_p2p_import": (C.c_int, [_P, _P]),
     "sllm_engine_forward": (C.c_int, [_P, _I, _I, _P, _P]),
     "sllm_engine_greedy": (C.c_int, [_P, _P, _I, _I, _P]),
     "sllm_engine_set_state": (C.c_int, [_P, _I, _I]),

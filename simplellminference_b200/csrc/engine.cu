@@ -27,6 +27,7 @@ int mha_decode_dispatch(const float* q, const void* kc, const void* vc, int kv_d
                         const int32_t* pos_dev, int pos, int max_len, int hd, int heads, int kv_heads, cudaStream_t st, bool pdl);
 size_t mha_workspace_bytes(int heads, int head_dim, int max_len);
 int check_gemv_args(const void* W, int w_dtype, const float* scales, int group, int rows, int cols);
+extern int g_tune_mega_debug;   // runtime.cu: measurement aids (sllm_tune key 8)
 }  // namespace sllm
 
 using namespace sllm;
@@ -121,6 +122,12 @@ struct sllm_engine {
     PfCache* pf = nullptr;
     uint8_t* pf_ws = nullptr;
     int pf_rows = 0;
+    // tensor-parallel prefill exchange over peer memory (prefill_tp.cu): this rank's block, the peers' mappings, call counter
+    uint8_t* pfx_block = nullptr;
+    void* pfx_peer[kMaxTp] = {};
+    bool pfx_ready = false;
+    uint32_t pfx_calls = 0, pfx_ctas = 0;
+    bool pfx_dirty = false;
     float *pf_x = nullptr, *pf_part = nullptr;
     uint16_t *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_s = nullptr;
     int32_t* pf_ids = nullptr;
@@ -130,6 +137,7 @@ struct sllm_engine {
 constexpr int kCumTables = 8;
 // ------------------------------------------------------------------------------------------- helpers ---
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int kPrefillBlock = 1024;   // prompt rows per pass of the batched prefill through the layers
 static size_t wbytes(int dtype, int64_t n) { return dtype == SLLM_F32 ? 4 * (size_t)n : dtype == SLLM_BF16 ? 2 * (size_t)n : (size_t)n; }
 
 template <class T>
@@ -814,6 +822,12 @@ int sllm_engine_create(const sllm_engine_config* cfg, sllm_stream_t stream, sllm
             cudaGetLastError(); set_error("peer-memory all-reduce: allocation failed"); sllm_engine_destroy(e); return SLLM_ENOMEM;
         }
     }
+    if ((tp == 2 || tp == 4 || tp == 8) && (cfg->flags & SLLM_ENGINE_P2P_ALLREDUCE) && e->mega && !pf_unsupported_reason(cfg->w_dtype, e->hd, e->d, e->q_loc, e->I_loc) && e->d % 8 == 0 && e->d <= 8192) {
+        const size_t total = pfx_block_bytes(kPrefillBlock, e->d);
+        if (cudaMalloc(&e->pfx_block, total) != cudaSuccess || cudaMemset(e->pfx_block, 0, total) != cudaSuccess) {
+            cudaGetLastError(); set_error("prefill exchange block: allocation of %zu MiB failed", total >> 20); sllm_engine_destroy(e); return SLLM_ENOMEM;
+        }
+    }
     // zero everything that is read before it is written: KV cache, workspaces, state
     cudaError_t ce = cudaMemsetAsync(e->key_cache, 0, e->arena + e->arena_used - reinterpret_cast<uint8_t*>(e->key_cache), e->stream);
     if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void**>(&e->h_state), 64);
@@ -832,6 +846,8 @@ void sllm_engine_destroy(sllm_engine* e) {
     if (e->p2p_dev) cudaFree(e->p2p_dev);
     if (e->p2p_block) cudaFree(e->p2p_block);
     if (e->ll_block) cudaFree(e->ll_block);
+    for (int r = 0; r < kMaxTp; ++r) if (e->pfx_peer[r]) cudaIpcCloseMemHandle(e->pfx_peer[r]);
+    if (e->pfx_block) cudaFree(e->pfx_block);
     if (e->pf_ws) cudaFree(e->pf_ws);
     if (e->pf) pf_cache_destroy(e->pf);
     if (e->emb.rm) cudaFree(e->emb.rm);   // a weight load that failed half way
@@ -950,6 +966,32 @@ int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles) {
     SLLM_CUDA(cudaStreamSynchronize(e->stream));
     e->p2p_ready = true;
     return maybe_build_graph(e);
+}
+
+/* The prefill exchange block (prefill_tp.cu): same messenger protocol as sllm_engine_p2p_export / _import. SLLM_ENOTSUP when the engine has
+   none (single rank, no SLLM_ENGINE_P2P_ALLREDUCE, or a shape the batched prefill does not take): prefill then all-reduces with NCCL. */
+int sllm_engine_prefill_p2p_export(sllm_engine* e, void* handle_bytes_64) {
+    SLLM_REQUIRE(e && handle_bytes_64, SLLM_EINVAL, "null argument");
+    if (!e->pfx_block) { set_error("this engine has no prefill exchange block"); return SLLM_ENOTSUP; }
+    cudaIpcMemHandle_t h;
+    SLLM_CUDA(cudaIpcGetMemHandle(&h, e->pfx_block));
+    std::memcpy(handle_bytes_64, &h, 64);
+    return SLLM_OK;
+}
+
+int sllm_engine_prefill_p2p_import(sllm_engine* e, const void* all_handles) {
+    SLLM_REQUIRE(e && all_handles, SLLM_EINVAL, "null argument");
+    if (!e->pfx_block) { set_error("this engine has no prefill exchange block"); return SLLM_ENOTSUP; }
+    for (int r = 0; r < e->tp; ++r) {
+        if (r == e->rank || e->pfx_peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, reinterpret_cast<const uint8_t*>(all_handles) + (size_t)r * 64, 64);
+        void* pp = nullptr;
+        SLLM_CUDA(cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess));
+        e->pfx_peer[r] = pp;
+    }
+    e->pfx_ready = true;
+    return SLLM_OK;
 }
 
 int sllm_engine_set_state(sllm_engine* e, int32_t token, int32_t pos) {
@@ -1141,6 +1183,10 @@ static int prefill_workspace(sllm_engine* e, int rows) {
     e->pf_xn = reinterpret_cast<uint16_t*>(e->pf_ws + o_xn); e->pf_q = reinterpret_cast<uint16_t*>(e->pf_ws + o_q);
     e->pf_att = reinterpret_cast<uint16_t*>(e->pf_ws + o_att); e->pf_s = reinterpret_cast<uint16_t*>(e->pf_ws + o_s);
     e->pf_ids = reinterpret_cast<int32_t*>(e->pf_ws + o_ids);
+    if (e->pfx_block) {   // the partial sums and the GEMM operand rows live in the block the peers have mapped
+        e->pf_part = reinterpret_cast<float*>(e->pfx_block + pfx_off_part(0, kPrefillBlock, e->d));
+        e->pf_xn = reinterpret_cast<uint16_t*>(e->pfx_block + pfx_off_xn(kPrefillBlock, e->d));
+    }
     e->pf_rows = rows;
     return SLLM_OK;
 }
@@ -1166,13 +1212,38 @@ static int prefill_block(sllm_engine* e, int T, int pos0, bool last_block) {
         return reinterpret_cast<const uint8_t*>(m.w) + (size_t)l * mega_matrix_bytes((int)m.rows, (int)m.cols, m.kind, e->cfg.w_dtype);
     };
     const size_t kv_layer_bytes = (size_t)e->esz_kv * e->S * e->kv_loc;
+    // tensor parallel with the peers' exchange blocks mapped: sum over ranks + residual + RMSNorm + distribution of the bf16 rows in ONE kernel
+    // over NVLink peer memory (prefill_tp.cu) instead of ncclAllReduce + RMSNorm; the fp32 residual stream is row-sharded from the first call on
+    const bool pfx = tp && e->pfx_ready;
+    PfxParams xp{};
+    if (pfx) {
+        xp.tp = e->tp; xp.rank = e->rank; xp.T = T; xp.d = d; xp.eps = s.eps; xp.x = e->pf_x;
+        xp.off_xn = pfx_off_xn(kPrefillBlock, d);
+        if (e->pfx_dirty) {   // a measurement run skipped the exchanges (and with them the zeroing of the partial-sum matrices)
+            SLLM_CUDA(cudaMemsetAsync(e->pfx_block + pfx_off_part(0, kPrefillBlock, d), 0, pfx_off_xn(kPrefillBlock, d) - pfx_off_part(0, kPrefillBlock, d), st));
+            e->pfx_dirty = false;
+        }
+        for (int r = 0; r < e->tp; ++r) xp.block[r] = (r == e->rank) ? e->pfx_block : reinterpret_cast<uint8_t*>(e->pfx_peer[r]);
+    }
+    // which = 0: the wo partial sums, 1: the down partial sums; the call zeroes the other matrix for the GEMM that accumulates into it next
+    float* const part2[2] = {pfx ? reinterpret_cast<float*>(e->pfx_block + pfx_off_part(0, kPrefillBlock, d)) : nullptr,
+                             pfx ? reinterpret_cast<float*>(e->pfx_block + pfx_off_part(1, kPrefillBlock, d)) : nullptr};
+    auto exchange = [&](int which, const float* norm_w, int row_lo, int row_hi, bool xlast) -> int {
+        if (g_tune_mega_debug & 16) { e->pfx_dirty = true; return SLLM_OK; }
+        xp.off_part = pfx_off_part(which, kPrefillBlock, d); xp.zero = part2[which ^ 1];   // measurement aid: prefill WITHOUT its exchanges (garbage results) = the GEMM / attention time alone
+        xp.norm_w = norm_w; xp.row_lo = row_lo; xp.row_hi = row_hi; xp.write_xlast = xlast ? 1 : 0;
+        xp.epoch = ++e->pfx_calls;
+        e->pfx_ctas += (uint32_t)pf_tp_exchange_grid(T, e->tp, sm_count());
+        xp.done_target = e->pfx_ctas;
+        return pf_tp_exchange(xp, sm_count(), st);
+    };
 #define PF(call) do { if (int rc = (call)) return rc; } while (0)
     PF(pf_embed(e->pf_ids, e->emb.w, e->V, d, e->pf_x, T, st));
     for (int l = 0; l < L; ++l) {
         uint8_t* kc = reinterpret_cast<uint8_t*>(e->key_cache) + (size_t)l * kv_layer_bytes;
         uint8_t* vc = reinterpret_cast<uint8_t*>(e->value_cache) + (size_t)l * kv_layer_bytes;
         // attention norm (+ under TP the all-reduced down partial of the previous layer)
-        PF(pf_rmsnorm(e->pf_x, (tp && l > 0) ? e->pf_part : nullptr, e->norms + (size_t)(2 * l) * d, e->pf_xn, T, d, s.eps, st));
+        if (!(pfx && l > 0)) PF(pf_rmsnorm(e->pf_x, (tp && l > 0) ? e->pf_part : nullptr, e->norms + (size_t)(2 * l) * d, e->pf_xn, T, d, s.eps, st));
         PfGemmArgs a{};
         a.A = e->pf_xn; a.W = tiled_layer(e->wqkv, l); a.T = T; a.N = e->q_loc + 2 * e->kv_loc; a.K = d; a.tiled = 1; a.epilogue = PF_EPI_QKV;
         a.q_out = e->pf_q; a.k_cache = kc; a.v_cache = vc; a.kv_dtype = e->cfg.kv_dtype; a.q_loc = e->q_loc; a.kv_loc = e->kv_loc; a.hd = e->hd;
@@ -1182,30 +1253,47 @@ static int prefill_block(sllm_engine* e, int T, int pos0, bool last_block) {
         PF(pf_attention(e->pf_q, kc, vc, e->cfg.kv_dtype, e->pf_att, T, pos0, e->S, e->hd, e->H_loc, e->KVH_loc, st));
         PfGemmArgs c{};
         c.A = e->pf_att; c.W = tiled_layer(e->wo, l); c.T = T; c.N = ((d + 1) / 2) * 2; c.K = e->q_loc; c.tiled = 1;
-        c.epilogue = tp ? PF_EPI_STORE : PF_EPI_RESID; c.out = tp ? e->pf_part : e->pf_x; c.ld_out = d; c.n_valid = d;
+        c.epilogue = pfx ? PF_EPI_ACCUM : tp ? PF_EPI_STORE : PF_EPI_RESID; c.out = pfx ? part2[0] : tp ? e->pf_part : e->pf_x; c.ld_out = d; c.n_valid = d;
         PF(pf_gemm(e->pf, c, st));
-        if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
-        PF(pf_rmsnorm(e->pf_x, tp ? e->pf_part : nullptr, e->norms + (size_t)(2 * l + 1) * d, e->pf_xn, T, d, s.eps, st));
+        if (pfx) {
+            PF(exchange(0, e->norms + (size_t)(2 * l + 1) * d, 0, T, false));
+        } else {
+            if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+            PF(pf_rmsnorm(e->pf_x, tp ? e->pf_part : nullptr, e->norms + (size_t)(2 * l + 1) * d, e->pf_xn, T, d, s.eps, st));
+        }
         PfGemmArgs g{};
         g.A = e->pf_xn; g.W = tiled_layer(e->wug, l); g.T = T; g.N = 2 * e->I_loc; g.K = d; g.tiled = 1; g.epilogue = PF_EPI_GATEUP;
         g.s_out = e->pf_s; g.I_loc = e->I_loc;
         PF(pf_gemm(e->pf, g, st));
         PfGemmArgs dn = c;
         dn.A = e->pf_s; dn.W = tiled_layer(e->wdown, l); dn.K = e->I_loc;
+        if (pfx) dn.out = part2[1];
         PF(pf_gemm(e->pf, dn, st));
-        if (tp) SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+        if (pfx) {   // sum over ranks + residual + the NEXT norm (the next layer's attention norm; after the last layer: the final norm of the last row)
+            if (l + 1 < L) PF(exchange(1, e->norms + (size_t)(2 * l + 2) * d, 0, T, false));
+            else PF(exchange(1, e->norms + (size_t)(2 * L) * d, T - 1, T, true));
+        } else if (tp) {
+            SLLM_NCCL(ncclAllReduce(e->pf_part, e->pf_part, (size_t)T * d, ncclFloat, ncclSum, e->comm, st));
+        }
     }
     if (last_block) {
         const size_t last = (size_t)(T - 1) * d;
-        PF(pf_rmsnorm(e->pf_x + last, tp ? e->pf_part + last : nullptr, e->norms + (size_t)(2 * L) * d, e->pf_xn, 1, d, s.eps, st));
-        SLLM_CUDA(cudaMemcpyAsync(e->x, e->pf_x + last, sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice, st));   // emb_output: final residual
+        if (pfx) {   // the exchange left the normalised last row in every rank's operand buffer and its fp32 residual row in every block
+            SLLM_CUDA(cudaMemcpyAsync(e->x, e->pfx_block + kPfxXlast, sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice, st));
+        } else {
+            PF(pf_rmsnorm(e->pf_x + last, tp ? e->pf_part + last : nullptr, e->norms + (size_t)(2 * L) * d, e->pf_xn, 1, d, s.eps, st));
+            SLLM_CUDA(cudaMemcpyAsync(e->x, e->pf_x + last, sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice, st));   // emb_output: final residual
+        }
         const TileGeom eg = mega_tile_geom(((e->V + 1) / 2) * 2, d, e->cfg.w_dtype);
         PfGemmArgs c{};
-        c.A = e->pf_xn; c.W = reinterpret_cast<const uint8_t*>(e->emb.w) + (size_t)(e->v0 / eg.R) * eg.KS * eg.tile_bytes;
+        c.A = pfx ? e->pf_xn + last : e->pf_xn; c.W = reinterpret_cast<const uint8_t*>(e->emb.w) + (size_t)(e->v0 / eg.R) * eg.KS * eg.tile_bytes;
         c.T = 1; c.N = ((e->V_loc + 1) / 2) * 2; c.K = d; c.tiled = 1; c.epilogue = PF_EPI_STORE; c.out = e->logits; c.ld_out = e->V_loc; c.n_valid = e->V_loc;
         PF(pf_gemm(e->pf, c, st));
         PF(sllm_argmax_f32(e->logits, e->V_loc, e->blk_idx, st));
-        if (tp) {
+        if (pfx) {
+            xp.epoch = ++e->pfx_calls;
+            PF(pf_tp_argmax(xp, e->logits, e->blk_idx, e->v0, e->state, e->prompt_dev, e->history_dev, st));
+        } else if (tp) {
             pf_pack_pair_kernel<<<1, 32, 0, st>>>(e->logits, e->blk_idx, e->v0, e->tp_pairs + 2 * e->rank);
             SLLM_NCCL(ncclAllGather(e->tp_pairs + 2 * e->rank, e->tp_pairs, 2, ncclFloat, e->comm, st));
             tp_merge_kernel<<<1, 32, 0, st>>>(e->tp_pairs, e->tp, e->state, e->prompt_dev, e->history_dev);
@@ -1234,11 +1322,12 @@ int sllm_engine_prefill(sllm_engine* e, const int32_t* prompt, int32_t n, int32_
     SLLM_REQUIRE(start_pos >= 0 && start_pos + n <= e->S, SLLM_EINVAL, "prompt of %d tokens at position %d overruns max_len %d", n, start_pos, e->S);
     for (int i = 0; i < n; ++i) SLLM_REQUIRE(prompt[i] >= 0 && prompt[i] < e->V, SLLM_EINVAL, "Token index %d is outside the vocabulary [0, %d).", prompt[i], e->V);
     if (const char* why = prefill_unsupported(e)) { set_error("%s", why); return SLLM_ENOTSUP; }
-    SLLM_REQUIRE(e->tp == 1 || e->comm, SLLM_ESTATE, "tensor-parallel prefill needs the NCCL communicator (sllm_engine_init_comm)");
+    SLLM_REQUIRE(e->tp == 1 || e->comm || e->pfx_ready, SLLM_ESTATE,
+                 "tensor-parallel prefill needs the peers' exchange blocks (sllm_engine_prefill_p2p_import) or the NCCL communicator (sllm_engine_init_comm)");
     SLLM_REQUIRE(e->tp == 1 || e->ll_ready, SLLM_ESTATE, "tensor-parallel engine: peer areas not exchanged yet");
     // blocks of up to kBlock rows through the tensor-core path; the last block also produces the last row's logits,
     // the arg-max and the step-state update (token = arg-max, position = start_pos + n, history)
-    constexpr int kBlock = 1024;
+    constexpr int kBlock = kPrefillBlock;
     if (int rc = prefill_workspace(e, std::min(n, kBlock))) return rc;
     if (n > 1) SLLM_CUDA(cudaMemcpyAsync(e->history_dev + start_pos, prompt + 1, sizeof(int32_t) * (size_t)(n - 1), cudaMemcpyHostToDevice, e->stream));
     if (int rc = set_state(e, prompt[n - 1], start_pos + n - 1, 0)) return rc;
@@ -1283,6 +1372,9 @@ int sllm_engine_buffer(sllm_engine* e, int32_t id, void** ptr, int64_t* n, int32
             if (!e->trace) { SLLM_CUDA(cudaMalloc(&e->trace, nb)); SLLM_CUDA(cudaMemset(e->trace, 0, nb)); e->mega_params.trace = e->trace; e->mega2_params.m.trace = e->trace; e->ll_params.trace = e->trace; }
             *ptr = e->trace; *n = (int64_t)(nb / 4); *dtype = SLLM_F32; break;
         }
+        case 201:   // timeline of the most recent prefill exchange (prefill_tp.cu): 2 x 8 u64 nanosecond stamps (last full call, last one-row call)
+            SLLM_REQUIRE(e->pfx_block, SLLM_ESTATE, "no prefill exchange block");
+            *ptr = e->pfx_block + kPfxTrace; *n = 32; *dtype = SLLM_F32; break;
         case 110: *ptr = e->emb.sc; *n = e->emb.sc ? (int64_t)e->V * e->d / e->cfg.group : 0; break;
         case 112: *ptr = e->wqkv.sc; *n = e->wqkv.sc ? (int64_t)e->L * e->wqkv.rows * e->wqkv.cols / e->cfg.group : 0; break;
         default: SLLM_REQUIRE(false, SLLM_EINVAL, "unknown buffer id %d", id);

@@ -45,7 +45,7 @@ constexpr size_t kPfSmem = 1024 /*alignment slack*/ + kPfRingBytes + 512 /*barri
 
 struct PfDev {           // kernel-side view of PfGemmArgs
     int32_t T, N, m_tiles, n_tiles, BN;
-    int32_t ksplit;       // > 1 (residual epilogue only): a tile's k-blocks are cut into ksplit work units whose partial sums are ADDED to
+    int32_t ksplit;       // > 1 (residual / accumulate epilogues only): a tile's k-blocks are cut into ksplit work units whose partial sums are ADDED to
                           // the residual stream with red.global.add — fills the machine when a GEMM has fewer tiles than SM pairs
     int32_t nkb, kb_per_seg, seg_elems, R, tiled;
     int32_t epilogue;
@@ -534,7 +534,8 @@ static PfPlan pf_plan(int T, int N, int K, int tiled, int epilogue, int bn_force
     int ksplit = 1;
     if (bn < 32 || bn > 256 || bn % 32) {
         const int workers = pl.pair ? sm_count() / 2 : sm_count();
-        const int max_split = (epilogue == PF_EPI_RESID && g_tune_pf_ksplit != 0) ? (g_tune_pf_ksplit > 0 ? g_tune_pf_ksplit : 4) : 1;
+        const bool adds = epilogue == PF_EPI_RESID || epilogue == PF_EPI_ACCUM;   // the epilogues whose partial sums may meet in L2
+        const int max_split = (adds && g_tune_pf_ksplit != 0) ? (g_tune_pf_ksplit > 0 ? g_tune_pf_ksplit : 4) : 1;
         double best = 1e30;
         for (int b = 256; b >= 64; b -= 32) {
             for (int sp = 1; sp <= max_split; ++sp) {
@@ -545,7 +546,7 @@ static PfPlan pf_plan(int T, int N, int K, int tiled, int epilogue, int bn_force
                 if (c < best - 1e-9) { best = c; bn = b; ksplit = sp; }
             }
         }
-    } else if (epilogue == PF_EPI_RESID && g_tune_pf_ksplit > 0 && pl.nkb / g_tune_pf_ksplit >= 1) {
+    } else if ((epilogue == PF_EPI_RESID || epilogue == PF_EPI_ACCUM) && g_tune_pf_ksplit > 0 && pl.nkb / g_tune_pf_ksplit >= 1) {
         ksplit = g_tune_pf_ksplit;
     }
     pl.bn = bn; pl.ksplit = ksplit;

@@ -96,6 +96,19 @@ class Engine:
         dist.barrier()
         _lib.check(self.lib.sllm_engine_p2p_import(self.h, raw))
         dist.barrier()
+        # the prefill exchange blocks (csrc/prefill_tp.cu), when the engine has one: batched prefill then needs no communicator at all
+        rc = self.lib.sllm_engine_prefill_p2p_export(self.h, buf)
+        if rc == 0:
+            mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+            if dist.get_backend() == "nccl":
+                mine = mine.cuda()
+            allh = [torch.zeros_like(mine) for _ in range(self.tp_size)]
+            dist.all_gather(allh, mine)
+            raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+            dist.barrier()
+            _lib.check(self.lib.sllm_engine_prefill_p2p_import(self.h, raw))
+            dist.barrier()
+        self.prefill_p2p = rc == 0
         return self
 
     # -- LlamaModel::forward: one token at one position; returns (logits np.float32[V_local], next_token) --

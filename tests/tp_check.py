@@ -3,6 +3,8 @@
 import os
 import sys
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -10,6 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import loader  # noqa: E402
+from simplellminference_b200 import _lib  # noqa: E402
 from simplellminference_b200.config import PRESETS, ModelShape, F32, BF16, INT8  # noqa: E402
 from simplellminference_b200.engine import Engine  # noqa: E402
 
@@ -67,10 +70,11 @@ def main():
         eng.close()
         if rank == 0:
             print(f"tp{world} {name}: {n_total - 1} tokens ok on every rank, max|dlogit|={err:.2e} (tol {tol:.1e})", flush=True)
-    # ---- batched prefill under tensor parallelism (tcgen05 GEMMs per rank + NCCL all-reduce of the [T][d] partial sums):
+    # ---- batched prefill under tensor parallelism (tcgen05 GEMMs per rank; the [T][d] partial sums meet either in the peer-memory exchange
+    # kernel of csrc/prefill_tp.cu or in ncclAllReduce + RMSNorm):
     # last-position logits against the oracle's token-by-token loop on the gain-1 blob (tests/test_prefill_gpu.py explains
     # why), then the decode that follows must agree on every rank.
-    ms = ModelShape(4096, 128, 1024, 1024, 2816, 400, 4, 8, 8)
+    ms = ModelShape(4096, 128, 1024, 1024, 2816, 1300, 4, 8, 8)
     if not (ms.kv_heads % world or ms.inter % world or ms.vocab % world):
         shape = loader.Shape(ms.vocab, ms.head_dim, ms.hidden, ms.kv_hidden, ms.inter, ms.max_len, ms.layers, ms.heads, ms.kv_heads, ms.eps, ms.theta)
         blob = port.fill_blob(shape, 21, BF16)
@@ -85,25 +89,46 @@ def main():
         want_l = om.forward(int(ids[n - 1]), n - 1)
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
-        eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=True, mega=True).load_blob(blob)
-        assert eng.mode == "megakernel(ll)" and eng.prefill_supported, eng.mode
-        eng.init_p2p(dist).init_comm(dist)
-        eng.prefill(ids)
-        torch.cuda.synchronize()
-        v_loc = ms.vocab // world
-        logits = eng.buffer("model_pred").cpu().numpy()
-        err = float(np.abs(logits - want_l[rank * v_loc:(rank + 1) * v_loc]).max())
-        tol = 3e-2 * max(1.0, float(np.abs(want_l).max()))
-        assert err <= tol, ("prefill", rank, err, tol)
-        eng.enqueue_steps(5)
-        toks = torch.tensor(eng.read_tokens(6), device="cuda")
-        assert int(toks[0]) == int(np.argmax(want_l)), (int(toks[0]), int(np.argmax(want_l)))
-        allt = [torch.zeros_like(toks) for _ in range(world)]
-        dist.all_gather(allt, toks)
-        assert all(torch.equal(t, allt[0]) for t in allt), "ranks disagree on the tokens decoded after a prefill"
-        eng.close()
-        if rank == 0:
-            print(f"tp{world} batched prefill of {n} tokens: max|dlogit|={err:.2e} (tol {tol:.1e}), next token and 5 decoded tokens agree on every rank", flush=True)
+        for exch in ("peer memory", "nccl"):
+            eng = Engine(ms, w_dtype=BF16, kv_dtype=BF16, tp_rank=rank, tp_size=world, stream=stream, p2p_allreduce=True, mega=True).load_blob(blob)
+            assert eng.mode == "megakernel(ll)" and eng.prefill_supported, eng.mode
+            if exch == "peer memory":   # the exchange blocks travel with init_p2p: no communicator is ever created
+                eng.init_p2p(dist)
+                assert eng.prefill_p2p
+            else:                        # the decode areas by hand, then NCCL for the prefill's all-reduce (the round-1 path)
+                buf = (C.c_uint8 * 64)()
+                _lib.check(eng.lib.sllm_engine_p2p_export(eng.h, buf))
+                mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone().cuda()
+                allh = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                dist.barrier()
+                _lib.check(eng.lib.sllm_engine_p2p_import(eng.h, b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)))
+                dist.barrier()
+                eng.init_comm(dist)
+            eng.prefill(ids)
+            torch.cuda.synchronize()
+            v_loc = ms.vocab // world
+            logits = eng.buffer("model_pred").cpu().numpy()
+            err = float(np.abs(logits - want_l[rank * v_loc:(rank + 1) * v_loc]).max())
+            tol = 3e-2 * max(1.0, float(np.abs(want_l).max()))
+            assert err <= tol, ("prefill", exch, rank, err, tol)
+            x_last = eng.buffer("emb_output").cpu().numpy()      # the final residual row must be on every rank
+            assert np.isfinite(x_last).all() and float(np.abs(x_last).max()) > 0, ("prefill", exch, rank)
+            eng.enqueue_steps(5)
+            toks = torch.tensor(eng.read_tokens(6), device="cuda")
+            assert int(toks[0]) == int(np.argmax(want_l)), (exch, int(toks[0]), int(np.argmax(want_l)))
+            allt = [torch.zeros_like(toks) for _ in range(world)]
+            dist.all_gather(allt, toks)
+            assert all(torch.equal(t, allt[0]) for t in allt), "ranks disagree on the tokens decoded after a prefill"
+            # a second, multi-block prompt through the same engine (1100 rows = two passes): epochs and counters carry over
+            if exch == "peer memory" and ms.max_len >= 1200:
+                ids2 = np.random.default_rng(6).integers(1, ms.vocab, size=1100, dtype=np.int32)
+                eng.prefill(ids2)
+                torch.cuda.synchronize()
+                assert np.isfinite(eng.buffer("model_pred").cpu().numpy()).all()
+            eng.close()
+            if rank == 0:
+                print(f"tp{world} batched prefill of {n} tokens [{exch}]: max|dlogit|={err:.2e} (tol {tol:.1e}), next token and 5 decoded tokens agree on every rank", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
