@@ -250,7 +250,7 @@ def batch_decode_sample(args):
     Runs in ONE child process after every timed region of this one and after its engine is gone; the child prints a JSON line
     per variant as it goes, so whatever happens there (error, time-out) costs only the variants not yet printed and never
     the headline numbers."""
-    variants = ["plain", "graph", "graph+rows4", "graph+rows4+ksplit"]
+    variants = ["plain", "tc+graph", "graph", "graph+rows4", "graph+rows4+ksplit"]   # tc+graph: the tensor-core step (8 .. 64 sequences)
     cmd = [sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), "--config", args.config, "--wdtype", args.wdtype,
            "--kvdtype", args.kvdtype, "--context", str(args.prompt_len), "--batches", "1,4,8,16", "--exp-batches", "8,16",
            "--variants", ",".join(variants), "--steps", "64", "--json"]

@@ -325,6 +325,12 @@ int sllm_batch_set_sampling(sllm_batch* b, int32_t slot, float temperature, int3
 /* n_steps tokens for EVERY live sequence, asynchronous. Takes the pages the steps will write first, for all sequences
  * or none: SLLM_ENOMEM (nothing enqueued) when the pool is short, SLLM_EINVAL when a sequence would pass max_len. */
 int sllm_batch_step(sllm_batch* b, int32_t n_steps);
+/* Opt-in (on != 0): the steps of this batch run their five projection groups as tcgen05 GEMMs over the live sequences' rows (the prefill GEMM
+ * kernel of csrc/prefill_gemm.cu) instead of batched GEMVs, so that every weight byte is read once per step however many sequences are live —
+ * the batched GEMVs stop scaling at ~4 sequences. GEMM operands are bf16 (activations rounded after RMSNorm / attention / SwiGLU, fp32
+ * accumulation): a sequence's results then agree with the reference within the bf16-operand tolerance of the prefill, not bit for bit.
+ * bf16 weights only (SLLM_ENOTSUP otherwise). The reference has no batched decode (model.h:15-18: one token, one position). */
+int sllm_batch_set_tensor_cores(sllm_batch* b, int32_t on);
 /* the tokens that followed positions 0.. of the slot's sequence (prompt tokens included, as sllm_engine_greedy
  * reports them), at most max_tokens; *n_out = how many. Synchronises the stream. */
 int sllm_batch_read(sllm_batch* b, int32_t slot, int32_t* tokens_out_host, int32_t max_tokens, int32_t* n_out);

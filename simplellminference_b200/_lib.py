@@ -95,6 +95,7 @@ SIGNATURES = {
     "sllm_batch_remove": (C.c_int, [_P, _I]),
     "sllm_batch_set_sampling": (C.c_int, [_P, _I, _F, _I, _F, C.c_uint64]),
     "sllm_batch_step": (C.c_int, [_P, _I]),
+    "sllm_batch_set_tensor_cores": (C.c_int, [_P, _I]),
     "sllm_batch_read": (C.c_int, [_P, _I, _P, _I, C.POINTER(_I)]),
     "sllm_batch_logits": (C.c_int, [_P, _I, _P]),
     "sllm_batch_buffer": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),

@@ -113,6 +113,11 @@ class BatchDecoder:
         """Draw this sequence's tokens (kernels.sample semantics, keyed by (seed, position)) instead of arg-max; temperature <= 0 = arg-max."""
         _lib.check(self.lib.sllm_batch_set_sampling(self.h, slot, float(temperature), int(top_k), float(top_p), int(seed)))
 
+    def set_tensor_cores(self, on: bool = True) -> None:
+        """Opt-in: the projections of every step as tcgen05 GEMMs over the live sequences' rows (weights read once per step however many
+        sequences are live; bf16 GEMM operands, so results match the reference within the prefill's tolerance, not bit for bit)."""
+        _lib.check(self.lib.sllm_batch_set_tensor_cores(self.h, int(bool(on))))
+
     def step(self, n_steps: int = 1) -> None:
         _lib.check(self.lib.sllm_batch_step(self.h, n_steps))
 

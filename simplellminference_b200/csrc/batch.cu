@@ -25,6 +25,7 @@
 
 #include "batch_gemv.cuh"
 #include "engine_view.cuh"
+#include "prefill.cuh"
 
 using namespace sllm;
 
@@ -126,6 +127,12 @@ struct sllm_batch {
     std::vector<cudaGraphExec_t> graphs;   // [max_seqs + 1]
     std::vector<int> graph_launches;       // kernel nodes of each graph
     std::vector<char> warmed;              // a direct step with this count has run (modules loaded, attributes set)
+    // opt-in tensor-core step (sllm_batch_set_tensor_cores): the five GEMV groups become tcgen05 GEMMs over the live slots' rows
+    bool tc = false;
+    PfCache* tc_pf = nullptr;
+    uint8_t* tc_ws = nullptr;
+    uint16_t *tc_xn = nullptr, *tc_att = nullptr, *tc_s = nullptr;   // bf16 GEMM operands: normalised rows, attention output, sigmoid(gate)*up
+    float *tc_qkv = nullptr, *tc_ug = nullptr;                       // fp32 GEMM results before RoPE / SwiGLU
 };
 
 template <class T>
@@ -390,7 +397,147 @@ static int enqueue_batch_step(sllm_batch* b, int hi) {
     return SLLM_OK;
 }
 
+namespace sllm { extern int g_tune_pf_pdl; }
+// ------------------------------------------------------------------------------- tensor-core step (opt-in) ---
+// With many live sequences the GEMV kernels above re-read the activations from shared memory once per weight row and stop scaling at
+// ~4 sequences (profiles/r02_batch_decode.jsonl). Here a step's rows [hi][d] go through the prefill GEMM (prefill_gemm.cu: tcgen05.mma,
+// TMEM accumulators, TMA operands; row-major bf16 weights): every weight byte is read once per step whatever the number of sequences.
+// The price is the prefill's: GEMM operands are bf16 (activations rounded after RMSNorm / attention / SwiGLU), accumulation fp32 —
+// per-sequence results agree with the reference within the bf16-operand tolerance (tests/test_zz_batch_gpu.py), not bit for bit.
+// RoPE + paged K/V write of the fp32 q/k/v rows: the epilogue of BQkvPolicy as a kernel of its own (rope_kernel.cpp:36-37)
+__global__ void __launch_bounds__(256) btc_rope_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ sin_t, const float* __restrict__ cos_t,
+                                                         float* __restrict__ q_out, void* k_pool, void* v_pool, PagedKv pk, int layer, int kv_dtype,
+                                                         int q_dim, int kv_dim, int hd) {
+    const int slot = blockIdx.x;
+    pdl_wait();                 // launched with programmatic stream serialization: resident early, the GEMM's results are complete from here on
+    pdl_launch_dependents();
+    const int pos = pk.pos[slot];
+    if (pos < 0) return;
+    const float* row = qkv + (size_t)slot * (q_dim + 2 * kv_dim);
+    const int half = hd >> 1, rope_units = (q_dim + kv_dim) >> 1, units = (q_dim + 2 * kv_dim) >> 1, kv_heads = kv_dim / hd;
+    const int pi = pos / pk.page_len, in_page = pos - pi * pk.page_len;
+    const int page = pk.block_table[(size_t)slot * pk.max_pages + pi];
+    auto store_kv = [&](void* pool, size_t idx, float v) {
+        if (kv_dtype == SLLM_BF16) reinterpret_cast<uint16_t*>(pool)[idx] = f32_to_bf16_bits(v);
+        else reinterpret_cast<float*>(pool)[idx] = v;
+    };
+    for (int u = blockIdx.y * blockDim.x + threadIdx.x; u < units; u += gridDim.y * blockDim.x) {   // grid.y CTAs share a slot's row
+        if (u < rope_units) {
+            const int head = u / half, j = u - head * half;
+            const int r0 = head * hd + j;
+            const float s0 = row[r0], s1 = row[r0 + half];
+            const float fci = sin_t[(int64_t)pos * half + j], fcr = cos_t[(int64_t)pos * half + j];
+            const float o0 = s0 * fcr - s1 * fci, o1 = s1 * fcr + s0 * fci;
+            if (r0 < q_dim) {
+                q_out[(size_t)slot * q_dim + r0] = o0;
+                q_out[(size_t)slot * q_dim + r0 + half] = o1;
+            } else {
+                const int kvh = head - q_dim / hd;
+                const size_t idx = paged_row_index(page, pk.layers, layer, kv_heads, kvh, pk.page_len, in_page, hd) + j;
+                store_kv(k_pool, idx, o0);
+                store_kv(k_pool, idx + half, o1);
+            }
+        } else {
+            const int c = 2 * (u - rope_units);
+            const int kvh = c / hd, j = c - kvh * hd;
+            const size_t idx = paged_row_index(page, pk.layers, layer, kv_heads, kvh, pk.page_len, in_page, hd) + j;
+            store_kv(v_pool, idx, row[q_dim + kv_dim + c]);
+            store_kv(v_pool, idx + 1, row[q_dim + kv_dim + c + 1]);
+        }
+    }
+}
+__global__ void btc_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n4) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2((uint32_t)f32_to_bf16_bits(v.x) | ((uint32_t)f32_to_bf16_bits(v.y) << 16),
+                                                      (uint32_t)f32_to_bf16_bits(v.z) | ((uint32_t)f32_to_bf16_bits(v.w) << 16));
+    }
+}
+// ug = [rows][up (inter) | gate (inter)] fp32 -> s = sigmoid(gate) * up as bf16 (swiglu_kernel.cpp:12-13)
+__global__ void btc_swiglu_kernel(const float* __restrict__ ug, uint16_t* __restrict__ s, int inter, size_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / inter, u = i - r * inter;
+        const float up = ug[r * 2 * inter + u], gate = ug[r * 2 * inter + inter + u];
+        s[i] = f32_to_bf16_bits((1.0f / (1.0f + expf(-gate))) * up);
+    }
+}
+
+static int enqueue_batch_step_tc(sllm_batch* b, int hi) {
+    const EngineView& ev = b->ev;
+    const int d = b->d, L = b->L, I = b->I, V = b->V, q_dim = b->q_dim, kv_dim = b->kv_dim, nqkv = q_dim + 2 * kv_dim;
+    cudaStream_t st = b->stream;
+    PagedKv pk{};
+    pk.block_table = b->block_table; pk.pos = b->pos; pk.max_pages = b->pages->max_pages; pk.page_len = b->pages->page_len;
+    pk.layers = L; pk.q_stride = q_dim; pk.heads = b->H;
+    const int nsplit = mha_paged_nsplit(b->KVH, hi, b->S);
+    const int64_t before = g_launches;
+    const bool pdl = g_tune_pf_pdl != 0;
+    auto small_grid = [&](size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)4 * sm_count()); };
+#define BT(call) do { if (int rc = (call)) return rc; } while (0)
+    auto gemm = [&](const void* A, const void* W, int N, int K, int epilogue, float* out) -> int {
+        PfGemmArgs a{};
+        a.A = A; a.W = W; a.T = hi; a.N = N; a.K = K; a.tiled = 0; a.epilogue = epilogue; a.out = out; a.ld_out = N; a.n_valid = N;
+        return pf_gemm(b->tc_pf, a, st);
+    };
+    {
+        dim3 grid(std::max(1, std::min((d + 255) / 256, 64)), hi);
+        batch_embed_kernel<<<grid, 256, 0, st>>>(b->token, b->pos, ev.emb, ev.w_dtype, ev.emb_sc, ev.group, b->x, V, d);
+        SLLM_LAUNCH_CHECK();
+        g_launches++;
+    }
+    for (int l = 0; l < L; ++l) {
+        BT(pf_rmsnorm(b->x, nullptr, ev.norms + (int64_t)(2 * l) * d, b->tc_xn, hi, d, ev.shape.eps, st));                       // A
+        BT(gemm(b->tc_xn, layer_w(b, ev.wqkv, nqkv, d, l), nqkv, d, PF_EPI_STORE, b->tc_qkv));
+        {
+            LaunchCfg lc(dim3(hi, std::max(1, std::min(16, (nqkv / 2 + 255) / 256))), dim3(256), 0, st, pdl);
+            SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, btc_rope_kv_kernel, (const float*)b->tc_qkv, ev.sin_t, ev.cos_t, b->q, b->k_pool, b->v_pool, pk, l, b->kv_dtype, q_dim,
+                                         kv_dim, b->hd));
+        }
+        BT(mha_paged_dispatch(b->q, b->k_pool, b->v_pool, b->kv_dtype, b->att, b->mha_ws, l, pk, hi, b->max_seqs, nsplit, b->hd, b->KVH, st));   // B
+        {
+            LaunchCfg lc(dim3(small_grid((size_t)hi * q_dim / 4)), dim3(256), 0, st, pdl);
+            SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, btc_to_bf16_kernel, (const float*)b->att, b->tc_att, (size_t)hi * q_dim / 4));
+        }
+        BT(gemm(b->tc_att, layer_w(b, ev.wo, d, q_dim, l), d, q_dim, PF_EPI_RESID, b->x));                                          // C: x += Wo.att
+        BT(pf_rmsnorm(b->x, nullptr, ev.norms + (int64_t)(2 * l + 1) * d, b->tc_xn, hi, d, ev.shape.eps, st));                   // D
+        BT(gemm(b->tc_xn, layer_w(b, ev.wug, 2 * (int64_t)I, d, l), 2 * I, d, PF_EPI_STORE, b->tc_ug));
+        {
+            LaunchCfg lc(dim3(small_grid((size_t)hi * I)), dim3(256), 0, st, pdl);
+            SLLM_CUDA(cudaLaunchKernelEx(&lc.cfg, btc_swiglu_kernel, (const float*)b->tc_ug, b->tc_s, I, (size_t)hi * I));
+        }
+        BT(gemm(b->tc_s, layer_w(b, ev.wdown, d, I, l), d, I, PF_EPI_RESID, b->x));                                                 // E: x += Wdown.s
+        g_launches += 4;   // the three small kernels + attention
+    }
+    BT(pf_rmsnorm(b->x, nullptr, ev.norms + (int64_t)(2 * L) * d, b->tc_xn, hi, d, ev.shape.eps, st));                           // F
+    BT(gemm(b->tc_xn, ev.emb, V, d, PF_EPI_STORE, b->logits));
+#undef BT
+    b->total_launches += g_launches - before;
+    if (b->n_sampling == 0) {
+        batch_argmax_feedback_kernel<<<hi, kArgmaxThreads, 0, st>>>(b->logits, V, b->token, b->pos, b->n_prompt, b->next, b->prompt, b->history, b->S);
+        SLLM_LAUNCH_CHECK();
+        g_launches++;
+        b->total_launches++;
+        return SLLM_OK;
+    }
+    for (int s = 0; s < hi; ++s) {
+        if (b->host_pos[s] < 0) continue;
+        if (int rc = sllm_sample_f32(b->logits + (size_t)s * V, V, b->s_temp[s], b->s_top_k[s], b->s_top_p[s], b->s_seed[s],
+                                     (uint64_t)b->host_pos[s], b->next + s, st)) return rc;
+        b->total_launches++;
+    }
+    batch_feedback_kernel<<<hi, 32, 0, st>>>(b->next, b->token, b->pos, b->n_prompt, b->prompt, b->history, b->S);
+    SLLM_LAUNCH_CHECK();
+    g_launches++;
+    b->total_launches++;
+    return SLLM_OK;
+}
+
 static int dispatch_batch_step(sllm_batch* b, int hi) {
+    if (b->tc) return enqueue_batch_step_tc(b, hi);
     switch (b->ev.w_dtype) {
         case SLLM_F32: return enqueue_batch_step<SLLM_F32>(b, hi);
         case SLLM_BF16: return enqueue_batch_step<SLLM_BF16>(b, hi);
@@ -500,6 +647,8 @@ void sllm_batch_destroy(sllm_batch* b) {
     }
     for (cudaGraphExec_t g : b->graphs)
         if (g) cudaGraphExecDestroy(g);
+    if (b->tc_ws) cudaFree(b->tc_ws);
+    if (b->tc_pf) pf_cache_destroy(b->tc_pf);
     sllm_kvpages_destroy(b->pages);
     delete b;
 }
@@ -547,6 +696,31 @@ int sllm_batch_set_sampling(sllm_batch* b, int32_t slot, float temperature, int3
     b->s_top_k[slot] = top_k;
     b->s_top_p[slot] = top_p;
     b->s_seed[slot] = seed;
+    return SLLM_OK;
+}
+
+/* Opt-in: run the steps of this batch on the tensor cores (see enqueue_batch_step_tc). bf16 weights only; SLLM_ENOTSUP otherwise. */
+int sllm_batch_set_tensor_cores(sllm_batch* b, int32_t on) {
+    SLLM_REQUIRE(b, SLLM_EINVAL, "null batch");
+    if (!on) { b->tc = false; return SLLM_OK; }
+    if (b->ev.w_dtype != SLLM_BF16) { set_error("tensor-core batch step: bf16 weights only"); return SLLM_ENOTSUP; }
+    if (b->d % 8 || b->q_dim % 8 || b->I % 8 || b->d % 4 || b->q_dim % 4) { set_error("tensor-core batch step: hidden, q and intermediate sizes must be multiples of 8"); return SLLM_ENOTSUP; }
+    if (!b->tc_ws) {
+        const size_t ms = (size_t)b->max_seqs;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
+        const size_t o_xn = take(2 * ms * b->d), o_att = take(2 * ms * b->q_dim), o_s = take(2 * ms * b->I),
+                     o_qkv = take(4 * ms * (b->q_dim + 2 * (size_t)b->kv_dim)), o_ug = take(4 * ms * 2 * (size_t)b->I);
+        if (cudaMalloc(&b->tc_ws, off) != cudaSuccess) { cudaGetLastError(); set_error("tensor-core batch step: cudaMalloc(%zu MiB) failed", off >> 20); return SLLM_ENOMEM; }
+        SLLM_CUDA(cudaMemsetAsync(b->tc_ws, 0, off, b->stream));
+        b->tc_xn = reinterpret_cast<uint16_t*>(b->tc_ws + o_xn); b->tc_att = reinterpret_cast<uint16_t*>(b->tc_ws + o_att);
+        b->tc_s = reinterpret_cast<uint16_t*>(b->tc_ws + o_s); b->tc_qkv = reinterpret_cast<float*>(b->tc_ws + o_qkv);
+        b->tc_ug = reinterpret_cast<float*>(b->tc_ws + o_ug);
+        b->tc_pf = pf_cache_create();
+    }
+    for (cudaGraphExec_t& g : b->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }   // graphs captured in the other mode
+    std::fill(b->warmed.begin(), b->warmed.end(), 0);
+    b->tc = true;
     return SLLM_OK;
 }
 

@@ -49,6 +49,8 @@ struct PfDev {           // kernel-side view of PfGemmArgs
                           // the residual stream with red.global.add — fills the machine when a GEMM has fewer tiles than SM pairs
     int32_t nkb, kb_per_seg, seg_elems, R, tiled;
     int32_t epilogue;
+    int32_t a_rows;       // rows of A one CTA stages per k-block: 128, or (one-SM kernel, T < 128) T rounded up to the 8-row swizzle period —
+                          // the rest of the 128-row operand tile is never loaded (its accumulator rows are never stored)
     float* out; int32_t ld_out, n_valid;
     uint16_t* q_out; uint8_t *kc, *vc; int32_t kv_dtype, q_loc, kv_loc, hd, S, pos0;
     const float *sin_t, *cos_t;
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
     const int BN = p.BN;
     const int b_rows = PAIR ? BN / 2 : BN;                 // W rows staged by one CTA
     const uint32_t b_bytes = (uint32_t)b_rows * kPfBK * 2, stage_bytes = kPfABytes + b_bytes;
+    const uint32_t tx_bytes = (uint32_t)p.a_rows * kPfBK * 2 + b_bytes;   // bytes the TMA really delivers per stage (a_rows < 128: skinny A)
     const int ST = min((int)(kPfRingBytes / stage_bytes), kPfMaxStages);
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader: issues the MMAs of the pair
     const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -361,13 +364,13 @@ __global__ void __launch_bounds__(kPfThreads, 1) pf_gemm_kernel(const __grid_con
                     uint8_t* b_dst = sB + (size_t)stage * b_bytes;
                     if (PAIR) {
                         // both CTAs' bytes are counted on the LEADER's barrier (it is the leader that issues the MMAs)
-                        if (rank == 0) mb_expect(full + stage, 2 * stage_bytes);
+                        if (rank == 0) mb_expect(full + stage, 2 * tx_bytes);
                         const uint32_t bar = mapa_u32(full + stage, 0);
                         tma_load_2d_pair(a_dst, &tmA, ks * p.seg_elems + kk * kPfBK, row0, bar);
                         if (p.tiled) tma_load_4d_pair(b_dst, &tmB, kk * kPfBK, 0, ks, n0 / p.R, bar);
                         else tma_load_4d_pair(b_dst, &tmB, kk * kPfBK, n0, 0, 0, bar);
                     } else {
-                        mb_expect(full + stage, stage_bytes);
+                        mb_expect(full + stage, tx_bytes);
                         tma_load_2d(a_dst, &tmA, ks * p.seg_elems + kk * kPfBK, row0, full + stage);
                         if (p.tiled) tma_load_4d(b_dst, &tmB, kk * kPfBK, 0, ks, n0 / p.R, full + stage);
                         else tma_load_4d(b_dst, &tmB, kk * kPfBK, n0, 0, 0, full + stage);
@@ -541,7 +544,8 @@ static PfPlan pf_plan(int T, int N, int K, int tiled, int epilogue, int bn_force
             for (int sp = 1; sp <= max_split; ++sp) {
                 if (sp > 1 && pl.nkb / sp < 8) break;   // keep at least 8 k-blocks per work unit
                 const long units = (long)pl.m_tiles * ((N + b - 1) / b) * sp;
-                const double unit_cost = (double)((pl.nkb + sp - 1) / sp) * (kPfBM + (pl.pair ? b / 2 : b)) + 10.0 * b;
+                const int a_rows = (!pl.pair && T < kPfBM) ? (T + 7) / 8 * 8 : kPfBM;   // operand rows a CTA really ingests per k-block
+                const double unit_cost = (double)((pl.nkb + sp - 1) / sp) * (a_rows + (pl.pair ? b / 2 : b)) + 10.0 * b;
                 const double c = (double)((units + workers - 1) / workers) * unit_cost;
                 if (c < best - 1e-9) { best = c; bn = b; ksplit = sp; }
             }
@@ -575,7 +579,8 @@ int pf_gemm(PfCache* cache, const PfGemmArgs& a, cudaStream_t st) {
     {
         const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.T};
         const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
-        const cuuint32_t box[2] = {kPfBK, kPfBM};
+        p.a_rows = (!pair && a.T < kPfBM) ? (a.T + 7) / 8 * 8 : kPfBM;
+        const cuuint32_t box[2] = {kPfBK, (cuuint32_t)p.a_rows};
         if (int rc = encode(&tmA, a.A, 2, dims, strides, box)) return rc;
     }
     const int box_rows = pair ? bn / 2 : bn;   // W rows one CTA stages per k-block

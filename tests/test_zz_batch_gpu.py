@@ -446,3 +446,74 @@ def test_split_down_projection_matches_oracle(port, wd):
         for key in (6, 7):
             lib.sllm_tune(key, 0)
 
+
+
+def _gain1_blob(port, ms, seed):
+    """bf16-exact synthetic blob with every projection scaled by 0.25 (tests/test_prefill_gpu.py::_blob explains why bf16-operand paths
+    are measured on the gain-1 model: on the gain-4 one the operand rounding is amplified chaotically layer by layer)."""
+    sh = oracle_shape(ms)
+    blob = port.fill_blob(sh, seed, BF16)
+    for seg in range(2, 9):
+        off, cnt = port.segment(sh, seg)[:2]
+        blob[off:off + cnt] *= 0.25
+    return blob
+
+
+@pytest.mark.parametrize("kvd", [F32, BF16])
+def test_tensor_core_step_matches_oracle_per_sequence(port, kvd):
+    """sllm_batch_set_tensor_cores: the projections of a step as tcgen05 GEMMs over the live rows. Seven sequences of different lengths,
+    admitted at different steps, each FED its whole token list (so no feedback can hide or amplify an error); after the last fed token
+    the logits of every sequence against the oracle's for that sequence alone within the bf16-operand tolerance (5e-3 of max|logit| on
+    the gain-1 model; the fp32 GEMV path of the same batch is held to 3e-4 and asserted here as the A/B partner), and the K row of layer 0
+    is the same in both modes up to the rounding of its inputs."""
+    ms = ModelShape(2048, 64, 512, 256, 1408, 96, 3, 8, 4)
+    shape = oracle_shape(ms)
+    blob = _gain1_blob(port, ms, 31)
+    rng = np.random.default_rng(12)
+    lens = [40, 17, 33, 5, 28, 40, 11]
+    joins = [0, 0, 2, 9, 9, 20, 30]
+    fed = [rng.integers(1, ms.vocab, size=n, dtype=np.int32) for n in lens]
+    want = []
+    for ids in fed:
+        om = port.model(shape, blob, threads=4, kv_bf16=(kvd == BF16))
+        for p in range(len(ids) - 1):
+            om.step(int(ids[p]), p)
+        want.append(om.forward(int(ids[-1]), len(ids) - 1))
+        om.close()
+    worst = {}
+    for tc in (False, True):
+        eng = Engine(ms, w_dtype=BF16, kv_dtype=kvd).load_blob(blob)
+        bd = BatchDecoder(eng, max_seqs=8, page_len=8, kv_dtype=kvd)
+        if tc:
+            bd.set_tensor_cores(True)
+        slots, done = {}, {}
+        for step in range(max(j + n for j, n in zip(joins, lens))):
+            for i, j in enumerate(joins):
+                if j == step:
+                    slots[i] = bd.add(fed[i])
+            bd.step(1)
+            for i, s in slots.items():
+                if i not in done and bd.position(s) == lens[i]:     # the step that consumed the last fed token
+                    done[i] = bd.logits(s).copy()
+                    assert np.array_equal(bd.tokens(s)[:-1], fed[i][1:]), i
+                    bd.remove(s)
+            slots = {i: s for i, s in slots.items() if i not in done}
+        assert len(done) == len(fed)
+        errs = [float(np.abs(done[i] - want[i]).max()) / max(1.0, float(np.abs(want[i]).max())) for i in range(len(fed))]
+        worst[tc] = max(errs)
+        for i, e in enumerate(errs):
+            assert e <= (5e-3 if tc else (3e-4 if kvd == F32 else 5e-3)), (tc, i, e)
+            srt = np.sort(want[i])
+            if srt[-1] - srt[-2] > 4 * e * max(1.0, float(np.abs(want[i]).max())):
+                assert int(np.argmax(done[i])) == int(np.argmax(want[i])), (tc, i)
+        bd.close(); eng.close()
+    print(f"\nbatched decode, {len(fed)} ragged sequences, kv={'f32' if kvd == F32 else 'bf16'}: max|dlogit|/max|logit| GEMV path {worst[False]:.1e}, tensor-core path {worst[True]:.1e}")
+
+
+def test_tensor_core_step_refuses_other_weight_types():
+    eng = Engine(PRESETS["tiny_gqa"], w_dtype=F32, kv_dtype=F32).load_synthetic(3)
+    bd = BatchDecoder(eng, max_seqs=2, page_len=8, kv_dtype=F32)
+    with pytest.raises(_lib.SllmError) as ei:
+        bd.set_tensor_cores(True)
+    assert ei.value.code == _lib.ENOTSUP
+    bd.close(); eng.close()

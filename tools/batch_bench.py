@@ -27,6 +27,8 @@ VARIANTS = {   # name -> sllm_tune keys switched on (5 graph replay, 6 four-row 
     "graph": (5,),
     "graph+rows4": (5, 6),
     "graph+rows4+ksplit": (5, 6, 7),
+    "tc": ("tc",),              # sllm_batch_set_tensor_cores: the projections as tcgen05 GEMMs over the live rows (bf16 operands)
+    "tc+graph": ("tc", 5),
 }
 
 
@@ -37,6 +39,9 @@ def main():
     ap.add_argument("--kvdtype", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--batches", default="1,2,4,8,16", help="sequence counts for the plain variant")
     ap.add_argument("--exp-batches", default="8,16", help="sequence counts for the experimental variants")
+    ap.add_argument("--tc-batches", default="8,16,32,64", help="sequence counts for the tensor-core variants")
+    ap.add_argument("--pf-bn", type=int, default=0, help="force the N tile of the tensor-core GEMMs (sllm_tune key 1; 0 = planner)")
+    ap.add_argument("--pf-ksplit", type=int, default=-1, help="force the K split of the residual GEMMs (sllm_tune key 4; -1 = planner)")
     ap.add_argument("--variants", default="plain", help="comma list out of: " + ", ".join(VARIANTS))
     ap.add_argument("--context", type=int, default=512)
     ap.add_argument("--steps", type=int, default=64)
@@ -72,13 +77,19 @@ def main():
     torch.cuda.set_stream(stream)
     eng = Engine(ms, w_dtype=wd, kv_dtype=kvd, stream=stream).load_synthetic(1234)
     lib = _lib.load()
+    if args.pf_bn:
+        _lib.check(lib.sllm_tune(1, args.pf_bn))
+    if args.pf_ksplit >= 0:
+        _lib.check(lib.sllm_tune(4, args.pf_ksplit))
     def run_variant(v):
         for key in (5, 6, 7):
             _lib.check(lib.sllm_tune(key, 1 if key in VARIANTS[v] else 0))
         rng = np.random.default_rng(1)
         rows = []
-        for B in [int(b) for b in (args.batches if v == "plain" else args.exp_batches).split(",")]:
+        for B in [int(b) for b in (args.batches if v == "plain" else args.tc_batches if "tc" in VARIANTS[v] else args.exp_batches).split(",")]:
             bd = BatchDecoder(eng, max_seqs=B, page_len=args.page_len, kv_dtype=kvd)
+            if "tc" in VARIANTS[v]:
+                bd.set_tensor_cores(True)
             for _ in range(B):
                 bd.add([int(rng.integers(1, ms.vocab))])
             bd.step(args.context)                      # untimed: fills every sequence's pages up to the context
@@ -104,7 +115,7 @@ def main():
                       f"({100 * r['frac_of_hbm_peak']:.1f} % of {peak:.0f})  {r['kernels_per_step']:.0f} kernels/step", flush=True)
             bd.close()
         if args.json:
-            print(json.dumps({"variant": v, "tune_keys_on": list(VARIANTS[v]),
+            print(json.dumps({"variant": v, "tune_keys_on": list(VARIANTS[v]), "pf_bn": args.pf_bn, "pf_ksplit": args.pf_ksplit,
                               "what": f"sllm_batch_step: {args.config}-shaped, {args.wdtype} weights, {args.kvdtype} cache pages of {args.page_len}, every sequence at "
                                       f"positions {args.context}..{args.context + args.steps - 1}; aggregate tokens/s over the sequences; algorithmic bytes = weights "
                                       "once per step + each sequence's K/V rows",

@@ -25,6 +25,9 @@ for s in "$@"; do
                step 200 mega_trace_tiny_v1 python tools/mega_trace.py --config tinyllama-1.1b --layers 22 --pos 1700
                step 200 mega_trace_110m_v2 python tools/mega_trace.py --config stories110M --wdtype f32 --kvdtype f32 --layers 12 --pos 128 --v2 ;;
     widetests) step 600 widetests python -m pytest tests/test_engine_gpu.py -q -x -k "wide_heads or int8 or medium" ;;
+    tcbatch)   step 600 tcbatch_tests python -m pytest tests/test_zz_batch_gpu.py -q -x -s -k "tensor_core"
+               step 600 batch_bench_tc python tools/batch_bench.py --variants tc,tc+graph --tc-batches 8,16,32,64 --json ;;
+    pftests)   step 900 pftests python -m pytest tests/test_prefill_gpu.py -q -x ;;
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
