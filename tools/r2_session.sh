@@ -28,6 +28,8 @@ for s in "$@"; do
     tcbatch)   step 600 tcbatch_tests python -m pytest tests/test_zz_batch_gpu.py -q -x -s -k "tensor_core"
                step 600 batch_bench_tc python tools/batch_bench.py --variants tc,tc+graph --tc-batches 8,16,32,64 --json ;;
     pftests)   step 900 pftests python -m pytest tests/test_prefill_gpu.py -q -x ;;
+    batchtests) step 900 batchtests python -m pytest tests/test_zz_batch_gpu.py -q -x ;;
+    tcbench)   step 600 batch_bench_tc python tools/batch_bench.py --variants tc+graph --tc-batches 8,16,32,64 --json ;;
     caltest)   step 300 caltest python -m pytest tests/test_engine_gpu.py -q -k "calibrated" ;;
     debug_v2)  step 240 mega_debug_v2 python tools/mega_debug.py --v2 ;;
     sweep)     step 400 mega_sweep python tools/mega_sweep.py ;;
