@@ -81,7 +81,8 @@ def pages_that_fit(shape, max_seqs: int, page_len: int, hbm_bytes: int, kv_dtype
 class BatchDecoder:
     """Up to ``max_seqs`` sequences stepping together over the weights of ``engine`` (one GPU, not a megakernel engine)."""
 
-    def __init__(self, engine: Engine, max_seqs: int, page_len: int = 64, n_pages: int | None = None, kv_dtype: int = BF16):
+    def __init__(self, engine: Engine, max_seqs: int, page_len: int = 64, n_pages: int | None = None, kv_dtype: int = BF16,
+                 tensor_cores: bool = False):
         self.lib = _lib.load()
         self.engine = engine   # keeps the weights alive
         if n_pages is None:    # enough for every slot to reach the engine's max_len ...
@@ -99,6 +100,8 @@ class BatchDecoder:
         self.h = h
         self.max_seqs, self.page_len, self.n_pages, self.kv_dtype = max_seqs, page_len, n_pages, kv_dtype
         self.max_len = engine.shape.max_len   # positions one sequence can reach (sllm_batch_step refuses to go past it)
+        if tensor_cores:
+            self.set_tensor_cores(True)
 
     def add(self, prompt) -> int:
         prompt = np.ascontiguousarray(prompt, dtype=np.int32)
