@@ -1,6 +1,7 @@
 """Batched multi-sequence decode over a paged KV cache: Python face of sllm_batch_* / sllm_kvpages_*
 (include/sllm_b200.h). Additive to the reference, which decodes one sequence at a time (include/model/model.h:15-18,
-source/model/model.cpp:148-185); every sequence of a batch follows the semantics of ``Engine.greedy``."""
+source/model/model.cpp:148-185); every sequence of a batch follows the semantics of ``Engine.greedy`` — token for token with the default
+fp32-activation step; within the bf16-operand tolerance of the prefill with the opt-in tensor-core step (``set_tensor_cores``)."""
 from __future__ import annotations
 
 import ctypes as C

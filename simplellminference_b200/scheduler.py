@@ -5,6 +5,8 @@ Additive to the reference, whose ``predict`` (source/model/model.cpp:142-187) se
 is decoded exactly as ``predict`` would decode it alone — prompt echo, then first-max arg-max feedback — so its result
 does not depend on what else is in flight (that is the parity property ``tests/test_zz_batch_gpu.py`` checks); the
 scheduler only decides WHEN a request runs. Optional EOS stop like ``predict.predict_ids`` (the reference never stops).
+That contract is the default fp32-activation decoder's; a decoder switched to the tensor-core step (``BatchDecoder(tensor_cores=True)``)
+rounds activations to bf16 as GEMM operands: same independence of the neighbours, results within the bf16-operand tolerance instead.
 
 Admission rule (no preemption, so it must be deadlock-free): a request is admitted only if the free pages cover its whole
 life (prompt + new tokens) on top of what the requests already in flight may still take. Steps are enqueued in chunks:
