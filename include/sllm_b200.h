@@ -213,7 +213,9 @@ int sllm_engine_p2p_import(sllm_engine* e, const void* all_handles /* tp_size * 
    block and imports everybody's (same messenger protocol as above). From then on sllm_engine_prefill sums the row-parallel partial
    matrices, adds the residual, normalises and distributes the rows in one kernel over NVLink peer memory (csrc/prefill_tp.cu).
    SLLM_ENOTSUP: the engine has no such block (one rank, no SLLM_ENGINE_P2P_ALLREDUCE, shape not taken by the batched prefill) — prefill
-   then needs the NCCL communicator. Replaces nothing in the reference (it has neither prefill nor a working multi-GPU build). */
+   then needs the NCCL communicator. Every rank must issue the same sequence of sllm_engine_prefill calls (the exchange kernels wait for each
+   other's epoch flags; a wait that is never answered traps after ~20 s instead of hanging the GPU): a prefill that failed on one rank only leaves
+   the ranks out of step — destroy the engines. Replaces nothing in the reference (it has neither prefill nor a working multi-GPU build). */
 int sllm_engine_prefill_p2p_export(sllm_engine* e, void* handle_bytes_64);
 int sllm_engine_prefill_p2p_import(sllm_engine* e, const void* all_handles /* tp_size * 64 bytes */);
 
