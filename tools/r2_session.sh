@@ -61,6 +61,10 @@ for s in "$@"; do
                step 120 ncu_pf_plain $PB
                step 600 ncu_pf_gemm ncu --set full --clock-control none --import-source on -k regex:pf_gemm_kernel -s 300 -c 8 -o "$OUT/r02_pf_gemm" -f $PB
                step 400 ncu_pf_attn ncu --set full --clock-control none --import-source on -k regex:pf_attn_kernel -s 40 -c 2 -o "$OUT/r02_pf_attn" -f $PB ;;
+    ncu_tc)    TB="python tools/batch_bench.py --variants tc --tc-batches 16 --context 520 --steps 2 --json"
+               step 300 ncu_tc_plain $TB
+               step 600 ncu_tc_gemm ncu --set full --clock-control none --import-source on -k regex:pf_gemm_kernel -s 66800 -c 8 -o "$OUT/r02_tc_gemm" -f $TB
+               step 600 ncu_tc_mha ncu --set full --clock-control none --import-source on -k regex:mha_paged -s 16660 -c 2 -o "$OUT/r02_tc_mha" -f $TB ;;
     smoke)     step 600 smoke python -c 'import __graft_entry__ as g; g.smoke(); print("__SMOKE_OK__")' ;;
     bench_ref) step 600 bench_ref python bench.py --impl reference --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_ref.log" | tail -1 > "$OUT/bench_ref.json" ;;
     bench_drv) step 600 bench_drv python bench.py --gpus 1 --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_drv.log" | tail -1 > "$OUT/bench_drv.json" ;;
