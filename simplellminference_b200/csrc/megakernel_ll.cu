@@ -24,6 +24,11 @@
 
 #include "mega_common.cuh"
 
+#ifndef SLLM_LL_KNS
+#define SLLM_LL_KNS 2   // attention splits in flight per polling round trip of the wo prologue's merge. A/B on one 2-GPU box (make EXTRA=-DSLLM_LL_KNS=3):
+                        // 3 in flight = one round trip less per layer but 60 more bytes of spills in the streaming loop: 481.8 vs 506.1 tok/s
+#endif
+
 namespace sllm {
 
 struct MegaLLSmem {
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
                 const int col = c4 * 4;
                 const int head = col / p.hd, j = col - head * p.hd;
                 const uint2* base = my_area + p.off_att + (int64_t)head * nsplit * rec;
-                constexpr int kNS = 2;
+                constexpr int kNS = SLLM_LL_KNS;
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int s_end = min(nsplit, (pt + 1) * blk);
                 for (int s0 = pt * blk; s0 < s_end; s0 += kNS) {

@@ -8,8 +8,20 @@ ap = argparse.ArgumentParser(); ap.add_argument("--layers", type=int, default=4)
 ap.add_argument("--config", default="llama2-7b"); ap.add_argument("--wdtype", default="bf16"); ap.add_argument("--kvdtype", default="bf16")
 a = ap.parse_args()
 ms = dataclasses.replace(PRESETS[a.config], layers=a.layers)
+# under torchrun (WORLD_SIZE > 1): the tensor-parallel word-based kernel, one rank per GPU; rank 0 prints its own timeline
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-eng = Engine(ms, w_dtype={'bf16': BF16, 'f32': F32}[a.wdtype], kv_dtype={'bf16': BF16, 'f32': F32}[a.kvdtype], stream=stream, mega=True, mega_ll=a.ll, mega_fuse_down=a.fuse_down, mega_v2=a.v2).load_synthetic(1)
+eng = Engine(ms, w_dtype={'bf16': BF16, 'f32': F32}[a.wdtype], kv_dtype={'bf16': BF16, 'f32': F32}[a.kvdtype], stream=stream, mega=True, mega_ll=a.ll, mega_fuse_down=a.fuse_down, mega_v2=a.v2,
+             tp_rank=rank, tp_size=world, p2p_allreduce=(world > 1)).load_synthetic(1)
+if world > 1:
+    eng.init_p2p(dist)
+    a.ll = True   # the only megakernel under tensor parallelism
 if a.calibrate: eng.calibrate(3)
 print("mode:", eng.mode, "calibrated" if a.calibrate else "")
 eng.set_state(1, a.pos); eng.enqueue_steps(3); torch.cuda.synchronize()
@@ -57,4 +69,6 @@ print("slowest CTAs (cta, smid, relative time):", [(int(c), int(smid[c]), round(
 print("fastest CTAs:", [(int(c), int(smid[c]), round(float(allm[c]), 3)) for c in order[:10]])
 print("relative time by smid parity / half:", {"smid<74": round(float(allm[smid < 74].mean()), 4), "smid>=74": round(float(allm[smid >= 74].mean()), 4),
       "even": round(float(allm[smid % 2 == 0].mean()), 4), "odd": round(float(allm[smid % 2 == 1].mean()), 4)})
-np.save("gpurun_out/mega_rel_time.npy", np.stack([smid.astype(np.float64), allm], 1)) if os.path.isdir("gpurun_out") else None
+np.save("gpurun_out/mega_rel_time.npy", np.stack([smid.astype(np.float64), allm], 1)) if (os.path.isdir("gpurun_out") and rank == 0) else None
+if world > 1:
+    torch.cuda.synchronize(); dist.barrier(); eng.close(); dist.destroy_process_group()

@@ -65,6 +65,7 @@ for s in "$@"; do
                step 300 ncu_tc_plain $TB
                step 600 ncu_tc_gemm ncu --set full --clock-control none --import-source on -k regex:pf_gemm_kernel -s 66800 -c 8 -o "$OUT/r02_tc_gemm" -f $TB
                step 600 ncu_tc_mha ncu --set full --clock-control none --import-source on -k regex:mha_paged -s 16660 -c 2 -o "$OUT/r02_tc_mha" -f $TB ;;
+    trace_tp*) n=${s#trace_tp}; step 300 "mega_trace_ll_tp${n}" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29800 + n)) tools/mega_trace.py --ll --layers 8 ;;
     smoke)     step 600 smoke python -c 'import __graft_entry__ as g; g.smoke(); print("__SMOKE_OK__")' ;;
     bench_ref) step 600 bench_ref python bench.py --impl reference --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_ref.log" | tail -1 > "$OUT/bench_ref.json" ;;
     bench_drv) step 600 bench_drv python bench.py --gpus 1 --steps 20 --warmup 5; grep -h '^{' "$OUT/bench_drv.log" | tail -1 > "$OUT/bench_drv.json" ;;
