@@ -24,6 +24,9 @@
 
 #include "mega_common.cuh"
 
+#ifndef SLLM_LL_SPLIT_ROWS
+#define SLLM_LL_SPLIT_ROWS 128   // cache rows per attention split. A/B at 2 ranks on one box: 128 -> 505.8, 160 -> 498.1, 200 -> 500.4 tok/s
+#endif
 #ifndef SLLM_LL_KNS
 #define SLLM_LL_KNS 2   // attention splits in flight per polling round trip of the wo prologue's merge. A/B on one 2-GPU box (make EXTRA=-DSLLM_LL_KNS=3):
                         // 3 in flight = one round trip less per layer but 60 more bytes of spills in the streaming loop: 481.8 vs 506.1 tok/s
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_ll_kernel(const MegaLLPa
     // attention splits actually used at this position: ~128 cache rows per split (every split costs the wo prologue two
     // polling round trips in the merge, so 32 splits of 16 rows — what a tensor-parallel rank with 4 KV heads would get —
     // are far slower than 5 splits of 128). Same value in every CTA of every rank.
-    const int nsplit = min(p.nsplit, max(1, (pos + 1 + 127) / 128));
+    const int nsplit = min(p.nsplit, max(1, (pos + 1 + SLLM_LL_SPLIT_ROWS - 1) / SLLM_LL_SPLIT_ROWS));
     const unsigned ebase = (unsigned)p.st->pad[1] * (unsigned)(p.L + 2) + 1u;   // epoch of layer l = ebase + l
     uint2* const my_area = p.area[p.rank];
 
