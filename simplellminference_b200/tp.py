@@ -52,3 +52,11 @@ def merge_argmax(pairs):
         if v > best_v or (v == best_v and i < best_i):
             best_v, best_i = v, i
     return best_i
+
+
+def prefill_rows(n_rows: int, size: int, rank: int) -> tuple[int, int]:
+    """Prompt rows [lo, hi) that `rank` owns in the tensor-parallel prefill exchange (csrc/prefill_tp.cu): blocks of
+    ceil(n_rows / size) rows in rank order; the last ranks may own fewer rows, or none."""
+    per = (n_rows + size - 1) // size
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
